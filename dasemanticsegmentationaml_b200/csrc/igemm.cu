@@ -1,0 +1,645 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a.
+//
+//   conv_igemm_kernel  : forward conv and data-gradient (any filter, stride 1/2, zero padding).
+//                        A = 128 output pixels x KC channels, fetched per filter tap by ONE 4-D
+//                        tiled TMA box over the NHWC activation tensor (out-of-bounds -> zero =
+//                        the conv's padding; elementStrides = the conv's stride).
+//                        B = BN output channels x KC, 2-D TMA over the packed K-major filter.
+//                        D = 128 x BN fp32 in TMEM.  Epilogue: bias, ReLU/LeakyReLU, per-channel
+//                        sum / sum-of-squares for train-mode BatchNorm, bf16 or fp32 NHWC store.
+//   wgrad_igemm_kernel : weight gradient.  Both operands are MN-major (channels contiguous, the
+//                        GEMM K extent is the pixel index), again plain NHWC TMA boxes.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include "igemm.cuh"
+#include "ptx.cuh"
+#include "status.h"
+
+namespace b200 {
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct PipeBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t accum;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with a halving butterfly (16 shuffles).
+// On return lane L holds in `v[0]` the total of column  col_of_lane(L) (see below); both lanes of
+// an (even, odd) pair hold the same column.
+__device__ __forceinline__ float column_sums16(float (&v)[16], int lane) {
+  // stage 0: xor 16, keep 8
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bool hi = lane & 16;
+    float send = hi ? v[j] : v[j + 8];
+    float keep = hi ? v[j + 8] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bool hi = lane & 8;
+    float send = hi ? v[j] : v[j + 4];
+    float keep = hi ? v[j + 4] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    bool hi = lane & 4;
+    float send = hi ? v[j] : v[j + 2];
+    float keep = hi ? v[j + 2] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    bool hi = lane & 2;
+    float send = hi ? v[0] : v[1];
+    float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+// column (0..15) whose total a lane holds after column_sums16
+__device__ __forceinline__ int column_of_lane(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PipeBarriers bars;
+  __shared__ float s_stats[2][256];
+
+  const int z = blockIdx.z;
+  const int tiles_per_img = p.tiles_h[z] * p.tiles_w[z];
+  if ((int)blockIdx.x >= tiles_per_img * p.n_img) return;  // class with a smaller sub-grid
+  const int n_img = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - n_img * tiles_per_img;
+  const int h0 = (t_in / p.tiles_w[z]) * p.th;
+  const int w0 = (t_in % p.tiles_w[z]) * p.tw;
+  const int n0 = blockIdx.y * p.BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 128u * p.KC * 2u;
+  const uint32_t b_bytes = (uint32_t)p.BN * p.KC * 2u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;  // both multiples of 1024
+  const int cin_blocks = p.cin_pad / p.KC;
+  const int nk = p.n_taps[z] * cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), 1);
+      mbar_init(smem_u32(&bars.empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars.accum), 1);
+    fence_mbar_init();
+  }
+  if (p.stats != nullptr) {
+    for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars.tmem_base), p.BN < 32 ? 32 : p.BN);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < p.n_taps[z]; ++t) {
+        const int hh = h0 * p.in_stride + p.tap_dh[z][t];
+        const int ww = w0 * p.in_stride + p.tap_dw[z][t];
+        const int kb = p.tap_k[z][t] * p.cin_pad;
+        for (int cb = 0; cb < cin_blocks; ++cb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&bars.full[s]);
+          mbar_expect_tx(full, stage_bytes);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          tma_load_4d(sa, &tmA, full, cb * p.KC, ww, hh, n_img);
+          tma_load_2d(sa + a_bytes, &tmB, full, kb + cb * p.KC, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t layout = (p.KC == 64) ? 2u : 4u;  // 128B / 64B swizzle
+      const uint32_t sbo = 8u * p.KC * 2u;              // 8 rows of KC bf16
+      const int ksteps = p.KC / 16;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&bars.full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, layout);
+          const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
+          umma_f16(tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars.empty[s]));  // frees the stage once these MMAs retire
+      }
+      umma_commit(smem_u32(&bars.accum));
+    }
+  } else {
+    // ----------------------------------------------------------------- epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int hl = row / p.tw, wl = row - hl * p.tw;
+    const int h = h0 + hl, w = w0 + wl;
+    const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+    const size_t pix =
+        ((size_t)n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
+    const size_t obase = pix * p.out_ld + p.out_coff + n0;
+
+    mbar_wait(smem_u32(&bars.accum), 0);
+    tc_fence_after();
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(r[j]);
+        if (p.bias != nullptr) x += __ldg(p.bias + n0 + c + j);
+        v[j] = apply_act(x, p.act, p.slope);
+      }
+      if (valid) {
+        if (p.out_f32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c);
+          o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                            pack_bf16(v[6], v[7]));
+          o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        }
+      }
+      if (p.stats != nullptr) {
+        float s1[16], s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          // statistics of the values as stored (bf16-rounded), so mean/var describe the tensor
+          // the normalisation pass will read
+          float x = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]))) : 0.f;
+          s1[j] = x;
+          s2[j] = x * x;
+        }
+        const float t1 = column_sums16(s1, lane);
+        const float t2 = column_sums16(s2, lane);
+        if ((lane & 1) == 0) {
+          const int col = c + column_of_lane(lane);
+          atomicAdd(&s_stats[0][col], t1);
+          atomicAdd(&s_stats[1][col], t2);
+        }
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      const int t = threadIdx.x - 64;
+      for (int col = t; col < p.BN; col += 128) {
+        atomicAdd(p.stats + n0 + col, s_stats[0][col]);
+        atomicAdd(p.stats + p.stats_ld + n0 + col, s_stats[1][col]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, p.BN < 32 ? 32 : p.BN);
+  }
+}
+
+// ------------------------------------------------------------------------ wgrad
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PipeBarriers bars;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // blockIdx.y = (tap, co_tile, ci_tile)
+  int y = blockIdx.y;
+  const int ci_t = y % p.ci_tiles;
+  y /= p.ci_tiles;
+  const int co_t = y % p.co_tiles;
+  const int tap = y / p.co_tiles;
+  const int co0 = co_t * 128, ci0 = ci_t * p.BNW;
+
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int total_tiles = tiles_per_img * p.n_img;
+  const int per_split = (total_tiles + p.splits - 1) / p.splits;
+  const int tile_begin = blockIdx.x * per_split;
+  const int tile_end = min(total_tiles, tile_begin + per_split);
+  const int nk = tile_end - tile_begin;
+  if (nk <= 0) return;
+
+  const int kpix = p.th * p.tw;                       // 64 or 128
+  const uint32_t box_bytes = (uint32_t)kpix * 128u;   // [kpix][64 ch] bf16
+  const int n_bbox = p.BNW / 64;
+  const uint32_t a_bytes = 2u * box_bytes;
+  const uint32_t stage_bytes = a_bytes + n_bbox * box_bytes;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), 1);
+      mbar_init(smem_u32(&bars.empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bars.accum), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars.tmem_base), p.BNW > 128 ? 256 : p.BNW);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDZ);
+    tma_prefetch_desc(&tmX);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+      for (int it = 0; it < nk; ++it) {
+        const int tile = tile_begin + it;
+        const int n_img = tile / tiles_per_img;
+        const int t_in = tile - n_img * tiles_per_img;
+        const int h0 = (t_in / p.tiles_w) * p.th;
+        const int w0 = (t_in % p.tiles_w) * p.tw;
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bars.full[s]);
+        mbar_expect_tx(full, stage_bytes);
+        const uint32_t sa = smem_base + s * stage_bytes;
+        tma_load_4d(sa, &tmDZ, full, co0, w0, h0, n_img);
+        tma_load_4d(sa + box_bytes, &tmDZ, full, co0 + 64, w0, h0, n_img);
+        for (int b = 0; b < n_bbox; ++b)
+          tma_load_4d(sa + a_bytes + b * box_bytes, &tmX, full, ci0 + b * 64,
+                      w0 * p.in_stride + dw, h0 * p.in_stride + dh, n_img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BNW, 1, 1);
+      const int ksteps = kpix / 16;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&bars.full[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+        for (int k = 0; k < ksteps; ++k) {
+          // MN-major, 128B swizzle: 64 channels contiguous, 8-pixel groups 1024 B apart (SBO),
+          // 64-channel groups one TMA box apart (LBO); a K step of 16 pixels = 2048 B.
+          const uint64_t da = make_smem_desc(sa + k * 2048, box_bytes, 1024, 2);
+          const uint64_t db = make_smem_desc(sb + k * 2048, box_bytes, 1024, 2);
+          umma_f16(tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars.empty[s]));
+      }
+      umma_commit(smem_u32(&bars.accum));
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(smem_u32(&bars.accum), 0);
+    tc_fence_after();
+    const int rs = p.tap_rs[tap];
+    for (int c = 0; c < p.BNW; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      if (co < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ci = ci0 + c + j;
+          if (ci < p.Cin)
+            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.RS + rs, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, p.BNW > 128 ? 256 : p.BNW);
+  }
+}
+
+// --------------------------------------------------------- filter repacking
+// PyTorch [Cout][Cin][RS] fp32  ->  bf16 [rows_pad][RS][inner_pad] (zero padded), with
+// (rows, inner) = (Cout, Cin) for forward or (Cin, Cout) for the data gradient.
+__global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                   int Cout, int Cin, int RS, int rows_pad, int inner_pad,
+                                   int transpose) {
+  const size_t total = (size_t)rows_pad * RS * inner_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int inner = i % inner_pad;
+    const int t = (i / inner_pad) % RS;
+    const int row = i / ((size_t)inner_pad * RS);
+    const int co = transpose ? inner : row;
+    const int ci = transpose ? row : inner;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * RS + t];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------ host launchers
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation view: channels [coff, coff+C) of a tensor whose pixels are `ld` apart.
+static int make_act_map(CUtensorMap* m, const void* base, int coff, int C, int ld, int N, int H,
+                        int W, int box_c, int box_w, int box_h, int stride, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_32B;
+  void* addr = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(base) + coff));
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  return B200_OK;
+}
+
+static int make_filter_map(CUtensorMap* m, const void* base, int rows, int ktot, int box_k,
+                           int box_rows, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled(filter) failed: %d", (int)r);
+  return B200_OK;
+}
+
+static void pick_patch(int Wo, int* th, int* tw, int pixels) {
+  // widest power-of-two patch row that does not overshoot the map width by more than it must
+  int w = 8;
+  while (w < pixels && w < Wo) w <<= 1;
+  if (w > pixels) w = pixels;
+  // keep patches at most 64 wide so that stride-2 boxes stay within the 256-element TMA limit
+  if (w > 64) w = 64;
+  *tw = w;
+  *th = pixels / w;
+}
+
+static int pick_bn(int cout_pad, int m_tiles) {
+  // largest N tile (dividing cout_pad) that still gives every SM a CTA; failing that the
+  // smallest candidate, which maximises the CTA count
+  const int cands[5] = {256, 128, 64, 32, 16};
+  int smallest = 0;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    if (cout_pad % bn) continue;
+    if ((long)m_tiles * (cout_pad / bn) >= 148) return bn;
+    if (bn >= 32 || smallest == 0) smallest = bn;
+  }
+  return smallest;
+}
+
+// Pipeline depth: prefer <= 110 KB so that two CTAs share an SM (one's epilogue overlaps the
+// other's main loop); fall back to the whole 190 KB for the widest tiles.
+static int pick_stages(int stage_bytes, int nk) {
+  int s = (110 * 1024) / stage_bytes;
+  if (s < 3) s = (190 * 1024) / stage_bytes;
+  if (s > kMaxStages) s = kMaxStages;
+  if (s > nk) s = nk < 2 ? 2 : nk;
+  return s;
+}
+
+static int g_smem_optin_done = 0;
+static int ensure_smem_optin() {
+  if (g_smem_optin_done) return B200_OK;
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return set_error(B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  g_smem_optin_done = 1;
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_pack_filter(const float* w, void* out_bf16, int Cout, int Cin, int RS, int rows_pad,
+                     int inner_pad, int transpose, cudaStream_t stream) {
+  const size_t total = (size_t)rows_pad * RS * inner_pad;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  pack_filter_kernel<<<blocks, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out_bf16), Cout, Cin,
+                                                 RS, rows_pad, inner_pad, transpose);
+  return check_launch("pack_filter");
+}
+
+// Generic implicit-GEMM launch.  `taps` is [n_classes][n_taps_max][3] = (dh, dw, k-slab).
+int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int Hin, int Win,
+                    const void* filt, int filt_rows, int cin_pad, int n_slabs,
+                    void* out, int out_ld, int out_coff, int Hout, int Wout, int out_f32,
+                    int n_classes, const int* class_Ho, const int* class_Wo, const int* class_oa,
+                    const int* class_ob, const int* class_ntaps, const int* taps, int taps_stride,
+                    int in_stride, int out_stride, const float* bias, int act, float slope,
+                    float* stats, int stats_ld, int bn_override, cudaStream_t stream) {
+  if (n_classes < 1 || n_classes > kMaxClasses) return set_error(B200_EINVAL, "conv_igemm: bad class count %d", n_classes);
+  if (cin_pad % 32) return set_error(B200_EINVAL, "conv_igemm: cin_pad %d not a multiple of 32", cin_pad);
+  if (in_ld % 8 || in_coff % 8 || out_ld % 8 || out_coff % 8)
+    return set_error(B200_EINVAL, "conv_igemm: channel strides/offsets must be multiples of 8");
+  if (filt_rows % 16) return set_error(B200_EINVAL, "conv_igemm: filter rows %d not a multiple of 16", filt_rows);
+  int rc = ensure_smem_optin();
+  if (rc) return rc;
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.KC = (cin_pad % 64 == 0) ? 64 : 32;
+  int max_wo = 0;
+  for (int z = 0; z < n_classes; ++z) max_wo = class_Wo[z] > max_wo ? class_Wo[z] : max_wo;
+  pick_patch(max_wo, &p.th, &p.tw, 128);
+  int max_tiles = 0;
+  for (int z = 0; z < n_classes; ++z) {
+    p.Ho[z] = class_Ho[z];
+    p.Wo[z] = class_Wo[z];
+    p.tiles_h[z] = (class_Ho[z] + p.th - 1) / p.th;
+    p.tiles_w[z] = (class_Wo[z] + p.tw - 1) / p.tw;
+    p.oa[z] = class_oa[z];
+    p.ob[z] = class_ob[z];
+    p.n_taps[z] = class_ntaps[z];
+    if (class_ntaps[z] > kMaxTaps) return set_error(B200_EINVAL, "conv_igemm: too many taps");
+    for (int t = 0; t < class_ntaps[z]; ++t) {
+      const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
+      p.tap_dh[z][t] = (int8_t)tp[0];
+      p.tap_dw[z][t] = (int8_t)tp[1];
+      p.tap_k[z][t] = (int8_t)tp[2];
+      if (tp[2] < 0 || tp[2] >= n_slabs) return set_error(B200_EINVAL, "conv_igemm: tap slab out of range");
+    }
+    int tiles = p.tiles_h[z] * p.tiles_w[z] * N;
+    max_tiles = tiles > max_tiles ? tiles : max_tiles;
+  }
+  p.n_img = N;
+  p.in_stride = in_stride;
+  p.cin_pad = cin_pad;
+  p.BN = bn_override > 0 ? bn_override : pick_bn(filt_rows, max_tiles);
+  if (filt_rows % p.BN) return set_error(B200_EINVAL, "conv_igemm: BN %d does not divide %d", p.BN, filt_rows);
+  const int stage_bytes = 128 * p.KC * 2 + p.BN * p.KC * 2;
+  int max_nk = 0;
+  for (int z = 0; z < n_classes; ++z) max_nk = class_ntaps[z] > max_nk ? class_ntaps[z] : max_nk;
+  max_nk *= cin_pad / p.KC;
+  p.stages = pick_stages(stage_bytes, max_nk);
+  if (p.stages < 2) return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
+  p.out = out;
+  p.out_ld = out_ld;
+  p.out_coff = out_coff;
+  p.Hout = Hout;
+  p.Wout = Wout;
+  p.os = out_stride;
+  p.bias = bias;
+  p.act = act;
+  p.slope = slope;
+  p.out_f32 = out_f32;
+  p.stats = stats;
+  p.stats_ld = stats_ld;
+
+  CUtensorMap tmA, tmB;
+  rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th, in_stride, p.KC * 2);
+  if (rc) return rc;
+  rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);
+  if (rc) return rc;
+
+  dim3 grid(max_tiles, filt_rows / p.BN, n_classes);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  conv_igemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  return check_launch("conv_igemm");
+}
+
+// dW (fp32, PyTorch [Cout][Cin][RS], pre-zeroed or accumulating) += dz (x) x
+int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int Ho, int Wo,
+                    const void* x, int x_ld, int x_coff, int Cin, int Hin, int Win,
+                    int n_taps, const int* taps /* [n_taps][3] = dh, dw, rs */, int RS,
+                    int in_stride, float* dw, cudaStream_t stream) {
+  if (n_taps < 1 || n_taps > kMaxTaps) return set_error(B200_EINVAL, "conv_wgrad: bad tap count");
+  if (dz_ld % 8 || dz_coff % 8 || x_ld % 8 || x_coff % 8)
+    return set_error(B200_EINVAL, "conv_wgrad: channel strides/offsets must be multiples of 8");
+  int rc = ensure_smem_optin();
+  if (rc) return rc;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  pick_patch(Wo, &p.th, &p.tw, 64);
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.tiles_h = (Ho + p.th - 1) / p.th;
+  p.tiles_w = (Wo + p.tw - 1) / p.tw;
+  p.n_img = N;
+  p.in_stride = in_stride;
+  p.n_taps = n_taps;
+  for (int t = 0; t < n_taps; ++t) {
+    p.tap_dh[t] = (int8_t)taps[3 * t];
+    p.tap_dw[t] = (int8_t)taps[3 * t + 1];
+    p.tap_rs[t] = (int8_t)taps[3 * t + 2];
+  }
+  p.RS = RS;
+  p.Cout = Cout;
+  p.Cin = Cin;
+  p.co_tiles = (Cout + 127) / 128;
+  const int cin64 = ((Cin + 63) / 64) * 64;
+  // ci per CTA: a multiple of 64 (one TMA box each) up to 256 that tiles cin64 with least waste
+  p.BNW = cin64 <= 256 ? cin64 : ((cin64 % 256 == 0) ? 256 : (cin64 % 192 == 0 ? 192 : 128));
+  p.ci_tiles = (cin64 + p.BNW - 1) / p.BNW;
+  const int kpix = p.th * p.tw;
+  const int stage_bytes = (2 + p.BNW / 64) * kpix * 128;
+  const int total_tiles = p.tiles_h * p.tiles_w * N;
+  const int ytiles = n_taps * p.co_tiles * p.ci_tiles;
+  int splits = (148 * 2 + ytiles - 1) / ytiles;  // about two CTAs per SM overall
+  if (splits > total_tiles) splits = total_tiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.stages = pick_stages(stage_bytes, (total_tiles + splits - 1) / splits);
+  p.dw = dw;
+
+  CUtensorMap tmDZ, tmX;
+  rc = make_act_map(&tmDZ, dz, dz_coff, Cout, dz_ld, N, Ho, Wo, 64, p.tw, p.th, 1, 128);
+  if (rc) return rc;
+  rc = make_act_map(&tmX, x, x_coff, Cin, x_ld, N, Hin, Win, 64, p.tw, p.th, in_stride, 128);
+  if (rc) return rc;
+  dim3 grid(splits, ytiles, 1);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  wgrad_igemm_kernel<<<grid, kThreads, smem, stream>>>(tmDZ, tmX, p);
+  return check_launch("conv_wgrad");
+}
+
+}  // extern "C"

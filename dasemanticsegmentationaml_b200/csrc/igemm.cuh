@@ -1,0 +1,62 @@
+// Parameter blocks shared by the tcgen05 implicit-GEMM convolution kernels and their host
+// launchers (igemm.cu).  See DESIGN.md "Dense convolutions" for the data layout.
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kMaxTaps = 16;    // 4x4 discriminator filters
+constexpr int kMaxClasses = 4;  // output-parity classes of a stride-2 dgrad
+
+// One launch = one implicit GEMM  out[pixel, co] = sum_{tap, ci} in[pixel*stride + tap, ci] * w[co, tap, ci].
+// A "class" (blockIdx.z) is a sub-grid of output pixels (used by strided dgrad, where the four
+// output parities see different filter taps); a forward conv has exactly one class.
+struct ConvParams {
+  // output sub-grid iterated by patch tiles, per class
+  int Ho[kMaxClasses], Wo[kMaxClasses];
+  int tiles_h[kMaxClasses], tiles_w[kMaxClasses];
+  int n_taps[kMaxClasses];
+  int8_t tap_dh[kMaxClasses][kMaxTaps];
+  int8_t tap_dw[kMaxClasses][kMaxTaps];
+  int8_t tap_k[kMaxClasses][kMaxTaps];  // index of the tap's K-slab in the packed filter
+  int oa[kMaxClasses], ob[kMaxClasses];  // output pixel offset of the class
+  int n_img;
+  int th, tw;        // patch of th*tw == 128 output pixels per CTA
+  int in_stride;     // traversal stride over the input
+  int cin_pad;       // K elements per tap in the packed filter (multiple of KC)
+  int KC;            // channels per pipeline stage: 64 (128B swizzle) or 32 (64B swizzle)
+  int BN;            // output channels per CTA (16..256, multiple of 16)
+  int stages;
+  // epilogue
+  void* out;
+  int out_ld;        // channel stride of an output pixel (elements)
+  int out_coff;      // first channel written
+  int Hout, Wout;    // full output map
+  int os;            // output pixel stride (2 for strided dgrad, else 1)
+  const float* bias; // nullptr or [>= grid.y*BN]
+  int act;           // 0 none, 1 relu, 2 leaky relu
+  float slope;
+  int out_f32;       // 1: fp32 output, 0: bf16
+  float* stats;      // nullptr, or [2][C] per-channel sum / sum of squares of the fp32 results
+  int stats_ld;      // C
+};
+
+// dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]
+struct WgradParams {
+  int Ho, Wo, tiles_h, tiles_w, n_img;
+  int th, tw;       // th*tw == KPIX pixels (the GEMM K extent) per stage
+  int in_stride;
+  int n_taps;
+  int8_t tap_dh[kMaxTaps];
+  int8_t tap_dw[kMaxTaps];
+  int RS;           // taps in the PyTorch filter (dW is [Cout][Cin][RS])
+  int8_t tap_rs[kMaxTaps];
+  int Cout, Cin;
+  int co_tiles, ci_tiles;
+  int BNW;          // ci per CTA: 64 / 128 / 256
+  int stages;
+  int splits;       // pixel-range splits (gridDim.x)
+  float* dw;        // fp32, PyTorch layout, accumulated atomically
+};
+
+}  // namespace b200

@@ -1,0 +1,134 @@
+"""tcgen05 implicit-GEMM convolution (forward / dgrad / wgrad) against torch fp32 on the same
+bf16-rounded operands.  bf16 products are exact in fp32, so only accumulation order differs:
+tolerance 2e-3 relative L2 for bf16 outputs (one rounding), 1e-4 for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def make_case(n, cin, cout, h, w, r, stride, pad, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    wgt = (torch.randn(cout, cin, r, r, device="cuda", generator=g) / (cin * r * r) ** 0.5)
+    wgt = wgt.to(torch.bfloat16).float()
+    return x, wgt
+
+
+FWD_CASES = [
+    # n, cin, cout, h, w, r, stride, pad
+    (2, 64, 64, 16, 32, 3, 1, 1),
+    (2, 64, 128, 16, 32, 1, 1, 0),
+    (1, 128, 256, 24, 40, 3, 1, 1),
+    (2, 32, 64, 45, 80, 3, 2, 1),
+    (2, 32, 64, 32, 64, 4, 2, 1),
+    (1, 256, 512, 23, 40, 4, 2, 1),
+    (2, 384, 256, 16, 16, 1, 1, 0),
+    (1, 64, 32, 20, 36, 3, 1, 1),
+    (2, 32, 32, 17, 33, 1, 1, 1),   # depthwise-separable discriminator pointwise: k=1, padding=1
+]
+
+
+@pytest.mark.parametrize("case", FWD_CASES)
+def test_conv_forward(cuda_lib, case):
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = case
+    x, wgt = make_case(*case)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wgt, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    filt = K.pack_filter(wgt)
+    geom = K.fwd_geometry(h, w, r, r, stride, pad)
+    out = torch.full((n, geom["Hout"], geom["Wout"], filt.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
+    K.conv_igemm(x, filt, out, geom)
+    torch.cuda.synchronize()
+    assert out.shape[1:3] == ref.shape[1:3]
+    err = rel_l2(out[..., :cout], ref)
+    assert err < 4e-3, err
+
+
+def test_conv_forward_epilogue_and_views(cuda_lib):
+    """bias + LeakyReLU, fp32 output, BN statistics, channel-slice input and output views."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w = 2, 64, 64, 19, 37
+    x, wgt = make_case(n, cin, cout, h, w, 3, 1, 1, seed=3)
+    big_in = torch.zeros(n, h, w, 192, device="cuda", dtype=torch.bfloat16)
+    big_in[..., 64:128] = x
+    bias = torch.randn(64, device="cuda")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wgt, bias=bias, padding=1)
+    ref = F.leaky_relu(ref, 0.2).permute(0, 2, 3, 1)
+    filt = K.pack_filter(wgt)
+    geom = K.fwd_geometry(h, w, 3, 3, 1, 1)
+    big_out = torch.zeros(n, h, w, 128, device="cuda", dtype=torch.float32)
+    stats = torch.zeros(2, 64, device="cuda")
+    K.conv_igemm(big_in[..., 64:128], filt, big_out[..., 64:128], geom, bias=bias, act=2, slope=0.2, stats=stats)
+    torch.cuda.synchronize()
+    assert rel_l2(big_out[..., 64:128], ref) < 1e-4
+    assert big_out[..., :64].abs().max().item() == 0.0
+    flat = ref.reshape(-1, 64)
+    assert rel_l2(stats[0], flat.sum(0)) < 1e-3
+    assert rel_l2(stats[1], (flat * flat).sum(0)) < 1e-3
+
+
+DGRAD_CASES = [
+    (2, 64, 64, 16, 32, 3, 1, 1),
+    (2, 64, 128, 16, 32, 1, 1, 0),
+    (2, 32, 64, 45, 80, 3, 2, 1),
+    (2, 32, 64, 32, 64, 4, 2, 1),
+    (1, 64, 128, 46, 82, 4, 2, 1),
+    (2, 32, 32, 17, 33, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_conv_dgrad(cuda_lib, case):
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = case
+    x, wgt = make_case(*case)
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    y = F.conv2d(xf, wgt, stride=stride, padding=pad)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dz = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+    y.backward(dz.float())
+    ref = xf.grad.permute(0, 2, 3, 1)
+    filt_t = K.pack_filter(wgt, transpose=True)
+    geom = K.dgrad_geometry(h, w, r, r, stride, pad)
+    dz_nhwc = dz.permute(0, 2, 3, 1).contiguous()
+    dx = torch.full((n, h, w, filt_t.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
+    K.conv_igemm(dz_nhwc, filt_t, dx, geom)
+    torch.cuda.synchronize()
+    err = rel_l2(dx[..., :cin], ref)
+    assert err < 4e-3, err
+
+
+WGRAD_CASES = [
+    (2, 64, 64, 16, 32, 3, 1, 1),
+    (2, 64, 128, 16, 32, 1, 1, 0),
+    (2, 128, 256, 24, 40, 3, 1, 1),
+    (2, 32, 64, 45, 80, 3, 2, 1),
+    (2, 32, 64, 32, 64, 4, 2, 1),
+    (1, 384, 256, 16, 16, 1, 1, 0),
+    (2, 32, 32, 17, 33, 1, 1, 1),
+    (2, 64, 32, 20, 36, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_conv_wgrad(cuda_lib, case):
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = case
+    x, wgt = make_case(*case)
+    wf = wgt.clone().requires_grad_(True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wf, stride=stride, padding=pad)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dz = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+    y.backward(dz.float())
+    dz_nhwc = dz.permute(0, 2, 3, 1).contiguous()
+    dw = torch.zeros_like(wgt)
+    K.conv_wgrad(dz_nhwc, x, dw, r, r, stride, pad)
+    torch.cuda.synchronize()
+    err = rel_l2(dw, wf.grad)
+    assert err < 1e-3, err
