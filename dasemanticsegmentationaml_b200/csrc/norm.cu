@@ -1,0 +1,372 @@
+// BatchNorm / activation passes over bf16 NHWC activations (HBM-bound, 16-byte vector accesses).
+//   reference: nn.BatchNorm2d + ReLU in ConvX (model/stdcnet.py:9-14) and ConvBNReLU
+//   (model/model_stages.py:21-29); BatchNorm2d + LeakyReLU(0.2) in DepthWiseSepBNFCDiscriminator
+//   (model/discriminator.py:103-131); LeakyReLU(0.2) after biased convs (discriminator.py:17-26).
+//
+// A "view" is (base pointer, pixel stride ld in elements): channels [0, C) of each of `npix`
+// pixels.  All C are multiples of 8.
+#include <stdint.h>
+
+#include "ptx.cuh"
+#include "status.h"
+
+namespace b200 {
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : v * slope;
+  return v;
+}
+__device__ __forceinline__ float act_grad(float pre, int act, float slope) {
+  if (act == 1) return pre > 0.f ? 1.f : 0.f;
+  if (act == 2) return pre > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// ---------------------------------------------------------------- statistics
+// stats[0][c] += sum x, stats[1][c] += sum x^2 over all pixels.  Block = (C/8) x PY threads; each
+// thread owns 8 channels and strides over pixels; partials are combined in shared memory.
+__global__ void __launch_bounds__(256)
+channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, int C, int64_t npix,
+                     float* __restrict__ stats) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int groups = C >> 3;
+  const int py = blockDim.x / groups;
+  const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float s1[8] = {0}, s2[8] = {0};
+  if (ty < py) {
+    for (int64_t p = (int64_t)blockIdx.x * py + ty; p < npix; p += (int64_t)gridDim.x * py) {
+      float v[8];
+      load8(x + p * ld + g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += v[j];
+        s2[j] += v[j] * v[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[g * 8 + j], s1[j]);
+      atomicAdd(&s_acc[C + g * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], s_acc[i]);
+}
+
+// mean / biased var from (sum, sumsq) -> scale = gamma*rstd, shift = beta - mean*scale; running
+// statistics updated with momentum (unbiased variance), exactly nn.BatchNorm2d's train step.
+// training == 0: scale/shift from the running statistics (eval mode).
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float momentum, float eps, int training,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    mean = stats[c] / count;
+    var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
+    if (running_mean != nullptr) {
+      const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float g = gamma != nullptr ? gamma[c] : 1.f;
+  const float b = beta != nullptr ? beta[c] : 0.f;
+  scale[c] = g * rstd;
+  shift[c] = b - mean * g * rstd;
+  if (mean_out != nullptr) mean_out[c] = mean;
+  if (rstd_out != nullptr) rstd_out[c] = rstd;
+}
+
+// ------------------------------------------------------------- normalise + act
+// y = act(x * scale[c] + shift[c])   (scale == nullptr: plain activation)
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
+                    int y_ld, int C, int64_t npix, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int act, float slope) {
+  const int groups = C >> 3;
+  const int64_t total = npix * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / groups;
+    const int g = (int)(i - p * groups);
+    float v[8];
+    load8(x + p * x_ld + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = v[j];
+      if (scale != nullptr) t = t * __ldg(scale + g * 8 + j) + __ldg(shift + g * 8 + j);
+      v[j] = act_fwd(t, act, slope);
+    }
+    store8(y + p * y_ld + g * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------ backward
+// g = (dy1 + dy2) * act'(z*scale + shift);  xhat = (z - mean) * rstd
+// red[0][c] += sum g (= dbeta), red[1][c] += sum g*xhat (= dgamma)
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
+                         const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
+                         const __nv_bfloat16* __restrict__ z, int z_ld, int C, int64_t npix,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, int act,
+                         float slope, float* __restrict__ red) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int groups = C >> 3;
+  const int py = blockDim.x / groups;
+  const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  if (ty < py) {
+    float sc[8], sh[8], mu[8], rs[8], a1[8] = {0}, a2[8] = {0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale[g * 8 + j];
+      sh[j] = shift[g * 8 + j];
+      mu[j] = mean[g * 8 + j];
+      rs[j] = rstd[g * 8 + j];
+    }
+    for (int64_t p = (int64_t)blockIdx.x * py + ty; p < npix; p += (int64_t)gridDim.x * py) {
+      float d[8], zz[8];
+      load8(dy1 + p * dy1_ld + g * 8, d);
+      if (dy2 != nullptr) {
+        float e[8];
+        load8(dy2 + p * dy2_ld + g * 8, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += e[j];
+      }
+      load8(z + p * z_ld + g * 8, zz);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = d[j] * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+        a1[j] += gg;
+        a2[j] += gg * (zz[j] - mu[j]) * rs[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_acc[g * 8 + j], a1[j]);
+      atomicAdd(&s_acc[C + g * 8 + j], a2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[i], s_acc[i]);
+}
+
+// dz = scale * (g - red0/M - xhat * red1/M)        (train-mode BatchNorm backward)
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
+                        const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
+                        const __nv_bfloat16* __restrict__ z, int z_ld,
+                        __nv_bfloat16* __restrict__ dz, int dz_ld, int C, int64_t npix,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ red, float inv_count, int act, float slope) {
+  const int groups = C >> 3;
+  const int64_t total = npix * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / groups;
+    const int g = (int)(i - p * groups);
+    float d[8], zz[8], o[8];
+    load8(dy1 + p * dy1_ld + g * 8, d);
+    if (dy2 != nullptr) {
+      float e[8];
+      load8(dy2 + p * dy2_ld + g * 8, e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += e[j];
+    }
+    load8(z + p * z_ld + g * 8, zz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+      const float gg = d[j] * act_grad(zz[j] * sc + sh, act, slope);
+      const float xhat = (zz[j] - __ldg(mean + c)) * __ldg(rstd + c);
+      o[j] = sc * (gg - __ldg(red + c) * inv_count - xhat * __ldg(red + C + c) * inv_count);
+    }
+    store8(dz + p * dz_ld + g * 8, o);
+  }
+}
+
+// Biased conv + LeakyReLU layers (no BatchNorm): dz = (dy1+dy2) * leaky'(a) with a the stored
+// activation (sign(a) == sign(pre-activation)); dbias[c] += sum dz.
+__global__ void __launch_bounds__(256)
+act_bwd_bias_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
+                    const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
+                    const __nv_bfloat16* __restrict__ a, int a_ld, __nv_bfloat16* __restrict__ dz,
+                    int dz_ld, int C, int64_t npix, int act, float slope,
+                    float* __restrict__ dbias) {
+  extern __shared__ float s_acc[];  // [C]
+  const int groups = C >> 3;
+  const int py = blockDim.x / groups;
+  const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  if (ty < py) {
+    float acc[8] = {0};
+    for (int64_t p = (int64_t)blockIdx.x * py + ty; p < npix; p += (int64_t)gridDim.x * py) {
+      float d[8], aa[8];
+      load8(dy1 + p * dy1_ld + g * 8, d);
+      if (dy2 != nullptr) {
+        float e[8];
+        load8(dy2 + p * dy2_ld + g * 8, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] += e[j];
+      }
+      load8(a + p * a_ld + g * 8, aa);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j] *= act_grad(aa[j], act, slope);
+        acc[j] += d[j];
+      }
+      store8(dz + p * dz_ld + g * 8, d);
+    }
+    if (dbias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[g * 8 + j], acc[j]);
+    }
+  }
+  __syncthreads();
+  if (dbias != nullptr)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], s_acc[i]);
+}
+
+// fp32 -> bf16 copy (gradient of the fp32 low-resolution logits entering the bf16 GEMMs)
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t count4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+static int reduce_grid(int64_t npix, int py) {
+  int64_t blocks = (npix + py * 8 - 1) / (py * 8);  // >= 8 pixels per thread
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static int stream_grid(int64_t total) {
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+static int check_c(int C, const char* what) {
+  if (C % 8 || C < 8 || C > 2048) return set_error(B200_EINVAL, "%s: C=%d must be a multiple of 8 in [8,2048]", what, C);
+  return B200_OK;
+}
+// threads per block so that blockDim is a multiple of the channel-group count
+static int block_for(int C) {
+  const int groups = C / 8;
+  int t = (256 / groups) * groups;
+  if (t == 0) t = groups;  // C = 2048 + : one row of groups
+  return t;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_channel_stats(const void* x, int ld, int C, int64_t npix, float* stats, cudaStream_t stream) {
+  int rc = check_c(C, "channel_stats");
+  if (rc) return rc;
+  const int threads = block_for(C);
+  channel_stats_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 2 * C * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(x), ld, C, npix, stats);
+  return check_launch("channel_stats");
+}
+
+int b200_bn_finalize(const float* stats, int C, float count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     int training, float* scale, float* shift, float* mean_out, float* rstd_out,
+                     cudaStream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(stats, C, count, gamma, beta, running_mean,
+                                                          running_var, momentum, eps, training,
+                                                          scale, shift, mean_out, rstd_out);
+  return check_launch("bn_finalize");
+}
+
+int b200_bn_act_apply(const void* x, int x_ld, void* y, int y_ld, int C, int64_t npix,
+                      const float* scale, const float* shift, int act, float slope,
+                      cudaStream_t stream) {
+  int rc = check_c(C, "bn_act_apply");
+  if (rc) return rc;
+  bn_act_apply_kernel<<<stream_grid(npix * (C / 8)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<__nv_bfloat16*>(y), y_ld, C, npix,
+      scale, shift, act, slope);
+  return check_launch("bn_act_apply");
+}
+
+int b200_bn_act_bwd_reduce(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
+                           int z_ld, int C, int64_t npix, const float* scale, const float* shift,
+                           const float* mean, const float* rstd, int act, float slope, float* red,
+                           cudaStream_t stream) {
+  int rc = check_c(C, "bn_act_bwd_reduce");
+  if (rc) return rc;
+  const int threads = block_for(C);
+  bn_act_bwd_reduce_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 2 * C * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(dy1), dy1_ld, static_cast<const __nv_bfloat16*>(dy2), dy2_ld,
+      static_cast<const __nv_bfloat16*>(z), z_ld, C, npix, scale, shift, mean, rstd, act, slope, red);
+  return check_launch("bn_act_bwd_reduce");
+}
+
+int b200_bn_act_bwd_apply(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
+                          int z_ld, void* dz, int dz_ld, int C, int64_t npix, const float* scale,
+                          const float* shift, const float* mean, const float* rstd,
+                          const float* red, float inv_count, int act, float slope,
+                          cudaStream_t stream) {
+  int rc = check_c(C, "bn_act_bwd_apply");
+  if (rc) return rc;
+  bn_act_bwd_apply_kernel<<<stream_grid(npix * (C / 8)), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(dy1), dy1_ld, static_cast<const __nv_bfloat16*>(dy2), dy2_ld,
+      static_cast<const __nv_bfloat16*>(z), z_ld, static_cast<__nv_bfloat16*>(dz), dz_ld, C, npix,
+      scale, shift, mean, rstd, red, inv_count, act, slope);
+  return check_launch("bn_act_bwd_apply");
+}
+
+int b200_cast_f32_bf16(const float* x, void* y, int64_t count, cudaStream_t stream) {
+  if (count % 4) return set_error(B200_EINVAL, "cast_f32_bf16: count must be a multiple of 4");
+  cast_f32_bf16_kernel<<<stream_grid(count / 4), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), count / 4);
+  return check_launch("cast_f32_bf16");
+}
+
+int b200_act_bwd_bias(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* a,
+                      int a_ld, void* dz, int dz_ld, int C, int64_t npix, int act, float slope,
+                      float* dbias, cudaStream_t stream) {
+  int rc = check_c(C, "act_bwd_bias");
+  if (rc) return rc;
+  const int threads = block_for(C);
+  act_bwd_bias_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, C * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(dy1), dy1_ld, static_cast<const __nv_bfloat16*>(dy2), dy2_ld,
+      static_cast<const __nv_bfloat16*>(a), a_ld, static_cast<__nv_bfloat16*>(dz), dz_ld, C, npix,
+      act, slope, dbias);
+  return check_launch("act_bwd_bias");
+}
+
+}  // extern "C"

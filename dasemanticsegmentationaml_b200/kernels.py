@@ -136,3 +136,226 @@ def fast_hist_accumulate(label, pred, n, hist, bad):
                                c_int(pred.element_size()), c_int64(label.numel()), c_int(n),
                                ptr(hist), ptr(bad), stream()), "b200_fast_hist")
     return hist
+
+
+def count_equal(label, pred, out):
+    check(lib().b200_count_equal(ptr(label), c_int(label.element_size()), ptr(pred),
+                                 c_int(pred.element_size()), c_int64(label.numel()), ptr(out),
+                                 stream()), "b200_count_equal")
+    return out
+
+
+# ------------------------------------------------------------------ BatchNorm / activation passes
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+
+
+def _pix(t):
+    n, h, w, c, ld = _nhwc_meta(t)
+    return n * h * w, c, ld
+
+
+def channel_stats(x, stats):
+    npix, c, ld = _pix(x)
+    check(lib().b200_channel_stats(ptr(x), c_int(ld), c_int(c), c_int64(npix), ptr(stats), stream()),
+          "b200_channel_stats")
+
+
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, training, scale, shift,
+                mean, rstd, momentum=0.1, eps=1e-5):
+    c = scale.numel()
+    check(lib().b200_bn_finalize(ptr(stats), c_int(c), c_float(count), ptr(gamma), ptr(beta),
+                                 ptr(running_mean), ptr(running_var), c_float(momentum), c_float(eps),
+                                 c_int(1 if training else 0), ptr(scale), ptr(shift), ptr(mean),
+                                 ptr(rstd), stream()), "b200_bn_finalize")
+
+
+def bn_act_apply(x, y, scale, shift, act, slope=0.0):
+    npix, c, x_ld = _pix(x)
+    npix2, c2, y_ld = _pix(y)
+    assert npix == npix2 and c == c2
+    check(lib().b200_bn_act_apply(ptr(x), c_int(x_ld), ptr(y), c_int(y_ld), c_int(c), c_int64(npix),
+                                  ptr(scale), ptr(shift), c_int(act), c_float(slope), stream()),
+          "b200_bn_act_apply")
+
+
+def bn_act_bwd_reduce(dy1, dy2, z, scale, shift, mean, rstd, act, slope, red):
+    npix, c, z_ld = _pix(z)
+    check(lib().b200_bn_act_bwd_reduce(
+        ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
+        ptr(z), c_int(z_ld), c_int(c), c_int64(npix), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+        c_int(act), c_float(slope), ptr(red), stream()), "b200_bn_act_bwd_reduce")
+
+
+def bn_act_bwd_apply(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope):
+    npix, c, z_ld = _pix(z)
+    check(lib().b200_bn_act_bwd_apply(
+        ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
+        ptr(z), c_int(z_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), ptr(scale),
+        ptr(shift), ptr(mean), ptr(rstd), ptr(red), c_float(1.0 / npix), c_int(act), c_float(slope),
+        stream()), "b200_bn_act_bwd_apply")
+
+
+def act_bwd_bias(dy1, dy2, a, dz, act, slope, dbias):
+    npix, c, a_ld = _pix(a)
+    check(lib().b200_act_bwd_bias(
+        ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
+        ptr(a), c_int(a_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), c_int(act),
+        c_float(slope), ptr(dbias), stream()), "b200_act_bwd_bias")
+
+
+# ------------------------------------------------------------------ depthwise / stem
+def dwconv_s2_fwd(x, k, w, bias, z, pool, act, slope, stats):
+    n, h, wd, c, x_ld = _nhwc_meta(x)
+    check(lib().b200_dwconv_s2_fwd(
+        ptr(x), c_int(x_ld), c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(bias),
+        ptr(z), c_int(z.stride(2)), ptr(pool), c_int(0 if pool is None else pool.stride(2)),
+        c_int(act), c_float(slope), ptr(stats), stream()), "b200_dwconv_s2_fwd")
+
+
+def dwconv_s2_dgrad(dz, dpool, k, w, dx):
+    n, h, wd, c, dx_ld = _nhwc_meta(dx)
+    check(lib().b200_dwconv_s2_dgrad(
+        ptr(dz), c_int(dz.stride(2)), ptr(dpool), c_int(0 if dpool is None else dpool.stride(2)),
+        c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(dx), c_int(dx_ld), stream()),
+        "b200_dwconv_s2_dgrad")
+
+
+def dwconv_s2_wgrad(dz, x, k, dw, dbias):
+    n, h, wd, c, x_ld = _nhwc_meta(x)
+    check(lib().b200_dwconv_s2_wgrad(
+        ptr(dz), c_int(dz.stride(2)), ptr(x), c_int(x_ld), c_int(n), c_int(h), c_int(wd), c_int(c),
+        c_int(k), ptr(dw), ptr(dbias), stream()), "b200_dwconv_s2_wgrad")
+
+
+def stem_fwd(img, w, z, stats):
+    n, _, h, wd = img.shape
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
+    check(lib().b200_stem_fwd(ptr(img), c_int(n), c_int(h), c_int(wd), ptr(w), ptr(z),
+                              c_int(z.stride(2)), ptr(stats), stream()), "b200_stem_fwd")
+
+
+def stem_wgrad(img, dz, dw):
+    n, _, h, wd = img.shape
+    check(lib().b200_stem_wgrad(ptr(img), c_int(n), c_int(h), c_int(wd), ptr(dz), c_int(dz.stride(2)),
+                                ptr(dw), stream()), "b200_stem_wgrad")
+
+
+# ------------------------------------------------------------------ attention
+def pool_sum(x, out):
+    n, h, w, c, ld = _nhwc_meta(x)
+    check(lib().b200_pool_sum(ptr(x), c_int(ld), c_int(n), c_int(h * w), c_int(c), ptr(out), stream()),
+          "b200_pool_sum")
+
+
+def fc_small_fwd(inp, in_scale, W, bn, training, act, pre, out, mean, rstd, momentum=0.1, eps=1e-5):
+    n, cin = inp.shape
+    co = W.shape[0]
+    gamma, beta, rm, rv = bn if bn is not None else (None, None, None, None)
+    check(lib().b200_fc_small_fwd(
+        ptr(inp), c_float(in_scale), c_int(n), c_int(cin), c_int(co), ptr(W),
+        c_int(0 if bn is None else 1), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), c_float(momentum),
+        c_float(eps), c_int(1 if training else 0), c_int(act), ptr(pre), ptr(out), ptr(mean), ptr(rstd),
+        stream()), "b200_fc_small_fwd")
+
+
+def fc_small_bwd(dout, out, pre, inp, in_scale, W, has_bn, training, gamma, mean, rstd, act, scratch,
+                 dW, dgamma, dbeta, din, accumulate_din=False):
+    n, cin = inp.shape
+    co = W.shape[0]
+    check(lib().b200_fc_small_bwd(
+        ptr(dout), ptr(out), ptr(pre), ptr(inp), c_float(in_scale), c_int(n), c_int(cin), c_int(co),
+        ptr(W), c_int(1 if has_bn else 0), c_int(1 if training else 0), ptr(gamma), ptr(mean), ptr(rstd),
+        c_int(act), ptr(scratch), ptr(dW), ptr(dgamma), ptr(dbeta), ptr(din),
+        c_int(1 if accumulate_din else 0), stream()), "b200_fc_small_bwd")
+
+
+def scale_add_bcast(a, s, s_plus, v, v_scale, t, out):
+    n, hs, ws, c, a_ld = _nhwc_meta(a)
+    n2, ho, wo, c2, out_ld = _nhwc_meta(out)
+    assert n == n2 and c == c2
+    check(lib().b200_scale_add_bcast(
+        ptr(a), c_int(a_ld), c_int(hs), c_int(ws), ptr(s), c_float(s_plus), ptr(v), c_float(v_scale),
+        ptr(t), c_int(0 if t is None else t.stride(2)), ptr(out), c_int(out_ld), c_int(n), c_int(ho),
+        c_int(wo), c_int(c), stream()), "b200_scale_add_bcast")
+
+
+def upsum_dot_reduce(dout, b, dsum, hs, ws, dot, vsum):
+    n, ho, wo, c, dout_ld = _nhwc_meta(dout)
+    check(lib().b200_upsum_dot_reduce(
+        ptr(dout), c_int(dout_ld), c_int(ho), c_int(wo), ptr(b), c_int(0 if b is None else b.stride(2)),
+        ptr(dsum), c_int(0 if dsum is None else dsum.stride(2)), c_int(n), c_int(hs), c_int(ws),
+        c_int(c), ptr(dot), ptr(vsum), stream()), "b200_upsum_dot_reduce")
+
+
+# ------------------------------------------------------------------ up-sampling / losses
+UP_LOGITS, UP_CE, UP_SOFTMAX, UP_ARGMAX = 0, 1, 2, 3
+
+
+def upsample_fwd(lr, H, W, n_classes, mode, out=None, out_flag=0, p_ld=0, labels=None, ignore_index=255,
+                 acc=None, loss_map=None):
+    n, h_lr, w_lr, ld = lr.shape
+    assert lr.dtype == torch.float32 and lr.is_contiguous()
+    check(lib().b200_upsample_fwd(
+        ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
+        c_int(mode), ptr(out), c_int(out_flag), c_int(p_ld), ptr(labels), c_int(ignore_index), ptr(acc),
+        ptr(loss_map), stream()), "b200_upsample_fwd")
+
+
+def upsample_bwd(lr, H, W, n_classes, mode, d_lr, grad_in=None, grad_is_bf16=0, p_ld=0, labels=None,
+                 ignore_index=255, pixel_weight=None, coef_num=None, coef_den=None, coef_scale=1.0):
+    n, h_lr, w_lr, ld = lr.shape
+    check(lib().b200_upsample_bwd(
+        ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
+        c_int(mode), ptr(grad_in), c_int(grad_is_bf16), c_int(p_ld), ptr(labels), c_int(ignore_index),
+        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), stream()),
+        "b200_upsample_bwd")
+
+
+def radix_select_desc(x, rank, state, hist):
+    check(lib().b200_radix_select_desc(ptr(x), c_int64(x.numel()), c_int64(rank), ptr(state), ptr(hist),
+                                       stream()), "b200_radix_select_desc")
+
+
+def ohem_reduce(x, state, threshold, keep_num, sums, out):
+    check(lib().b200_ohem_reduce(ptr(x), c_int64(x.numel()), ptr(state), c_float(threshold),
+                                 c_int64(keep_num), ptr(sums), ptr(out), stream()), "b200_ohem_reduce")
+
+
+def ohem_weights(x, sel, wout):
+    check(lib().b200_ohem_weights(ptr(x), c_int64(x.numel()), ptr(sel), ptr(wout), stream()),
+          "b200_ohem_weights")
+
+
+def bce_const_fwd(x, target, out):
+    check(lib().b200_bce_const_fwd(ptr(x), c_int(x.numel()), c_float(target), ptr(out), stream()),
+          "b200_bce_const_fwd")
+
+
+def bce_const_bwd(x, target, gscale, gmul, dx):
+    check(lib().b200_bce_const_bwd(ptr(x), c_int(x.numel()), c_float(target), ptr(gscale), c_float(gmul),
+                                   ptr(dx), stream()), "b200_bce_const_bwd")
+
+
+# ------------------------------------------------------------------ discriminator classifier
+def classifier_fwd(x, w, bias, out):
+    n, h, wd, c, ld = _nhwc_meta(x)
+    check(lib().b200_classifier_fwd(ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w),
+                                    ptr(bias), ptr(out), stream()), "b200_classifier_fwd")
+
+
+def classifier_dgrad(dout, w, dx):
+    n, h, wd, c, ld = _nhwc_meta(dx)
+    check(lib().b200_classifier_dgrad(ptr(dout), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w), ptr(dx),
+                                      c_int(ld), stream()), "b200_classifier_dgrad")
+
+
+def classifier_wgrad(dout, x, dw, dbias):
+    n, h, wd, c, ld = _nhwc_meta(x)
+    check(lib().b200_classifier_wgrad(ptr(dout), ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c),
+                                      ptr(dw), ptr(dbias), stream()), "b200_classifier_wgrad")
+
+
+def cast_f32_bf16(x, y):
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    check(lib().b200_cast_f32_bf16(ptr(x), ptr(y), c_int64(x.numel()), stream()), "b200_cast_f32_bf16")
+    return y

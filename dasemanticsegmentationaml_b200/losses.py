@@ -1,0 +1,184 @@
+"""Losses and logit consumers fused with the bilinear (align_corners=True) up-sampling.
+
+Each function takes the network's LOW-resolution class logits (fp32 ``[N, h, w, 32]`` NHWC, as
+returned by ``BiSeNet.forward_lowres``) and is one autograd node backed by the kernels in
+``csrc/loss.cu``; the full-size logit tensor is never written unless ``upsample_logits`` is asked
+for it.  Loss composition mirrors the reference:
+
+* ``upsample_cross_entropy``  = F.interpolate(bilinear, align_corners=True) + CrossEntropyLoss(ignore_index=255)
+  (model_stages.py:240-242, train.py:66,86-89,135,214-217)
+* ``upsample_softmax``        = F.interpolate + F.softmax(dim=1)           (train.py:230,248,257)
+* ``bce_with_logits_const``   = BCEWithLogitsLoss against zeros / ones       (train.py:173,231-232,249-250,258)
+* ``upsample_ohem_cross_entropy`` = F.interpolate + OHEM_CrossEntroy_Loss    (utils.py:256-271)
+* ``upsample_argmax``         = F.interpolate + reverse_one_hot per sample   (utils.py:98-122)
+"""
+import torch
+
+from . import kernels as K
+
+F32 = torch.float32
+BF16 = torch.bfloat16
+
+
+class _UpsampleLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lr, H, W, n_classes, dtype):
+        n = lr.shape[0]
+        out = torch.empty((n, n_classes, H, W), dtype=dtype, device=lr.device)
+        K.upsample_fwd(lr, H, W, n_classes, K.UP_LOGITS, out=out, out_flag=1 if dtype == BF16 else 0)
+        ctx.save_for_backward(lr)
+        ctx.meta = (H, W, n_classes)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (lr,) = ctx.saved_tensors
+        H, W, n_classes = ctx.meta
+        d_lr = torch.zeros_like(lr)
+        dout = dout.contiguous()
+        if dout.dtype not in (F32, BF16):
+            dout = dout.float()
+        K.upsample_bwd(lr, H, W, n_classes, K.UP_LOGITS, d_lr, grad_in=dout,
+                       grad_is_bf16=1 if dout.dtype == BF16 else 0)
+        return d_lr, None, None, None, None
+
+
+def upsample_logits(lr, H, W, n_classes=19, dtype=F32):
+    """Full-size logits ``[N, n_classes, H, W]`` (NCHW) from the low-resolution map."""
+    return _UpsampleLogits.apply(lr, H, W, n_classes, dtype)
+
+
+class _UpsampleCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lr, labels, H, W, n_classes, ignore_index):
+        acc = torch.zeros(2, dtype=torch.float64, device=lr.device)
+        K.upsample_fwd(lr, H, W, n_classes, K.UP_CE, labels=labels, ignore_index=ignore_index, acc=acc)
+        ctx.save_for_backward(lr, labels, acc)
+        ctx.meta = (H, W, n_classes, ignore_index)
+        return (acc[0] / acc[1]).to(F32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lr, labels, acc = ctx.saved_tensors
+        H, W, n_classes, ignore_index = ctx.meta
+        d_lr = torch.zeros_like(lr)
+        K.upsample_bwd(lr, H, W, n_classes, K.UP_CE, d_lr, labels=labels, ignore_index=ignore_index,
+                       coef_num=g.to(F32).contiguous(), coef_den=acc[1:])
+        return d_lr, None, None, None, None, None
+
+
+def _check_labels(labels, n, H, W):
+    if labels.dim() == 4 and labels.shape[1] == 1:
+        labels = labels[:, 0]
+    assert labels.shape == (n, H, W), "labels must be [N, H, W] (or [N, 1, H, W])"
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    return labels.contiguous()
+
+
+def upsample_cross_entropy(lr, labels, n_classes=19, ignore_index=255):
+    """mean over non-ignored pixels of -log softmax(upsample(lr))[label]."""
+    labels = _check_labels(labels, lr.shape[0], labels.shape[-2], labels.shape[-1])
+    H, W = labels.shape[1:]
+    return _UpsampleCE.apply(lr, labels, H, W, n_classes, ignore_index)
+
+
+class _UpsampleSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lr, H, W, n_classes):
+        n = lr.shape[0]
+        p = torch.empty((n, H, W, 32), dtype=BF16, device=lr.device)
+        K.upsample_fwd(lr, H, W, n_classes, K.UP_SOFTMAX, out=p, p_ld=32)
+        ctx.save_for_backward(lr)
+        ctx.meta = (H, W, n_classes)
+        return p.permute(0, 3, 1, 2)[:, :n_classes]
+
+    @staticmethod
+    def backward(ctx, dp):
+        (lr,) = ctx.saved_tensors
+        H, W, n_classes = ctx.meta
+        from .model._glue import to_nhwc
+        d = to_nhwc(dp)
+        d_lr = torch.zeros_like(lr)
+        K.upsample_bwd(lr, H, W, n_classes, K.UP_SOFTMAX, d_lr, grad_in=d, grad_is_bf16=1, p_ld=d.stride(2))
+        return d_lr, None, None, None
+
+
+def upsample_softmax(lr, H, W, n_classes=19):
+    """softmax(upsample(lr), dim=1) as a bf16 channels-last ``[N, n_classes, H, W]`` tensor (a view of
+    a 32-channel NHWC buffer whose padding channels are zero) — the discriminator's input."""
+    return _UpsampleSoftmax.apply(lr, H, W, n_classes)
+
+
+class _BCEConst(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        xf = x.contiguous()
+        out = torch.zeros((), dtype=F32, device=x.device)
+        K.bce_const_fwd(xf, float(target), out)
+        ctx.save_for_backward(xf)
+        ctx.target = float(target)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        K.bce_const_bwd(x, ctx.target, g.to(F32).contiguous(), 1.0, dx)
+        return dx, None
+
+
+def bce_with_logits_const(logits, target):
+    """BCEWithLogitsLoss(logits, full_like(logits, target)) for fp32 discriminator outputs."""
+    assert logits.dtype == F32
+    return _BCEConst.apply(logits, target)
+
+
+class _UpsampleOhemCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lr, labels, H, W, n_classes, threshold, keep_num):
+        n = lr.shape[0]
+        dev = lr.device
+        loss_map = torch.empty((n, H, W), dtype=F32, device=dev)
+        acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        # the reference's OHEM has no ignore_index (utils.py:261): every pixel takes part
+        K.upsample_fwd(lr, H, W, n_classes, K.UP_CE, labels=labels, ignore_index=-1, acc=acc, loss_map=loss_map)
+        state = torch.empty(2, dtype=torch.int32, device=dev)
+        hist = torch.empty(256, dtype=torch.int32, device=dev)
+        K.radix_select_desc(loss_map, keep_num, state, hist)
+        sums = torch.empty(5, dtype=torch.float64, device=dev)
+        sel = torch.empty(4, dtype=F32, device=dev)
+        K.ohem_reduce(loss_map, state, threshold, keep_num, sums, sel)
+        ctx.save_for_backward(lr, labels, loss_map, sel)
+        ctx.meta = (H, W, n_classes)
+        return sel[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        lr, labels, loss_map, sel = ctx.saved_tensors
+        H, W, n_classes = ctx.meta
+        weights = torch.empty_like(loss_map)
+        K.ohem_weights(loss_map, sel, weights)
+        d_lr = torch.zeros_like(lr)
+        K.upsample_bwd(lr, H, W, n_classes, K.UP_CE, d_lr, labels=labels, ignore_index=-1,
+                       pixel_weight=weights, coef_num=g.to(F32).contiguous())
+        return d_lr, None, None, None, None, None, None
+
+
+def upsample_ohem_cross_entropy(lr, labels, threshold, keep_num, n_classes=19):
+    """OHEM_CrossEntroy_Loss(threshold, keep_num)(upsample(lr), labels) with a radix-select k-th
+    largest instead of torch.sort.  Labels must lie in [0, n_classes) (the reference raises otherwise)."""
+    labels = _check_labels(labels, lr.shape[0], labels.shape[-2], labels.shape[-1])
+    H, W = labels.shape[1:]
+    if not (0 <= keep_num < labels.numel()):
+        raise IndexError("keep_num %d out of range for %d pixels" % (keep_num, labels.numel()))
+    return _UpsampleOhemCE.apply(lr, labels, H, W, n_classes, float(threshold), int(keep_num))
+
+
+def upsample_argmax(lr, H, W, n_classes=19, dtype=torch.int64):
+    """Per-pixel class map ``[N, H, W]`` (int64 like reverse_one_hot, or uint8)."""
+    n = lr.shape[0]
+    out = torch.empty((n, H, W), dtype=dtype, device=lr.device)
+    with torch.no_grad():
+        K.upsample_fwd(lr.detach(), H, W, n_classes, K.UP_ARGMAX, out=out, out_flag=1 if dtype == torch.uint8 else 0)
+    return out

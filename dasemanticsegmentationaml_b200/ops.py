@@ -1,0 +1,289 @@
+"""Layer-level forward/backward built from the CUDA kernels (no autograd in here).
+
+Each ``*_fwd`` returns ``(output, ctx)`` and each ``*_bwd`` consumes that ctx.  Activations are
+bf16 NHWC tensors ``[N, H, W, C]`` (channel slices of wider buffers are fine, see kernels.py);
+parameters stay the fp32 ``nn.Parameter`` masters, their bf16 GEMM packings are cached per
+parameter version.  torch is used for allocation only.
+"""
+import torch
+
+from . import kernels as K
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+# when True the packed-filter cache is bypassed (needed while capturing CUDA graphs: the captured
+# graph must contain the repacking kernels because the fp32 masters change between replays)
+FORCE_REPACK = False
+_pack_cache = {}
+
+
+def packed_filter(weight, transpose):
+    key = (weight.data_ptr(), bool(transpose), tuple(weight.shape))
+    ver = weight._version
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver and not FORCE_REPACK:
+        return hit[1]
+    if hit is not None and hit[1].device == weight.device:
+        buf = hit[1]  # repack in place: stable pointer for graphs, no allocator churn
+        cout, cin, r, s = weight.shape
+        w = weight.detach()
+        K.check(K.lib().b200_pack_filter(K.ptr(w), K.ptr(buf), K.c_int(cout), K.c_int(cin),
+                                         K.c_int(r * s), K.c_int(buf.shape[0]), K.c_int(buf.shape[2]),
+                                         K.c_int(1 if transpose else 0), K.stream()), "b200_pack_filter")
+    else:
+        buf = K.pack_filter(weight, transpose)
+    _pack_cache[key] = (ver, buf)
+    return buf
+
+
+def clear_caches():
+    _pack_cache.clear()
+
+
+def empty_act(n, h, w, c, device):
+    return torch.empty((n, h, w, c), dtype=BF16, device=device)
+
+
+# --------------------------------------------------------------------------- BatchNorm (+act)
+class BNCtx:
+    __slots__ = ("z", "scale", "shift", "mean", "rstd", "act", "slope", "training")
+
+
+def bn_act_fwd(z, stats, bn, training, act, slope=0.0, out=None):
+    """z: raw conv output; stats: [2, C] sums (train) or None (eval); bn = (gamma, beta, rm, rv)."""
+    n, h, w, c = z.shape
+    gamma, beta, rm, rv = bn
+    buf = torch.empty((4, c), dtype=F32, device=z.device)
+    K.bn_finalize(stats, float(n * h * w), gamma, beta, rm, rv, training, buf[0], buf[1], buf[2], buf[3])
+    a = out if out is not None else torch.empty_like(z)
+    K.bn_act_apply(z, a, buf[0], buf[1], act, slope)
+    ctx = BNCtx()
+    ctx.z, ctx.scale, ctx.shift, ctx.mean, ctx.rstd = z, buf[0], buf[1], buf[2], buf[3]
+    ctx.act, ctx.slope, ctx.training = act, slope, training
+    return a, ctx
+
+
+def bn_act_bwd(ctx, dy1, dy2=None):
+    """-> (dz, dgamma, dbeta) for train-mode BatchNorm followed by ctx.act."""
+    if not ctx.training:
+        raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference's training path")
+    c = ctx.z.shape[3]
+    red = torch.zeros((2, c), dtype=F32, device=ctx.z.device)
+    K.bn_act_bwd_reduce(dy1, dy2, ctx.z, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, ctx.act, ctx.slope, red)
+    dz = torch.empty(ctx.z.shape, dtype=BF16, device=ctx.z.device)
+    K.bn_act_bwd_apply(dy1, dy2, ctx.z, dz, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, red, ctx.act, ctx.slope)
+    return dz, red[1], red[0]
+
+
+# --------------------------------------------------------------------------- dense conv (+BN+act)
+class ConvCtx:
+    __slots__ = ("x", "weight", "stride", "pad", "bn", "a", "act", "slope", "stem_img")
+
+
+def conv_raw_fwd(x, weight, stride, pad, stats=None, bias=None, act=K.ACT_NONE, slope=0.0, out=None,
+                 out_dtype=BF16):
+    """Implicit-GEMM convolution of an NHWC bf16 view; returns the [N,Ho,Wo,rows_pad] result."""
+    n, h, w, _ = x.shape
+    _, _, r, s = weight.shape
+    geom = K.fwd_geometry(h, w, r, s, stride, pad)
+    filt = packed_filter(weight, False)
+    if out is None:
+        out = torch.empty((n, geom["Hout"], geom["Wout"], filt.shape[0]), dtype=out_dtype, device=x.device)
+    K.conv_igemm(x, filt, out, geom, bias=bias, act=act, slope=slope, stats=stats)
+    return out
+
+
+def conv_dgrad(dz, weight, stride, pad, hin, win):
+    """dx[N,hin,win,round16(Cin)] of a dense conv given dz (NHWC bf16 view over the conv's output)."""
+    _, _, r, s = weight.shape
+    geom = K.dgrad_geometry(hin, win, r, s, stride, pad)
+    filt_t = packed_filter(weight, True)
+    dx = torch.empty((dz.shape[0], hin, win, filt_t.shape[0]), dtype=BF16, device=dz.device)
+    if filt_t.shape[2] > dz.shape[3]:
+        pass  # TMA zero-fills the channels beyond dz's view
+    K.conv_igemm(dz, filt_t, dx, geom)
+    return dx
+
+
+def conv_wgrad(dz, x, weight, stride, pad):
+    cout, cin, r, s = weight.shape
+    dw = torch.zeros((cout, cin, r, s), dtype=F32, device=dz.device)
+    K.conv_wgrad(dz, x, dw, r, s, stride, pad)
+    return dw
+
+
+def conv_bn_act_fwd(x, weight, bn, stride, pad, training, act=K.ACT_RELU, slope=0.0, out=None):
+    """ConvX / ConvBNReLU: bias-free conv -> BatchNorm2d -> activation (stdcnet.py:6-15,
+    model_stages.py:11-29).  `x` is an NHWC bf16 view, or the fp32 NCHW image for the 3-channel stem."""
+    cout = weight.shape[0]
+    stats = torch.zeros((2, cout), dtype=F32, device=weight.device) if training else None
+    ctx = ConvCtx()
+    ctx.stem_img = None
+    if x.dim() == 4 and x.dtype == F32 and x.shape[1] == 3 and weight.shape[1] == 3:
+        # stem: 3x3 stride 2 directly from the NCHW image
+        assert weight.shape[2] == 3 and stride == 2 and pad == 1 and cout == 32
+        n, _, h, w = x.shape
+        z = empty_act(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cout, x.device)
+        K.stem_fwd(x, weight.detach(), z, stats)
+        ctx.stem_img = x
+    else:
+        assert cout % 16 == 0, "BatchNorm'd convs have a multiple of 16 output channels"
+        z = conv_raw_fwd(x, weight, stride, pad, stats=stats)
+    a, bnctx = bn_act_fwd(z, stats, bn, training, act, slope, out)
+    ctx.x, ctx.weight, ctx.stride, ctx.pad, ctx.bn, ctx.a = x, weight, stride, pad, bnctx, a
+    ctx.act, ctx.slope = act, slope
+    return a, ctx
+
+
+def conv_bn_act_bwd(ctx, dy1, dy2=None, need_dx=True):
+    """-> (dx or None, dW, dgamma, dbeta)"""
+    dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy1, dy2)
+    if ctx.stem_img is not None:
+        dw = torch.zeros(ctx.weight.shape, dtype=F32, device=dz.device)
+        K.stem_wgrad(ctx.stem_img, dz, dw)
+        return None, dw, dgamma, dbeta
+    dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad)
+    dx = None
+    if need_dx:
+        dx = conv_dgrad(dz, ctx.weight, ctx.stride, ctx.pad, ctx.x.shape[1], ctx.x.shape[2])
+    return dx, dw, dgamma, dbeta
+
+
+# --------------------------------------------------------------------------- biased conv + LeakyReLU
+class ConvBiasCtx:
+    __slots__ = ("x", "weight", "stride", "pad", "a", "act", "slope", "has_bias")
+
+
+def conv_bias_act_fwd(x, weight, bias_padded, stride, pad, act, slope):
+    """FCDiscriminator layers (discriminator.py:17-25): conv + bias + LeakyReLU fused in the epilogue."""
+    a = conv_raw_fwd(x, weight, stride, pad, bias=bias_padded, act=act, slope=slope)
+    ctx = ConvBiasCtx()
+    ctx.x, ctx.weight, ctx.stride, ctx.pad, ctx.a, ctx.act, ctx.slope = x, weight, stride, pad, a, act, slope
+    return a, ctx
+
+
+def conv_bias_act_bwd(ctx, dy1, dy2=None, need_dx=True, need_dw=True):
+    """-> (dx, dW, dbias)"""
+    c = ctx.a.shape[3]
+    dz = torch.empty(ctx.a.shape, dtype=BF16, device=ctx.a.device)
+    dbias = torch.zeros((c,), dtype=F32, device=ctx.a.device) if need_dw else None
+    K.act_bwd_bias(dy1, dy2, ctx.a, dz, ctx.act, ctx.slope, dbias)
+    dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad) if need_dw else None
+    dx = None
+    if need_dx:
+        dx = conv_dgrad(dz, ctx.weight, ctx.stride, ctx.pad, ctx.x.shape[1], ctx.x.shape[2])
+    if dbias is not None:
+        dbias = dbias[:ctx.weight.shape[0]]
+    return dx, dw, dbias
+
+
+# --------------------------------------------------------------------------- global-pool attention
+class FcCtx:
+    __slots__ = ("inp", "in_scale", "W", "bn", "training", "act", "pre", "out", "mean", "rstd")
+
+
+def fc_fwd(inp, in_scale, weight, bn, training, act):
+    """1x1 conv on an [N, C] vector (+BatchNorm over the batch) + activation."""
+    n = inp.shape[0]
+    co = weight.shape[0]
+    if bn is not None and training and n < 2:
+        raise ValueError("Expected more than 1 value per channel when training, got input size [%d, %d, 1, 1]" % (n, co))
+    buf = torch.empty((2, n, co), dtype=F32, device=inp.device)
+    ms = torch.empty((2, co), dtype=F32, device=inp.device)
+    W = weight.detach().view(co, -1)
+    K.fc_small_fwd(inp, in_scale, W, bn, training, act, buf[0], buf[1], ms[0], ms[1])
+    ctx = FcCtx()
+    ctx.inp, ctx.in_scale, ctx.W, ctx.bn, ctx.training, ctx.act = inp, in_scale, W, bn, training, act
+    ctx.pre, ctx.out, ctx.mean, ctx.rstd = buf[0], buf[1], ms[0], ms[1]
+    return buf[1], ctx
+
+
+def fc_bwd(ctx, dout, need_din=True):
+    """-> (din [N, Cin] (already multiplied by in_scale), dW (conv-shaped), dgamma, dbeta)"""
+    n, cin = ctx.inp.shape
+    co = ctx.W.shape[0]
+    dev = dout.device
+    scratch = torch.empty((n, co), dtype=F32, device=dev)
+    dW = torch.zeros((co, cin), dtype=F32, device=dev)
+    has_bn = ctx.bn is not None
+    dgb = torch.zeros((2, co), dtype=F32, device=dev) if has_bn else None
+    din = torch.empty((n, cin), dtype=F32, device=dev) if need_din else None
+    K.fc_small_bwd(dout, ctx.out, ctx.pre, ctx.inp, ctx.in_scale, ctx.W, has_bn, ctx.training,
+                   ctx.bn[0] if has_bn else None, ctx.mean, ctx.rstd, ctx.act, scratch, dW,
+                   dgb[0] if has_bn else None, dgb[1] if has_bn else None, din)
+    return din, dW.view(co, cin, 1, 1), (dgb[0] if has_bn else None), (dgb[1] if has_bn else None)
+
+
+def pool_sum(x):
+    out = torch.zeros((x.shape[0], x.shape[3]), dtype=F32, device=x.device)
+    K.pool_sum(x, out)
+    return out
+
+
+# --------------------------------------------------------------------------- depthwise + BN (+pool)
+class DwCtx:
+    __slots__ = ("x", "weight", "k", "bn", "z", "a", "act", "slope", "has_pool", "bias")
+
+
+def dw_bn_fwd(x, weight, bn, training, pool_out=None, act=K.ACT_NONE, slope=0.0, bias=None):
+    """Depthwise k x k stride-2 conv (+ fused 3x3/s2 average pool of the same input) followed by
+    BatchNorm (+act).  With bn=None: conv + bias + act only."""
+    n, h, w, c = x.shape
+    k = weight.shape[2]
+    ho, wo = (h + 2 - k) // 2 + 1, (w + 2 - k) // 2 + 1
+    wflat = weight.detach().view(-1)
+    ctx = DwCtx()
+    ctx.x, ctx.weight, ctx.k, ctx.act, ctx.slope, ctx.has_pool, ctx.bias = x, weight, k, act, slope, pool_out is not None, bias
+    if bn is not None:
+        z = empty_act(n, ho, wo, c, x.device)
+        stats = torch.zeros((2, c), dtype=F32, device=x.device) if training else None
+        K.dwconv_s2_fwd(x, k, wflat, bias, z, pool_out, K.ACT_NONE, 0.0, stats)
+        a, ctx.bn = bn_act_fwd(z, stats, bn, training, act, slope)
+        ctx.z, ctx.a = z, a
+        return a, ctx
+    a = empty_act(n, ho, wo, c, x.device)
+    K.dwconv_s2_fwd(x, k, wflat, bias, a, pool_out, act, slope, None)
+    ctx.bn, ctx.z, ctx.a = None, None, a
+    return a, ctx
+
+
+def dw_bn_bwd(ctx, dy, dpool=None, need_dx=True):
+    """-> (dx, dW, dbias, dgamma, dbeta)"""
+    dev = dy.device
+    c = ctx.x.shape[3]
+    dgamma = dbeta = dbias = None
+    if ctx.bn is not None:
+        dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy)
+        if ctx.bias is not None:
+            dbias = torch.zeros((c,), dtype=F32, device=dev)
+    else:
+        dz = torch.empty(ctx.a.shape, dtype=BF16, device=dev)
+        dbias = torch.zeros((c,), dtype=F32, device=dev) if ctx.bias is not None else None
+        K.act_bwd_bias(dy, None, ctx.a, dz, ctx.act, ctx.slope, None)
+    dw = torch.zeros((c * ctx.k * ctx.k,), dtype=F32, device=dev)
+    K.dwconv_s2_wgrad(dz, ctx.x, ctx.k, dw, dbias)
+    dx = None
+    if need_dx:
+        dx = torch.empty(ctx.x.shape, dtype=BF16, device=dev)
+        K.dwconv_s2_dgrad(dz, dpool, ctx.k, ctx.weight.detach().view(-1), dx)
+    return dx, dw.view(ctx.weight.shape[0], 1, ctx.k, ctx.k)[: ctx.weight.shape[0]], dbias, dgamma, dbeta
+
+
+# --------------------------------------------------------------------------- small helpers
+def add_acts(a, b):
+    """a + b for two NHWC bf16 views of the same shape (gradient joins of branching features)."""
+    out = torch.empty(a.shape, dtype=BF16, device=a.device)
+    K.scale_add_bcast(a, None, 1.0, None, 0.0, b, out)
+    return out
+
+
+def add_bcast_vec(a, v):
+    """a[n,h,w,c] + v[n,c]"""
+    out = torch.empty(a.shape, dtype=BF16, device=a.device)
+    K.scale_add_bcast(a, None, 1.0, v, 1.0, None, out)
+    return out
+
+
+def zeros_act(shape, device):
+    return torch.zeros(shape, dtype=BF16, device=device)

@@ -1,0 +1,147 @@
+"""Training / evaluation steps with the loss composition of the reference's ``train.py``.
+
+``train_step`` is the body of ``train()`` (train.py:76-93), ``train_da_step`` the body of
+``train_DA()``'s inner loop (train.py:192-262) and ``val`` the evaluation loop (train.py:24-61),
+restated over the fused B200 ops:
+
+* the three cross-entropy terms consume the low-resolution logits directly (bilinear up-sampling,
+  log-softmax and NLL fused, nothing of size N x 19 x H x W is written);
+* ``softmax(output)`` feeding the discriminator is one fused up-sample+softmax kernel writing bf16;
+* BCE-with-logits against all-zeros / all-ones needs no target tensor;
+* bf16 needs no loss scaling, so the reference's fp16 ``GradScaler`` (train.py:137,219-221) is gone;
+* multi-GPU is one process per GPU: gradients are averaged with one NCCL all-reduce per optimizer
+  step (the reference's nn.DataParallel reduce-add, train.py:145-152,497), the evaluation
+  confusion matrices are summed with an int64 all-reduce.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import losses
+from .utils import compute_global_accuracy, fast_hist_device, per_class_iu
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_grads(params, world=None):
+    """Average ``.grad`` over ranks with ONE all-reduce over a flat fp32 bucket; parameters whose
+    grad is None on this step (dead classifier head, aux heads in the adversarial pass) are skipped
+    on every rank alike."""
+    world = world or _world()
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat)
+    flat.div_(world)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+
+
+def supervised_loss(model, images, labels, loss="ce", ohem_threshold=0.3567, ohem_keep=None):
+    """loss1 + loss2 + loss3 over (out, out16, out32)  (train.py:84-89 / 212-217)."""
+    lr = model.forward_lowres(images)
+    if loss == "ohem":
+        if ohem_keep is None:
+            ohem_keep = labels.numel() // 16
+        terms = [losses.upsample_ohem_cross_entropy(t, labels, ohem_threshold, ohem_keep) for t in lr]
+    else:
+        terms = [losses.upsample_cross_entropy(t, labels) for t in lr]
+    return terms[0] + terms[1] + terms[2], lr
+
+
+def train_step(model, optimizer, images, labels, loss="ce", **kw):
+    """One supervised iteration (train.py:76-93). Returns the loss tensor (no host sync)."""
+    model.train()
+    optimizer.zero_grad()
+    total, _ = supervised_loss(model, images, labels, loss, **kw)
+    total.backward()
+    allreduce_grads(_opt_params(optimizer))
+    optimizer.step()
+    return total.detach()
+
+
+def _opt_params(optimizer):
+    return [p for g in optimizer.param_groups for p in g["params"]]
+
+
+def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images_t, lambda_adv=0.001):
+    """One adversarial domain-adaptation iteration (train.py:192-262).
+
+    Returns (loss_seg, loss_adv_G, loss_D_source, loss_D_target) as device scalars."""
+    H, W = images.shape[2:]
+    optimizer.zero_grad()
+    optimizer_D.zero_grad()
+    model.train()
+    model_D.train()
+    for p in model_D.parameters():          # train.py:207-208
+        p.requires_grad = False
+
+    # train the segmentation net on the labelled source batch (train.py:211-221)
+    loss, lr_src = supervised_loss(model, images, labels)
+    loss.backward()
+    allreduce_grads(_opt_params(optimizer))
+    optimizer.step()
+
+    # adversarial term on the target batch, through the frozen discriminator (train.py:223-237)
+    lr_tgt = model.forward_lowres(images_t)
+    optimizer.zero_grad()
+    d_out = model_D(losses.upsample_softmax(lr_tgt[0], H, W))
+    loss_adv_g = losses.bce_with_logits_const(d_out, 0.0)
+    (loss_adv_g * lambda_adv).backward()
+    allreduce_grads(_opt_params(optimizer))
+    optimizer.step()
+
+    # train the discriminator on detached predictions (train.py:240-262)
+    for p in model_D.parameters():
+        p.requires_grad = True
+    out_src = lr_src[0].detach()
+    out_tgt = lr_tgt[0].detach()
+    d_out = model_D(losses.upsample_softmax(out_src, H, W))
+    loss_d_src = losses.bce_with_logits_const(d_out, 0.0)
+    loss_d_src.backward()
+    allreduce_grads(_opt_params(optimizer_D))
+    optimizer_D.step()
+
+    d_out = model_D(losses.upsample_softmax(out_tgt, H, W))
+    loss_d_tgt = losses.bce_with_logits_const(d_out, 1.0)
+    optimizer_D.zero_grad()
+    loss_d_tgt.backward()
+    allreduce_grads(_opt_params(optimizer_D))
+    optimizer_D.step()
+    return loss.detach(), loss_adv_g.detach(), loss_d_src.detach(), loss_d_tgt.detach()
+
+
+@torch.no_grad()
+def eval_batch(model, images, labels, n_classes=19, hist=None, pred_dtype=torch.uint8):
+    """Forward + fused up-sample/argmax + confusion-matrix accumulation for a whole batch, all on
+    the device (train.py:30-47 handles one image at a time through the host).  Returns
+    (hist int64 [n*n] on the device, pred [N, H, W])."""
+    model.eval()
+    H, W = images.shape[2:]
+    lr = model.forward_lowres(images)
+    pred = losses.upsample_argmax(lr[0], H, W, n_classes, pred_dtype)
+    lab = labels[:, 0] if labels.dim() == 4 else labels
+    hist = fast_hist_device(lab.long(), pred, n_classes, hist)
+    return hist, pred
+
+
+def val(model, batches, n_classes=19):
+    """Evaluation loop (train.py:24-61): (mean pixel precision, mIoU).  ``batches`` yields
+    (images, labels) CUDA tensors; the confusion matrix is summed over ranks with NCCL."""
+    hist = None
+    precisions = []
+    for images, labels in batches:
+        hist, pred = eval_batch(model, images, labels, n_classes, hist)
+        lab = labels[:, 0] if labels.dim() == 4 else labels
+        for i in range(images.shape[0]):
+            precisions.append(compute_global_accuracy(pred[i], lab[i]))
+    if _world() > 1:
+        dist.all_reduce(hist)
+    h = hist.cpu().numpy().reshape(n_classes, n_classes).astype(np.float64)
+    miou_list = per_class_iu(h)
+    return float(np.mean(precisions)), float(np.mean(miou_list))
