@@ -1,0 +1,148 @@
+"""Teacher-forced composites (bottlenecks, ARM tails, FFM, heads) against the oracle.
+Inputs/weights are bf16-rounded on both sides; the oracle keeps fp32 intermediates, so the gates
+are looser than for a single layer: activations rel-L2 <= 2e-2, gradients cosine >= 0.99."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import segnet_oracle as O
+from tests.helpers import bf16_round, cosine, load_oracle_state, rel_l2, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def cl(x):
+    return x.to(BF).contiguous(memory_format=torch.channels_last)
+
+
+def rounded(sd):
+    return {k: (bf16_round(v) if (v.is_floating_point() and v.dim() == 4) else v.clone()) for k, v in sd.items()}
+
+
+def check_grads(module, osd, prefix="", tol=0.99):
+    bad = []
+    for k, p in module.named_parameters():
+        ko = prefix + k
+        if ko in osd and osd[ko].grad is not None:
+            c = cosine(p.grad, osd[ko].grad)
+            if not c > tol:
+                bad.append((k, c))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("cfg", [(64, 256, 2, 32, 64), (256, 256, 1, 16, 32), (512, 1024, 2, 9, 17)])
+def test_cat_bottleneck(cuda_lib, cfg):
+    from dasemanticsegmentationaml_b200.model import CatBottleneck
+    cin, cout, stride, h, w = cfg
+    full = O.make_bisenet_state(seed=3, randomize_bn=True)
+    src = {(64, 256, 2): "cp.backbone.features.2", (256, 256, 1): "cp.backbone.features.3",
+           (512, 1024, 2): "cp.backbone.features.6"}[(cin, cout, stride)]
+    sd = rounded({k[len(src) + 1:]: v for k, v in full.items() if k.startswith(src + ".")})
+    m = load_oracle_state(CatBottleneck(cin, cout, 4, stride), sd).to(DEV).train()
+    g = torch.Generator().manual_seed(1)
+    x = bf16_round(torch.randn(4, cin, h, w, generator=g).abs()).to(DEV)
+    xp = x.clone().requires_grad_(True)
+    y = m(cl(xp))
+    osd = to_device(sd, DEV, True)
+    osd = {"b." + k: v for k, v in osd.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = O.cat_bottleneck(osd, "b", xo, cout, stride, True)
+    assert y.shape == yo.shape
+    print("bottleneck", cfg, "rel-L2", rel_l2(y, yo))
+    assert rel_l2(y, yo) < 2e-2
+    dy = bf16_round(torch.randn(yo.shape, generator=g)).to(DEV)
+    y.backward(dy.to(BF))
+    yo.backward(dy)
+    check_grads(m, osd, "b.")
+    c = cosine(xp.grad, xo.grad)
+    print("dx cosine", c)
+    assert c > 0.99
+
+
+@pytest.mark.parametrize("mode", ["plain", "vec_up", "tensor_up", "odd_up"])
+def test_arm_tail(cuda_lib, mode):
+    from dasemanticsegmentationaml_b200.model import AttentionRefinementModule
+    from dasemanticsegmentationaml_b200.model._glue import to_nhwc
+    full = O.make_bisenet_state(seed=3, randomize_bn=True)
+    sd = rounded({k[len("cp.arm16."):]: v for k, v in full.items() if k.startswith("cp.arm16.")})
+    m = load_oracle_state(AttentionRefinementModule(512, 128), sd).to(DEV).train()
+    g = torch.Generator().manual_seed(2)
+    n, h, w = 4, 12, 20
+    x = bf16_round(torch.randn(n, 512, h, w, generator=g).abs()).to(DEV)
+    osd = {"a." + k: v for k, v in to_device(sd, DEV, True).items()}
+    xo = x.clone().requires_grad_(True)
+    feat_o = O.attention_refinement(osd, "a", xo, True)
+    if mode == "plain":
+        xp = x.clone().requires_grad_(True)
+        y = m(cl(xp))
+        yo = feat_o
+        dy = bf16_round(torch.randn(yo.shape, generator=g)).to(DEV)
+        y.backward(dy.to(BF))
+        yo.backward(dy)
+        assert rel_l2(y, yo) < 2e-2
+        check_grads(m, osd, "a.")
+        assert cosine(xp.grad, xo.grad) > 0.99
+        return
+    out_hw = (2 * h, 2 * w) if mode != "odd_up" else (2 * h - 1, 2 * w - 1)
+    vec = torch.randn(n, 128, generator=g).to(DEV).requires_grad_(True)
+    t = bf16_round(torch.randn(n, 128, h, w, generator=g)).to(DEV).requires_grad_(True)
+    with torch.no_grad():
+        xin = to_nhwc(cl(x))
+        add_vec = vec.detach().clone() if mode == "vec_up" else None
+        add_t = to_nhwc(cl(t.detach())) if mode != "vec_up" else None
+        out, ctx = m._fwd_tail(xin, add_vec=add_vec, add_t=add_t, out_hw=out_hw)
+    add_o = vec[:, :, None, None] if mode == "vec_up" else t
+    yo = F.interpolate(feat_o + add_o, out_hw, mode="nearest")
+    y = out.permute(0, 3, 1, 2)
+    print("arm", mode, "rel-L2", rel_l2(y, yo))
+    assert rel_l2(y, yo) < 2e-2
+    dy = bf16_round(torch.randn(yo.shape, generator=g)).to(DEV)
+    yo.backward(dy)
+    with torch.no_grad():
+        dx, d_vec, d_t, grads = m._bwd_tail(ctx, to_nhwc(cl(dy)), True)
+    for p, gr in grads.items():
+        p.grad = gr
+    check_grads(m, osd, "a.")
+    assert cosine(dx.permute(0, 3, 1, 2), xo.grad) > 0.99
+    if mode == "vec_up":
+        assert cosine(d_vec, vec.grad) > 0.999
+    else:
+        assert cosine(d_t.permute(0, 3, 1, 2), t.grad) > 0.999
+
+
+def test_ffm_and_head(cuda_lib):
+    from dasemanticsegmentationaml_b200.model import FeatureFusionModule, BiSeNetOutput
+    full = O.make_bisenet_state(seed=3, randomize_bn=True)
+    g = torch.Generator().manual_seed(4)
+    n, h, w = 4, 16, 24
+    sd = rounded({k[4:]: v for k, v in full.items() if k.startswith("ffm.")})
+    m = load_oracle_state(FeatureFusionModule(384, 256), sd).to(DEV).train()
+    fsp = bf16_round(torch.randn(n, 256, h, w, generator=g).abs()).to(DEV)
+    fcp = bf16_round(torch.randn(n, 128, h, w, generator=g).abs()).to(DEV)
+    a, b = fsp.clone().requires_grad_(True), fcp.clone().requires_grad_(True)
+    y = m(cl(a), cl(b))
+    osd = {"ffm." + k: v for k, v in to_device(sd, DEV, True).items()}
+    ao, bo = fsp.clone().requires_grad_(True), fcp.clone().requires_grad_(True)
+    yo = O.feature_fusion(osd, "ffm", ao, bo, True)
+    assert rel_l2(y, yo) < 2e-2
+    dy = bf16_round(torch.randn(yo.shape, generator=g)).to(DEV)
+    y.backward(dy.to(BF))
+    yo.backward(dy)
+    check_grads(m, osd, "ffm.")
+    assert cosine(a.grad, ao.grad) > 0.99 and cosine(b.grad, bo.grad) > 0.99
+
+    sd = rounded({k[len("conv_out16."):]: v for k, v in full.items() if k.startswith("conv_out16.")})
+    hd = load_oracle_state(BiSeNetOutput(128, 64, 19), sd).to(DEV).train()
+    x = fcp.clone().requires_grad_(True)
+    y = hd(cl(x))
+    osd = {"h." + k: v for k, v in to_device(sd, DEV, True).items()}
+    xo = fcp.clone().requires_grad_(True)
+    yo = O.seg_head(osd, "h", xo, True)
+    assert y.shape == yo.shape and rel_l2(y, yo) < 2e-2
+    dy = torch.randn(yo.shape, generator=g).to(DEV)
+    y.backward(dy)
+    yo.backward(dy)
+    check_grads(hd, osd, "h.")
+    assert cosine(x.grad, xo.grad) > 0.99
