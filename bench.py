@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star hot path: the adversarial domain-adaptation train step
+(BiSeNet-STDC813 + discriminator, forward/backward/update) on synthetic Cityscapes/GTAV-shaped data.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+Prints ONE JSON line (rank 0).  `value` is whole-job source images per second with the inputs
+resident in HBM; `e2e` is the same step driven from pinned HOST buffers through the public API
+(H2D copies and the D2H read of the losses inside the timed region).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, BATCH, NCLS = 512, 1024, 8, 19
+WORKLOADS = {
+    "da_dense": "config[2]: adversarial DA train step, FCDiscriminator, 512x1024, batch 8/GPU",
+    "da_dwsep": "config[3]: DA train step, DepthWiseSepFCDiscriminator, 512x1024, batch 8/GPU",
+    "da_dwsep_bn": "config[3]: DA train step, DepthWiseSepBNFCDiscriminator, 512x1024, batch 8/GPU",
+    "supervised": "config[1]: supervised train step (3x CE), 720x1280, batch 8",
+}
+# algorithmic dense-conv FLOPs per (source, target) pair / image
+GFLOP_PER_UNIT = {"da_dense": 444.87, "da_dwsep": 226.0, "da_dwsep_bn": 226.0, "supervised": 186.14}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="da_dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-kernel time table here")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_da_step_rate(workload, batch, steps, warmup, threads=None):
+    """Oracle port of the reference step (fp32, CPU, all host threads): images per second."""
+    import torch
+    from oracle import segnet_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    kind = {"da_dense": "dense", "da_dwsep": "dwsep", "da_dwsep_bn": "dwsep_bn"}.get(workload)
+    h, w = (720, 1280) if workload == "supervised" else (H, W)
+    g = torch.Generator().manual_seed(0)
+    seg = O.clone_state(O.make_bisenet_state(seed=0), requires_grad=True)
+    opt = torch.optim.SGD([v for v in seg.values() if v.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    x = torch.randn(batch, 3, h, w, generator=g)
+    xt = torch.randn(batch, 3, h, w, generator=g)
+    labels = torch.randint(0, NCLS, (batch, h, w), generator=g)
+    if kind:
+        dsd = O.clone_state(O.make_discriminator_state(kind, seed=1), requires_grad=True)
+        opt_d = torch.optim.Adam([v for v in dsd.values() if v.requires_grad], lr=1e-3, betas=(0.9, 0.99))
+
+    def step():
+        if kind:
+            O.da_step(seg, dsd, kind, x, labels, xt, opt, opt_d)
+        else:
+            opt.zero_grad()
+            loss, _ = O.supervised_loss(seg, x, labels, True)
+            loss.backward()
+            opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = args.steps or 2
+    warmup = args.warmup if args.warmup is not None else 1
+    batch = 2  # bounded sample: BatchNorm on the 1x1 pooled maps needs >= 2 images per step
+    rate, ms, threads = cpu_da_step_rate(args.workload, batch, steps, warmup)
+    sample = "%d-image %s step(s) of the oracle port (fp32, torch CPU), %d warm-up" % (batch, args.workload, warmup)
+    line = {
+        "impl": "reference", "metric": "da_train_step_img_per_s" if args.workload != "supervised" else "train_step_img_per_s",
+        "value": rate, "unit": "img/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "batch_per_step": batch, "height": H, "width": W},
+        "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from dasemanticsegmentationaml_b200 import _lib, build
+    from dasemanticsegmentationaml_b200 import train as T
+    from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, DepthWiseSepFCDiscriminator,
+                                                      DepthWiseSepBNFCDiscriminator)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.ensure_device(local)
+
+    steps = args.steps or 20
+    warmup = max(3, args.warmup if args.warmup is not None else 5)
+    nb = args.batch
+    h, w = (720, 1280) if args.workload == "supervised" else (H, W)
+
+    torch.manual_seed(0)  # identical initial weights on every rank
+    model = BiSeNet("STDCNet813", NCLS).to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    model_d = opt_d = None
+    if args.workload != "supervised":
+        cls = {"da_dense": FCDiscriminator, "da_dwsep": DepthWiseSepFCDiscriminator,
+               "da_dwsep_bn": DepthWiseSepBNFCDiscriminator}[args.workload]
+        model_d = cls(NCLS).to(dev)
+        opt_d = torch.optim.Adam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99))
+
+    g = torch.Generator().manual_seed(100 + rank)  # rank-dependent data
+    host = {
+        "images": torch.randn(nb, 3, h, w, generator=g).pin_memory(),
+        "labels": torch.randint(0, NCLS + 1, (nb, h, w), generator=g).pin_memory(),
+        "images_t": torch.randn(nb, 3, h, w, generator=g).pin_memory(),
+    }
+    host["labels"][host["labels"] == NCLS] = 255
+    devbuf = {k: v.to(dev) for k, v in host.items()}
+
+    def step(buf):
+        if model_d is None:
+            return (T.train_step(model, opt, buf["images"], buf["labels"]),)
+        return T.train_da_step(model, model_d, opt, opt_d, buf["images"], buf["labels"], buf["images_t"])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(devbuf)
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    sync_all()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses = step(devbuf)
+    e1.record()
+    sync_all()
+    launches = _lib.launch_count - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clk = clocks.stop() if clocks else None
+    loss_vals = [float(v) for v in losses]
+
+    # ---- timed region 2: end to end from pinned host buffers -------------------------------------
+    stage = {k: torch.empty_like(v) for k, v in devbuf.items()}
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if model_d is not None or k != "images_t")
+    sync_all()
+    e0.record()
+    for _ in range(steps):
+        for k in stage:
+            if model_d is None and k == "images_t":
+                continue
+            stage[k].copy_(host[k], non_blocking=True)
+        out = step(stage)
+        host_losses = torch.stack([o.float() for o in out]).cpu()  # D2H read of the step's result
+    e1.record()
+    sync_all()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item())
+
+    # ---- per-kernel profile of ONE step (CUDA events around every launch of ours) -----------------
+    prof = None
+    if not args.no_profile:
+        sync_all()
+        _lib.profile_start()
+        step(devbuf)
+        prof = _lib.profile_stop()
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    unit_per_step = nb * world
+    value = unit_per_step * steps / (ms_total / 1e3)
+    line = {
+        "metric": "da_train_step_img_per_s" if model_d is not None else "train_step_img_per_s",
+        "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": nb, "height": h, "width": w,
+                   "classes": NCLS, "parallelism": "dp%d" % world,
+                   "l2": "inputs (134 MB/step) and activations (>1 GB/step) exceed the 126 MB L2; no explicit flush",
+                   "pairs_per_s": value if model_d is not None else None,
+                   "losses_last_step": loss_vals},
+        "e2e": {"value": unit_per_step * steps / (e2e_ms / 1e3), "unit": "img/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(out), "ms_per_step": e2e_ms / steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+    }
+    step_tf = GFLOP_PER_UNIT[args.workload] * nb / 1e3 / (ms_total / steps / 1e3)  # TFLOP/s per GPU, whole step
+    line["config"]["step_algorithmic_tflops_per_gpu"] = step_tf
+    if prof:
+        conv = [v for k, v in prof.items() if k in ("b200_conv_igemm",)]
+        tot_ms = sum(v["ms"] for v in prof.values())
+        table = sorted(((k, v["calls"], v["ms"], v["flops"]) for k, v in prof.items()), key=lambda r: -r[2])
+        if conv and conv[0]["ms"] > 0:
+            c = conv[0]
+            ach = c["flops"] / (c["ms"] / 1e3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
+                                "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                                "frac": ach / peaks["tf_sustained"], "traffic": None,
+                                "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                                "launches_per_step": c["calls"], "avg_launch_ms": c["ms"] / c["calls"],
+                                "share_of_kernel_time": c["ms"] / tot_ms}
+        line["kernel_time_ms_per_step"] = {k: round(ms_, 3) for k, _, ms_, _ in table}
+        if "b200_conv_wgrad" in prof and prof["b200_conv_wgrad"]["ms"] > 0:
+            wg = prof["b200_conv_wgrad"]
+            line["wgrad_tflops"] = wg["flops"] / (wg["ms"] / 1e3) / 1e12
+        if args.profile_json:
+            with open(args.profile_json, "w") as f:
+                json.dump({k: v for k, v in prof.items()}, f, indent=1)
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            rate, cms, threads = cpu_da_step_rate(args.workload, 2, 1, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
+                                    "sample": "one 2-image step of the oracle port (fp32 torch CPU) after one warm-up step, %.1f s" % (cms / 1e3)}
+        except Exception as ex:  # the baseline is informational; never lose the GPU line over it
+            line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,53 @@ def check(rc, what=""):
         raise B200Error("%s failed (%d): %s" % (what or "libb200seg call", rc, last_error()))
 
 
+# kernels launched per entry point when it is more than one (for the launch counter)
+_MULTI = {"b200_radix_select_desc": 9, "b200_ohem_reduce": 2, "b200_fc_small_bwd": 2}
+launch_count = 0      # kernels launched through this binding since import
+_profile = None       # None, or a list of (name, start_event, end_event, flops, bytes)
+
+
+def call(name, *args, flops=0.0, nbytes=0.0):
+    """Invoke an entry point on the current stream, raise on error, count its launches and, while
+    profiling, bracket it with CUDA events on the launching stream."""
+    global launch_count
+    fn = getattr(lib(), name)
+    if _profile is None:
+        rc = fn(*args)
+    else:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _profile.append((name, e0, e1, flops, nbytes))
+    if rc != 0:
+        raise B200Error("%s failed (%d): %s" % (name, rc, last_error()))
+    launch_count += _MULTI.get(name, 1)
+
+
+def profile_start():
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """-> {name: dict(calls, ms, flops, bytes)} for the calls made since profile_start()."""
+    global _profile
+    import torch
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1, flops, nbytes in _profile or []:
+        a = agg.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+        a["calls"] += 1
+        a["ms"] += e0.elapsed_time(e1)
+        a["flops"] += flops
+        a["bytes"] += nbytes
+    _profile = None
+    return agg
+
+
 def ensure_device(index):
     """Refuse to run on anything but an sm_100 device (no multi-arch dispatch by design)."""
     if index in _checked_devices:

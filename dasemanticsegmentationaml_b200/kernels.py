@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import c_float, c_int, c_int64, check, int_array, lib, ptr, stream
+from ._lib import c_float, c_int, c_int64, call, check, int_array, lib, ptr, stream
 
 
 def round_up(v, m):
@@ -40,72 +40,104 @@ def pack_filter(weight, transpose=False):
     w = weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    check(lib().b200_pack_filter(ptr(w), ptr(out), c_int(cout), c_int(cin), c_int(r * s),
+    call("b200_pack_filter", ptr(w), ptr(out), c_int(cout), c_int(cin), c_int(r * s),
                                  c_int(rows_pad), c_int(inner_pad), c_int(1 if transpose else 0),
-                                 stream()), "b200_pack_filter")
+                                 stream())
     return out
 
 
 # ------------------------------------------------------------------ geometry
+class Geometry(object):
+    """Tap tables of one implicit-GEMM launch, with the ctypes arrays pre-built (cached per shape)."""
+
+    def __init__(self, classes, in_stride, out_stride, hout, wout):
+        self.classes, self.in_stride, self.out_stride, self.Hout, self.Wout = classes, in_stride, out_stride, hout, wout
+        self.tmax = max(len(c["taps"]) for c in classes)
+        flat = []
+        for c in classes:
+            for t in range(self.tmax):
+                flat += list(c["taps"][t]) if t < len(c["taps"]) else [0, 0, 0]
+        self.c_n = c_int(len(classes))
+        self.c_ho = int_array([c["Ho"] for c in classes])
+        self.c_wo = int_array([c["Wo"] for c in classes])
+        self.c_oa = int_array([c["oa"] for c in classes])
+        self.c_ob = int_array([c["ob"] for c in classes])
+        self.c_nt = int_array([len(c["taps"]) for c in classes])
+        self.c_taps = int_array(flat)
+        self.px_taps = sum(c["Ho"] * c["Wo"] * len(c["taps"]) for c in classes)
+
+    def __getitem__(self, key):  # dict-style access used by callers/tests
+        return getattr(self, key)
+
+
+_geom_cache = {}
+
+
 def fwd_geometry(hin, win, r, s, stride, pad):
-    ho = (hin + 2 * pad - r) // stride + 1
-    wo = (win + 2 * pad - s) // stride + 1
-    taps = [(i - pad, j - pad, i * s + j) for i in range(r) for j in range(s)]
-    return dict(classes=[dict(Ho=ho, Wo=wo, oa=0, ob=0, taps=taps)], in_stride=stride, out_stride=1,
-                Hout=ho, Wout=wo)
+    key = ("f", hin, win, r, s, stride, pad)
+    g = _geom_cache.get(key)
+    if g is None:
+        ho = (hin + 2 * pad - r) // stride + 1
+        wo = (win + 2 * pad - s) // stride + 1
+        taps = [(i - pad, j - pad, i * s + j) for i in range(r) for j in range(s)]
+        g = _geom_cache[key] = Geometry([dict(Ho=ho, Wo=wo, oa=0, ob=0, taps=taps)], stride, 1, ho, wo)
+    return g
 
 
 def dgrad_geometry(hin, win, r, s, stride, pad):
-    """Geometry of dx[N,hin,win,Cin] = conv_transpose(dz); dz is the kernel's *input*."""
+    """Geometry of dx[N,hin,win,Cin] = conv_transpose(dz); dz is the kernel's *input*.  A stride-2
+    conv splits into the four output-parity classes, each a stride-1 conv over dz with its own taps."""
+    key = ("d", hin, win, r, s, stride, pad)
+    g = _geom_cache.get(key)
+    if g is not None:
+        return g
     if stride == 1:
         taps = [(pad - i, pad - j, i * s + j) for i in range(r) for j in range(s)]
-        return dict(classes=[dict(Ho=hin, Wo=win, oa=0, ob=0, taps=taps)], in_stride=1, out_stride=1,
-                    Hout=hin, Wout=win)
-    assert stride == 2
-    classes = []
-    for a in range(2):
-        for b in range(2):
-            taps = [((a + pad - i) // 2, (b + pad - j) // 2, i * s + j)
-                    for i in range(r) if (a + pad - i) % 2 == 0
-                    for j in range(s) if (b + pad - j) % 2 == 0]
-            hc, wc = (hin - a + 1) // 2, (win - b + 1) // 2
-            if not taps:
-                raise ValueError("strided dgrad class without taps (1x1 stride-2 conv?)")
-            if hc > 0 and wc > 0:
-                classes.append(dict(Ho=hc, Wo=wc, oa=a, ob=b, taps=taps))
-    return dict(classes=classes, in_stride=1, out_stride=2, Hout=hin, Wout=win)
+        g = Geometry([dict(Ho=hin, Wo=win, oa=0, ob=0, taps=taps)], 1, 1, hin, win)
+    else:
+        assert stride == 2
+        classes = []
+        for a in range(2):
+            for b in range(2):
+                taps = [((a + pad - i) // 2, (b + pad - j) // 2, i * s + j)
+                        for i in range(r) if (a + pad - i) % 2 == 0
+                        for j in range(s) if (b + pad - j) % 2 == 0]
+                hc, wc = (hin - a + 1) // 2, (win - b + 1) // 2
+                if not taps:
+                    raise ValueError("strided dgrad class without taps (1x1 stride-2 conv?)")
+                if hc > 0 and wc > 0:
+                    classes.append(dict(Ho=hc, Wo=wc, oa=a, ob=b, taps=taps))
+        g = Geometry(classes, 1, 2, hin, win)
+    _geom_cache[key] = g
+    return g
 
 
-def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_tile=0):
-    """out[N,Hout,Wout,rows_pad] = implicit-GEMM conv of x with a packed filter (see pack_filter)."""
+def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_tile=0, k_real=None, n_real=None):
+    """out[N,Hout,Wout,rows_pad] = implicit-GEMM conv of x with a packed filter (see pack_filter).
+    k_real / n_real: un-padded reduction / output channel counts (for the algorithmic FLOP count)."""
     n, hin, win, cin, in_ld = _nhwc_meta(x)
     n2, hout, wout, cout_view, out_ld = _nhwc_meta(out)
     rows_pad, n_slabs, cin_pad = filt.shape
-    assert n2 == n and hout == geom["Hout"] and wout == geom["Wout"], "output shape mismatch"
+    assert n2 == n and hout == geom.Hout and wout == geom.Wout, "output shape mismatch"
     assert cout_view == rows_pad, "output view must expose exactly the packed filter's rows"
     assert x.dtype == torch.bfloat16 and filt.dtype == torch.bfloat16
     out_f32 = 1 if out.dtype == torch.float32 else 0
     if not out_f32:
         assert out.dtype == torch.bfloat16
-    classes = geom["classes"]
-    tmax = max(len(c["taps"]) for c in classes)
-    flat = []
-    for c in classes:
-        for t in range(tmax):
-            flat += list(c["taps"][t]) if t < len(c["taps"]) else [0, 0, 0]
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.dim() == 2 and stats.shape[0] == 2
-    check(lib().b200_conv_igemm(
-        ptr(x), c_int(in_ld), c_int(0), c_int(cin), c_int(n), c_int(hin), c_int(win),
-        ptr(filt), c_int(rows_pad), c_int(cin_pad), c_int(n_slabs),
-        ptr(out), c_int(out_ld), c_int(0), c_int(hout), c_int(wout), c_int(out_f32),
-        c_int(len(classes)), int_array([c["Ho"] for c in classes]), int_array([c["Wo"] for c in classes]),
-        int_array([c["oa"] for c in classes]), int_array([c["ob"] for c in classes]),
-        int_array([len(c["taps"]) for c in classes]), int_array(flat), c_int(tmax),
-        c_int(geom["in_stride"]), c_int(geom["out_stride"]), ptr(bias), c_int(act), c_float(slope),
-        ptr(stats), c_int(0 if stats is None else stats.shape[1]), c_int(bn_tile), stream()),
-        "b200_conv_igemm")
+    flops = 2.0 * geom.px_taps * n * (k_real or min(cin, cin_pad)) * (n_real or rows_pad)
+    call("b200_conv_igemm",
+         ptr(x), c_int(in_ld), c_int(0), c_int(cin), c_int(n), c_int(hin), c_int(win),
+         ptr(filt), c_int(rows_pad), c_int(cin_pad), c_int(n_slabs),
+         ptr(out), c_int(out_ld), c_int(0), c_int(hout), c_int(wout), c_int(out_f32),
+         geom.c_n, geom.c_ho, geom.c_wo, geom.c_oa, geom.c_ob, geom.c_nt, geom.c_taps, c_int(geom.tmax),
+         c_int(geom.in_stride), c_int(geom.out_stride), ptr(bias), c_int(act), c_float(slope),
+         ptr(stats), c_int(0 if stats is None else stats.shape[1]), c_int(bn_tile), stream(), flops=flops)
     return out
+
+
+_wgrad_taps = {}
 
 
 def conv_wgrad(dz, x, dw, r, s, stride, pad):
@@ -114,15 +146,18 @@ def conv_wgrad(dz, x, dw, r, s, stride, pad):
     n2, hin, win, _, x_ld = _nhwc_meta(x)
     cout, cin = dw.shape[0], dw.shape[1]
     assert n2 == n and dw.dtype == torch.float32 and dw.is_contiguous()
-    taps = []
-    for i in range(r):
-        for j in range(s):
-            taps += [i - pad, j - pad, i * s + j]
-    check(lib().b200_conv_wgrad(
+    taps = _wgrad_taps.get((r, s, pad))
+    if taps is None:
+        flat = []
+        for i in range(r):
+            for j in range(s):
+                flat += [i - pad, j - pad, i * s + j]
+        taps = _wgrad_taps[(r, s, pad)] = int_array(flat)
+    call("b200_conv_wgrad", 
         ptr(dz), c_int(dz_ld), c_int(0), c_int(cout), c_int(n), c_int(ho), c_int(wo),
         ptr(x), c_int(x_ld), c_int(0), c_int(cin), c_int(hin), c_int(win),
-        c_int(r * s), int_array(taps), c_int(r * s), c_int(stride), ptr(dw), stream()),
-        "b200_conv_wgrad")
+        c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), stream(),
+        flops=2.0 * n * ho * wo * r * s * cout * cin)
     return dw
 
 
@@ -132,16 +167,16 @@ def fast_hist_accumulate(label, pred, n, hist, bad):
     assert label.numel() == pred.numel()
     label = label.contiguous()
     pred = pred.contiguous()
-    check(lib().b200_fast_hist(ptr(label), c_int(label.element_size()), ptr(pred),
+    call("b200_fast_hist", ptr(label), c_int(label.element_size()), ptr(pred),
                                c_int(pred.element_size()), c_int64(label.numel()), c_int(n),
-                               ptr(hist), ptr(bad), stream()), "b200_fast_hist")
+                               ptr(hist), ptr(bad), stream())
     return hist
 
 
 def count_equal(label, pred, out):
-    check(lib().b200_count_equal(ptr(label), c_int(label.element_size()), ptr(pred),
+    call("b200_count_equal", ptr(label), c_int(label.element_size()), ptr(pred),
                                  c_int(pred.element_size()), c_int64(label.numel()), ptr(out),
-                                 stream()), "b200_count_equal")
+                                 stream())
     return out
 
 
@@ -156,135 +191,131 @@ def _pix(t):
 
 def channel_stats(x, stats):
     npix, c, ld = _pix(x)
-    check(lib().b200_channel_stats(ptr(x), c_int(ld), c_int(c), c_int64(npix), ptr(stats), stream()),
-          "b200_channel_stats")
+    call("b200_channel_stats", ptr(x), c_int(ld), c_int(c), c_int64(npix), ptr(stats), stream())
 
 
 def bn_finalize(stats, count, gamma, beta, running_mean, running_var, training, scale, shift,
                 mean, rstd, momentum=0.1, eps=1e-5):
     c = scale.numel()
-    check(lib().b200_bn_finalize(ptr(stats), c_int(c), c_float(count), ptr(gamma), ptr(beta),
+    call("b200_bn_finalize", ptr(stats), c_int(c), c_float(count), ptr(gamma), ptr(beta),
                                  ptr(running_mean), ptr(running_var), c_float(momentum), c_float(eps),
                                  c_int(1 if training else 0), ptr(scale), ptr(shift), ptr(mean),
-                                 ptr(rstd), stream()), "b200_bn_finalize")
+                                 ptr(rstd), stream())
 
 
 def bn_act_apply(x, y, scale, shift, act, slope=0.0):
     npix, c, x_ld = _pix(x)
     npix2, c2, y_ld = _pix(y)
     assert npix == npix2 and c == c2
-    check(lib().b200_bn_act_apply(ptr(x), c_int(x_ld), ptr(y), c_int(y_ld), c_int(c), c_int64(npix),
-                                  ptr(scale), ptr(shift), c_int(act), c_float(slope), stream()),
-          "b200_bn_act_apply")
+    call("b200_bn_act_apply", ptr(x), c_int(x_ld), ptr(y), c_int(y_ld), c_int(c), c_int64(npix),
+                                  ptr(scale), ptr(shift), c_int(act), c_float(slope), stream())
 
 
 def bn_act_bwd_reduce(dy1, dy2, z, scale, shift, mean, rstd, act, slope, red):
     npix, c, z_ld = _pix(z)
-    check(lib().b200_bn_act_bwd_reduce(
+    call("b200_bn_act_bwd_reduce", 
         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
         ptr(z), c_int(z_ld), c_int(c), c_int64(npix), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
-        c_int(act), c_float(slope), ptr(red), stream()), "b200_bn_act_bwd_reduce")
+        c_int(act), c_float(slope), ptr(red), stream())
 
 
 def bn_act_bwd_apply(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope):
     npix, c, z_ld = _pix(z)
-    check(lib().b200_bn_act_bwd_apply(
+    call("b200_bn_act_bwd_apply", 
         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
         ptr(z), c_int(z_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), ptr(scale),
         ptr(shift), ptr(mean), ptr(rstd), ptr(red), c_float(1.0 / npix), c_int(act), c_float(slope),
-        stream()), "b200_bn_act_bwd_apply")
+        stream())
 
 
 def act_bwd_bias(dy1, dy2, a, dz, act, slope, dbias):
     npix, c, a_ld = _pix(a)
-    check(lib().b200_act_bwd_bias(
+    call("b200_act_bwd_bias", 
         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
         ptr(a), c_int(a_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), c_int(act),
-        c_float(slope), ptr(dbias), stream()), "b200_act_bwd_bias")
+        c_float(slope), ptr(dbias), stream())
 
 
 # ------------------------------------------------------------------ depthwise / stem
 def dwconv_s2_fwd(x, k, w, bias, z, pool, act, slope, stats):
     n, h, wd, c, x_ld = _nhwc_meta(x)
-    check(lib().b200_dwconv_s2_fwd(
+    call("b200_dwconv_s2_fwd", 
         ptr(x), c_int(x_ld), c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(bias),
         ptr(z), c_int(z.stride(2)), ptr(pool), c_int(0 if pool is None else pool.stride(2)),
-        c_int(act), c_float(slope), ptr(stats), stream()), "b200_dwconv_s2_fwd")
+        c_int(act), c_float(slope), ptr(stats), stream())
 
 
 def dwconv_s2_dgrad(dz, dpool, k, w, dx):
     n, h, wd, c, dx_ld = _nhwc_meta(dx)
-    check(lib().b200_dwconv_s2_dgrad(
+    call("b200_dwconv_s2_dgrad", 
         ptr(dz), c_int(dz.stride(2)), ptr(dpool), c_int(0 if dpool is None else dpool.stride(2)),
-        c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(dx), c_int(dx_ld), stream()),
-        "b200_dwconv_s2_dgrad")
+        c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(dx), c_int(dx_ld), stream())
 
 
 def dwconv_s2_wgrad(dz, x, k, dw, dbias):
     n, h, wd, c, x_ld = _nhwc_meta(x)
-    check(lib().b200_dwconv_s2_wgrad(
+    call("b200_dwconv_s2_wgrad", 
         ptr(dz), c_int(dz.stride(2)), ptr(x), c_int(x_ld), c_int(n), c_int(h), c_int(wd), c_int(c),
-        c_int(k), ptr(dw), ptr(dbias), stream()), "b200_dwconv_s2_wgrad")
+        c_int(k), ptr(dw), ptr(dbias), stream())
 
 
 def stem_fwd(img, w, z, stats):
     n, _, h, wd = img.shape
     assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
-    check(lib().b200_stem_fwd(ptr(img), c_int(n), c_int(h), c_int(wd), ptr(w), ptr(z),
-                              c_int(z.stride(2)), ptr(stats), stream()), "b200_stem_fwd")
+    call("b200_stem_fwd", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(w), ptr(z),
+                              c_int(z.stride(2)), ptr(stats), stream())
 
 
 def stem_wgrad(img, dz, dw):
     n, _, h, wd = img.shape
-    check(lib().b200_stem_wgrad(ptr(img), c_int(n), c_int(h), c_int(wd), ptr(dz), c_int(dz.stride(2)),
-                                ptr(dw), stream()), "b200_stem_wgrad")
+    call("b200_stem_wgrad", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(dz), c_int(dz.stride(2)),
+                                ptr(dw), stream())
 
 
 # ------------------------------------------------------------------ attention
 def pool_sum(x, out):
     n, h, w, c, ld = _nhwc_meta(x)
-    check(lib().b200_pool_sum(ptr(x), c_int(ld), c_int(n), c_int(h * w), c_int(c), ptr(out), stream()),
-          "b200_pool_sum")
+    call("b200_pool_sum", ptr(x), c_int(ld), c_int(n), c_int(h * w), c_int(c), ptr(out), stream())
 
 
 def fc_small_fwd(inp, in_scale, W, bn, training, act, pre, out, mean, rstd, momentum=0.1, eps=1e-5):
     n, cin = inp.shape
     co = W.shape[0]
     gamma, beta, rm, rv = bn if bn is not None else (None, None, None, None)
-    check(lib().b200_fc_small_fwd(
+    call("b200_fc_small_fwd", 
         ptr(inp), c_float(in_scale), c_int(n), c_int(cin), c_int(co), ptr(W),
         c_int(0 if bn is None else 1), ptr(gamma), ptr(beta), ptr(rm), ptr(rv), c_float(momentum),
         c_float(eps), c_int(1 if training else 0), c_int(act), ptr(pre), ptr(out), ptr(mean), ptr(rstd),
-        stream()), "b200_fc_small_fwd")
+        stream())
 
 
 def fc_small_bwd(dout, out, pre, inp, in_scale, W, has_bn, training, gamma, mean, rstd, act, scratch,
                  dW, dgamma, dbeta, din, accumulate_din=False):
     n, cin = inp.shape
     co = W.shape[0]
-    check(lib().b200_fc_small_bwd(
+    call("b200_fc_small_bwd", 
         ptr(dout), ptr(out), ptr(pre), ptr(inp), c_float(in_scale), c_int(n), c_int(cin), c_int(co),
         ptr(W), c_int(1 if has_bn else 0), c_int(1 if training else 0), ptr(gamma), ptr(mean), ptr(rstd),
         c_int(act), ptr(scratch), ptr(dW), ptr(dgamma), ptr(dbeta), ptr(din),
-        c_int(1 if accumulate_din else 0), stream()), "b200_fc_small_bwd")
+        c_int(1 if accumulate_din else 0), stream())
 
 
 def scale_add_bcast(a, s, s_plus, v, v_scale, t, out):
     n, hs, ws, c, a_ld = _nhwc_meta(a)
     n2, ho, wo, c2, out_ld = _nhwc_meta(out)
     assert n == n2 and c == c2
-    check(lib().b200_scale_add_bcast(
+    call("b200_scale_add_bcast", 
         ptr(a), c_int(a_ld), c_int(hs), c_int(ws), ptr(s), c_float(s_plus), ptr(v), c_float(v_scale),
         ptr(t), c_int(0 if t is None else t.stride(2)), ptr(out), c_int(out_ld), c_int(n), c_int(ho),
-        c_int(wo), c_int(c), stream()), "b200_scale_add_bcast")
+        c_int(wo), c_int(c), stream())
 
 
 def upsum_dot_reduce(dout, b, dsum, hs, ws, dot, vsum):
     n, ho, wo, c, dout_ld = _nhwc_meta(dout)
-    check(lib().b200_upsum_dot_reduce(
+    call("b200_upsum_dot_reduce", 
         ptr(dout), c_int(dout_ld), c_int(ho), c_int(wo), ptr(b), c_int(0 if b is None else b.stride(2)),
         ptr(dsum), c_int(0 if dsum is None else dsum.stride(2)), c_int(n), c_int(hs), c_int(ws),
-        c_int(c), ptr(dot), ptr(vsum), stream()), "b200_upsum_dot_reduce")
+        c_int(c), ptr(dot), ptr(vsum), stream())
 
 
 # ------------------------------------------------------------------ up-sampling / losses
@@ -295,67 +326,64 @@ def upsample_fwd(lr, H, W, n_classes, mode, out=None, out_flag=0, p_ld=0, labels
                  acc=None, loss_map=None):
     n, h_lr, w_lr, ld = lr.shape
     assert lr.dtype == torch.float32 and lr.is_contiguous()
-    check(lib().b200_upsample_fwd(
+    call("b200_upsample_fwd", 
         ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
         c_int(mode), ptr(out), c_int(out_flag), c_int(p_ld), ptr(labels), c_int(ignore_index), ptr(acc),
-        ptr(loss_map), stream()), "b200_upsample_fwd")
+        ptr(loss_map), stream())
 
 
 def upsample_bwd(lr, H, W, n_classes, mode, d_lr, grad_in=None, grad_is_bf16=0, p_ld=0, labels=None,
                  ignore_index=255, pixel_weight=None, coef_num=None, coef_den=None, coef_scale=1.0):
     n, h_lr, w_lr, ld = lr.shape
-    check(lib().b200_upsample_bwd(
+    call("b200_upsample_bwd", 
         ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
         c_int(mode), ptr(grad_in), c_int(grad_is_bf16), c_int(p_ld), ptr(labels), c_int(ignore_index),
-        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), stream()),
-        "b200_upsample_bwd")
+        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), stream())
 
 
 def radix_select_desc(x, rank, state, hist):
-    check(lib().b200_radix_select_desc(ptr(x), c_int64(x.numel()), c_int64(rank), ptr(state), ptr(hist),
-                                       stream()), "b200_radix_select_desc")
+    call("b200_radix_select_desc", ptr(x), c_int64(x.numel()), c_int64(rank), ptr(state), ptr(hist),
+                                       stream())
 
 
 def ohem_reduce(x, state, threshold, keep_num, sums, out):
-    check(lib().b200_ohem_reduce(ptr(x), c_int64(x.numel()), ptr(state), c_float(threshold),
-                                 c_int64(keep_num), ptr(sums), ptr(out), stream()), "b200_ohem_reduce")
+    call("b200_ohem_reduce", ptr(x), c_int64(x.numel()), ptr(state), c_float(threshold),
+                                 c_int64(keep_num), ptr(sums), ptr(out), stream())
 
 
 def ohem_weights(x, sel, wout):
-    check(lib().b200_ohem_weights(ptr(x), c_int64(x.numel()), ptr(sel), ptr(wout), stream()),
-          "b200_ohem_weights")
+    call("b200_ohem_weights", ptr(x), c_int64(x.numel()), ptr(sel), ptr(wout), stream())
 
 
 def bce_const_fwd(x, target, out):
-    check(lib().b200_bce_const_fwd(ptr(x), c_int(x.numel()), c_float(target), ptr(out), stream()),
-          "b200_bce_const_fwd")
+    call("b200_bce_const_fwd", ptr(x), c_int(x.numel()), c_float(target), ptr(out), stream())
 
 
 def bce_const_bwd(x, target, gscale, gmul, dx):
-    check(lib().b200_bce_const_bwd(ptr(x), c_int(x.numel()), c_float(target), ptr(gscale), c_float(gmul),
-                                   ptr(dx), stream()), "b200_bce_const_bwd")
+    call("b200_bce_const_bwd", ptr(x), c_int(x.numel()), c_float(target), ptr(gscale), c_float(gmul),
+                                   ptr(dx), stream())
 
 
 # ------------------------------------------------------------------ discriminator classifier
 def classifier_fwd(x, w, bias, out):
     n, h, wd, c, ld = _nhwc_meta(x)
-    check(lib().b200_classifier_fwd(ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w),
-                                    ptr(bias), ptr(out), stream()), "b200_classifier_fwd")
+    call("b200_classifier_fwd", ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w),
+                                    ptr(bias), ptr(out), stream())
 
 
 def classifier_dgrad(dout, w, dx):
     n, h, wd, c, ld = _nhwc_meta(dx)
-    check(lib().b200_classifier_dgrad(ptr(dout), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w), ptr(dx),
-                                      c_int(ld), stream()), "b200_classifier_dgrad")
+    call("b200_classifier_dgrad", ptr(dout), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w), ptr(dx),
+                                      c_int(ld), stream())
 
 
 def classifier_wgrad(dout, x, dw, dbias):
     n, h, wd, c, ld = _nhwc_meta(x)
-    check(lib().b200_classifier_wgrad(ptr(dout), ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c),
-                                      ptr(dw), ptr(dbias), stream()), "b200_classifier_wgrad")
+    call("b200_classifier_wgrad", ptr(dout), ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c),
+                                      ptr(dw), ptr(dbias), stream())
 
 
 def cast_f32_bf16(x, y):
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
-    check(lib().b200_cast_f32_bf16(ptr(x), ptr(y), c_int64(x.numel()), stream()), "b200_cast_f32_bf16")
+    call("b200_cast_f32_bf16", ptr(x), ptr(y), c_int64(x.numel()), stream())
     return y

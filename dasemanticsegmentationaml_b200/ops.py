@@ -28,9 +28,8 @@ def packed_filter(weight, transpose):
         buf = hit[1]  # repack in place: stable pointer for graphs, no allocator churn
         cout, cin, r, s = weight.shape
         w = weight.detach()
-        K.check(K.lib().b200_pack_filter(K.ptr(w), K.ptr(buf), K.c_int(cout), K.c_int(cin),
-                                         K.c_int(r * s), K.c_int(buf.shape[0]), K.c_int(buf.shape[2]),
-                                         K.c_int(1 if transpose else 0), K.stream()), "b200_pack_filter")
+        K.call("b200_pack_filter", K.ptr(w), K.ptr(buf), K.c_int(cout), K.c_int(cin), K.c_int(r * s),
+               K.c_int(buf.shape[0]), K.c_int(buf.shape[2]), K.c_int(1 if transpose else 0), K.stream())
     else:
         buf = K.pack_filter(weight, transpose)
     _pack_cache[key] = (ver, buf)
@@ -89,8 +88,9 @@ def conv_raw_fwd(x, weight, stride, pad, stats=None, bias=None, act=K.ACT_NONE, 
     geom = K.fwd_geometry(h, w, r, s, stride, pad)
     filt = packed_filter(weight, False)
     if out is None:
-        out = torch.empty((n, geom["Hout"], geom["Wout"], filt.shape[0]), dtype=out_dtype, device=x.device)
-    K.conv_igemm(x, filt, out, geom, bias=bias, act=act, slope=slope, stats=stats)
+        out = torch.empty((n, geom.Hout, geom.Wout, filt.shape[0]), dtype=out_dtype, device=x.device)
+    K.conv_igemm(x, filt, out, geom, bias=bias, act=act, slope=slope, stats=stats,
+                 k_real=weight.shape[1], n_real=weight.shape[0])
     return out
 
 
@@ -100,9 +100,7 @@ def conv_dgrad(dz, weight, stride, pad, hin, win):
     geom = K.dgrad_geometry(hin, win, r, s, stride, pad)
     filt_t = packed_filter(weight, True)
     dx = torch.empty((dz.shape[0], hin, win, filt_t.shape[0]), dtype=BF16, device=dz.device)
-    if filt_t.shape[2] > dz.shape[3]:
-        pass  # TMA zero-fills the channels beyond dz's view
-    K.conv_igemm(dz, filt_t, dx, geom)
+    K.conv_igemm(dz, filt_t, dx, geom, k_real=weight.shape[0], n_real=weight.shape[1])
     return dx
 
 
