@@ -5,6 +5,7 @@
 
 #include "ptx.cuh"
 #include "status.h"
+#include "b200seg.h"
 
 namespace b200 {
 

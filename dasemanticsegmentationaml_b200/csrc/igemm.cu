@@ -15,6 +15,7 @@
 #include "igemm.cuh"
 #include "ptx.cuh"
 #include "status.h"
+#include "b200seg.h"
 
 namespace b200 {
 

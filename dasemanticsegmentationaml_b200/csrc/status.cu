@@ -1,4 +1,5 @@
 #include "status.h"
+#include "b200seg.h"
 
 #include <stdarg.h>
 #include <stdio.h>

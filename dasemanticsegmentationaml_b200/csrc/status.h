@@ -4,11 +4,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#define B200_OK 0
-#define B200_EINVAL (-1)   /* bad shape / alignment / argument */
-#define B200_ECUDA (-2)    /* CUDA runtime error (launch, attribute, memcpy) */
-#define B200_EDRIVER (-3)  /* driver entry point / tensor-map encoding failure */
-#define B200_EARCH (-4)    /* device is not compute capability 10.x */
+#include "b200seg.h"
+
+
+
+
+
+
 
 namespace b200 {
 int set_error(int code, const char* fmt, ...);

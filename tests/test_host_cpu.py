@@ -1,0 +1,107 @@
+"""CPU-side checks (no GPU): the C-ABI library builds, loads and exports every symbol declared in
+include/b200seg.h; the drop-in modules reproduce the reference's state_dict layout (432-entry BiSeNet,
+the three discriminators, the shipped GTA5_10_D1.pth key set); host-side geometry of the implicit GEMM."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from dasemanticsegmentationaml_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "b200seg.h")).read()
+    names = sorted(set(re.findall(r"\b(b200_\w+)\s*\(", header)))
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.b200_version.restype = ctypes.c_int
+    assert lib.b200_version() >= 100
+    lib.b200_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.b200_last_error(), bytes)
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions(lib_path):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out or "UTCMMA" in out, "no tcgen05.mma in SASS"
+    assert "UTMALDG" in out, "no TMA tensor loads in SASS"
+    assert "LDTM" in out, "no TMEM loads in SASS"
+
+
+def test_product_state_dict_layout_matches_reference():
+    from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, DepthWiseSepFCDiscriminator,
+                                                      DepthWiseSepBNFCDiscriminator)
+    layout = json.load(open(os.path.join(GOLD, "state_dict_layout.json")))
+    net = BiSeNet("STDCNet813", 19)
+    got = [[k, list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()]
+    assert got == layout["bisenet"]
+    assert len(got) == 432
+    assert [n for n, _ in net.named_parameters()] == layout["bisenet_param_names"]
+    assert sum(p.numel() for p in net.parameters()) == 11550496
+    for name, cls in (("dense", FCDiscriminator), ("dwsep", DepthWiseSepFCDiscriminator),
+                      ("dwsep_bn", DepthWiseSepBNFCDiscriminator)):
+        got = [[k, list(v.shape), str(v.dtype)] for k, v in cls(19).state_dict().items()]
+        assert got == layout["disc_" + name]
+    wrapped = torch.nn.DataParallel(DepthWiseSepBNFCDiscriminator(19)).state_dict()
+    assert [[k, list(v.shape), str(v.dtype)] for k, v in wrapped.items()] == layout["shipped_D1"]
+    wd, nowd, lr_wd, lr_nowd = net.get_params()
+    assert len(wd) + len(nowd) + len(lr_wd) + len(lr_nowd) > 0 and len(lr_wd) == 9
+
+
+def test_modules_refuse_cpu_tensors():
+    from dasemanticsegmentationaml_b200 import _lib
+    from dasemanticsegmentationaml_b200.model import ConvX
+    from dasemanticsegmentationaml_b200 import utils as U
+    with pytest.raises(_lib.B200Error):
+        ConvX(16, 16)(torch.zeros(1, 16, 8, 8))
+    with pytest.raises(_lib.B200Error):
+        U.fast_hist(np.zeros(4, dtype=np.int64), np.zeros(4, dtype=np.int64), 19)
+
+
+def test_dgrad_geometry_matches_conv_transpose():
+    """The parity-class decomposition used for stride-2 data gradients, checked on the host against
+    torch's conv_transpose arithmetic for one channel."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    for (h, w, r, stride, pad) in [(9, 12, 3, 2, 1), (10, 8, 4, 2, 1), (7, 7, 3, 1, 1), (6, 5, 1, 1, 1)]:
+        ho = (h + 2 * pad - r) // stride + 1
+        wo = (w + 2 * pad - r) // stride + 1
+        g = torch.Generator().manual_seed(h * w)
+        wt = torch.randn(1, 1, r, r, generator=g, dtype=torch.float64)
+        dz = torch.randn(1, 1, ho, wo, generator=g, dtype=torch.float64)
+        x = torch.zeros(1, 1, h, w, dtype=torch.float64, requires_grad=True)
+        torch.nn.functional.conv2d(x, wt, stride=stride, padding=pad).backward(dz)
+        geom = K.dgrad_geometry(h, w, r, r, stride, pad)
+        dx = torch.zeros(h, w, dtype=torch.float64)
+        for c in geom.classes:
+            for i in range(c["Ho"]):
+                for j in range(c["Wo"]):
+                    acc = 0.0
+                    for dh, dw, slab in c["taps"]:
+                        a, b = i * geom.in_stride + dh, j * geom.in_stride + dw
+                        if 0 <= a < ho and 0 <= b < wo:
+                            acc += dz[0, 0, a, b].item() * wt[0, 0, slab // r, slab % r].item()
+                    dx[i * geom.out_stride + c["oa"], j * geom.out_stride + c["ob"]] = acc
+        assert torch.allclose(dx, x.grad[0, 0], atol=1e-12)
+
+
+def test_poly_lr_and_per_class_iu_host_side():
+    from dasemanticsegmentationaml_b200 import utils as U
+    from oracle import segnet_oracle as O
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.1)
+    assert U.poly_lr_scheduler(opt, 0.01, 3, max_iter=50) == O.poly_lr(0.01, 3, 50)
+    assert opt.param_groups[0]["lr"] == O.poly_lr(0.01, 3, 50)
+    h = np.arange(361).reshape(19, 19)
+    assert np.array_equal(U.per_class_iu(h), O.per_class_iu(h))
