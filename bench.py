@@ -113,7 +113,9 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 100 ms from before the warm-up; stop()
+    summarises the samples whose timestamps fall inside the timed window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -126,31 +128,39 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons, power = [], [], set(), []
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in out.strip().splitlines():
             f = [t.strip() for t in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]),
+                             [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 - 0.05 <= r[0] <= t1 + 0.05]
+        window = "timed region"
+        if not inside and rows:  # region shorter than the sampling period: take the closest samples
+            inside = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+            window = "nearest samples (timed region shorter than the 100 ms period)"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted(set(n for r in inside for n in r[4]))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max([r[2] for r in inside]) if inside else None,
+                "power_w_max": max([r[3] for r in inside]) if inside else None, "samples": len(inside),
+                "window": window, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------- B200 arm
@@ -212,11 +222,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(warmup):
         step(devbuf)
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
     sync_all()
-    clocks = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
     l0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -224,12 +235,13 @@ def run_b200(args):
         losses = step(devbuf)
     e1.record()
     sync_all()
+    t_wall1 = time.time()
     launches = _lib.launch_count - l0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
     loss_vals = [float(v) for v in losses]
 
     # ---- timed region 2: end to end from pinned host buffers -------------------------------------
@@ -305,7 +317,7 @@ def run_b200(args):
             line["wgrad_tflops"] = wg["flops"] / (wg["ms"] / 1e3) / 1e12
         if args.profile_json:
             with open(args.profile_json, "w") as f:
-                json.dump({k: v for k, v in prof.items()}, f, indent=1)
+                json.dump({"by_kernel": prof, "by_shape": _lib.last_profile_detail}, f, indent=1)
     if not args.no_cpu_baseline and world == 1:
         try:
             rate, cms, threads = cpu_da_step_rate(args.workload, 2, 1, 1)

@@ -46,7 +46,7 @@ launch_count = 0      # kernels launched through this binding since import
 _profile = None       # None, or a list of (name, start_event, end_event, flops, bytes)
 
 
-def call(name, *args, flops=0.0, nbytes=0.0):
+def call(name, *args, flops=0.0, nbytes=0.0, tag=None):
     """Invoke an entry point on the current stream, raise on error, count its launches and, while
     profiling, bracket it with CUDA events on the launching stream."""
     global launch_count
@@ -60,7 +60,7 @@ def call(name, *args, flops=0.0, nbytes=0.0):
         e0.record()
         rc = fn(*args)
         e1.record()
-        _profile.append((name, e0, e1, flops, nbytes))
+        _profile.append((name, e0, e1, flops, nbytes, tag))
     if rc != 0:
         raise B200Error("%s failed (%d): %s" % (name, rc, last_error()))
     launch_count += _MULTI.get(name, 1)
@@ -77,14 +77,22 @@ def profile_stop():
     import torch
     torch.cuda.synchronize()
     agg = {}
-    for name, e0, e1, flops, nbytes in _profile or []:
-        a = agg.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
-        a["calls"] += 1
-        a["ms"] += e0.elapsed_time(e1)
-        a["flops"] += flops
-        a["bytes"] += nbytes
+    detail = {}
+    for name, e0, e1, flops, nbytes, tag in _profile or []:
+        ms = e0.elapsed_time(e1)
+        for key, table in ((name, agg), ("%s %s" % (name, tag), detail)):
+            a = table.setdefault(key, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            a["calls"] += 1
+            a["ms"] += ms
+            a["flops"] += flops
+            a["bytes"] += nbytes
     _profile = None
+    global last_profile_detail
+    last_profile_detail = detail
     return agg
+
+
+last_profile_detail = {}
 
 
 def ensure_device(index):

@@ -133,7 +133,9 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
          ptr(out), c_int(out_ld), c_int(0), c_int(hout), c_int(wout), c_int(out_f32),
          geom.c_n, geom.c_ho, geom.c_wo, geom.c_oa, geom.c_ob, geom.c_nt, geom.c_taps, c_int(geom.tmax),
          c_int(geom.in_stride), c_int(geom.out_stride), ptr(bias), c_int(act), c_float(slope),
-         ptr(stats), c_int(0 if stats is None else stats.shape[1]), c_int(bn_tile), stream(), flops=flops)
+         ptr(stats), c_int(0 if stats is None else stats.shape[1]), c_int(bn_tile), stream(), flops=flops,
+         tag="M%d N%d K%dx%d s%d/%d%s" % (n * geom.classes[0]["Ho"] * geom.classes[0]["Wo"] * len(geom.classes), rows_pad, cin_pad,
+                                            len(geom.classes[0]["taps"]), geom.in_stride, geom.out_stride, " stats" if stats is not None else ""))
     return out
 
 
@@ -157,7 +159,7 @@ def conv_wgrad(dz, x, dw, r, s, stride, pad):
         ptr(dz), c_int(dz_ld), c_int(0), c_int(cout), c_int(n), c_int(ho), c_int(wo),
         ptr(x), c_int(x_ld), c_int(0), c_int(cin), c_int(hin), c_int(win),
         c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), stream(),
-        flops=2.0 * n * ho * wo * r * s * cout * cin)
+        flops=2.0 * n * ho * wo * r * s * cout * cin, tag="px%d co%d ci%d taps%d s%d" % (n * ho * wo, cout, cin, r * s, stride))
     return dw
 
 
@@ -208,7 +210,8 @@ def bn_act_apply(x, y, scale, shift, act, slope=0.0):
     npix2, c2, y_ld = _pix(y)
     assert npix == npix2 and c == c2
     call("b200_bn_act_apply", ptr(x), c_int(x_ld), ptr(y), c_int(y_ld), c_int(c), c_int64(npix),
-                                  ptr(scale), ptr(shift), c_int(act), c_float(slope), stream())
+                                  ptr(scale), ptr(shift), c_int(act), c_float(slope), stream(),
+         nbytes=4.0 * npix * c, tag="px%d C%d" % (npix, c))
 
 
 def bn_act_bwd_reduce(dy1, dy2, z, scale, shift, mean, rstd, act, slope, red):
@@ -216,7 +219,8 @@ def bn_act_bwd_reduce(dy1, dy2, z, scale, shift, mean, rstd, act, slope, red):
     call("b200_bn_act_bwd_reduce", 
         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
         ptr(z), c_int(z_ld), c_int(c), c_int64(npix), ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
-        c_int(act), c_float(slope), ptr(red), stream())
+        c_int(act), c_float(slope), ptr(red), stream(),
+        nbytes=(4.0 if dy2 is None else 6.0) * npix * c, tag="px%d C%d%s" % (npix, c, "" if dy2 is None else " +dy2"))
 
 
 def bn_act_bwd_apply(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope):
@@ -225,7 +229,7 @@ def bn_act_bwd_apply(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope)
         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
         ptr(z), c_int(z_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), ptr(scale),
         ptr(shift), ptr(mean), ptr(rstd), ptr(red), c_float(1.0 / npix), c_int(act), c_float(slope),
-        stream())
+        stream(), nbytes=(6.0 if dy2 is None else 8.0) * npix * c, tag="px%d C%d%s" % (npix, c, "" if dy2 is None else " +dy2"))
 
 
 def act_bwd_bias(dy1, dy2, a, dz, act, slope, dbias):

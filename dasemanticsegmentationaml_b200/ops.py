@@ -15,29 +15,37 @@ F32 = torch.float32
 # when True the packed-filter cache is bypassed (needed while capturing CUDA graphs: the captured
 # graph must contain the repacking kernels because the fp32 masters change between replays)
 FORCE_REPACK = False
-_pack_cache = {}
 
 
 def packed_filter(weight, transpose):
-    key = (weight.data_ptr(), bool(transpose), tuple(weight.shape))
-    ver = weight._version
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver and not FORCE_REPACK:
-        return hit[1]
-    if hit is not None and hit[1].device == weight.device:
-        buf = hit[1]  # repack in place: stable pointer for graphs, no allocator churn
+    """bf16 GEMM packing of a conv filter, cached ON the parameter object (so it dies with it and a
+    recycled device address can never alias a stale packing) and refreshed when the parameter's
+    version counter or storage changes (optimizer steps, load_state_dict, .to())."""
+    cache = getattr(weight, "_b200_pack", None)
+    if cache is None:
+        cache = {}
+        try:
+            weight._b200_pack = cache
+        except AttributeError:
+            pass
+    ver, ptr_now = weight._version, weight.data_ptr()
+    hit = cache.get(bool(transpose))
+    if hit is not None and hit[0] == ver and hit[1] == ptr_now and not FORCE_REPACK:
+        return hit[2]
+    if hit is not None and hit[2].device == weight.device:
+        buf = hit[2]  # repack in place: stable pointer for graphs, no allocator churn
         cout, cin, r, s = weight.shape
         w = weight.detach()
         K.call("b200_pack_filter", K.ptr(w), K.ptr(buf), K.c_int(cout), K.c_int(cin), K.c_int(r * s),
                K.c_int(buf.shape[0]), K.c_int(buf.shape[2]), K.c_int(1 if transpose else 0), K.stream())
     else:
         buf = K.pack_filter(weight, transpose)
-    _pack_cache[key] = (ver, buf)
+    cache[bool(transpose)] = (ver, ptr_now, buf)
     return buf
 
 
 def clear_caches():
-    _pack_cache.clear()
+    pass
 
 
 def empty_act(n, h, w, c, device):
