@@ -389,6 +389,28 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// All stale packings of a model in ONE launch.  table[i] = {src, dst, Cout, Cin, RS, rows_pad,
+// inner_pad, transpose} (int64 each); grid = (chunks, n_filters).
+__global__ void pack_filters_batched_kernel(const long long* __restrict__ table) {
+  const long long* t = table + (size_t)blockIdx.y * 8;
+  const float* w = reinterpret_cast<const float*>(t[0]);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t[1]);
+  const int Cout = (int)t[2], Cin = (int)t[3], RS = (int)t[4], rows_pad = (int)t[5], inner_pad = (int)t[6];
+  const int transpose = (int)t[7];
+  const size_t total = (size_t)rows_pad * RS * inner_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int inner = i % inner_pad;
+    const int tt = (i / inner_pad) % RS;
+    const int row = i / ((size_t)inner_pad * RS);
+    const int co = transpose ? inner : row;
+    const int ci = transpose ? row : inner;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * RS + tt];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 // ------------------------------------------------------------ host launchers
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -510,6 +532,13 @@ int b200_pack_filter(const float* w, void* out_bf16, int Cout, int Cin, int RS, 
   return check_launch("pack_filter");
 }
 
+int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStream_t stream) {
+  if (n_filters <= 0) return B200_OK;
+  pack_filters_batched_kernel<<<dim3(48, n_filters), 256, 0, stream>>>(
+      reinterpret_cast<const long long*>(table_dev));
+  return check_launch("pack_filters_batched");
+}
+
 // Generic implicit-GEMM launch.  `taps` is [n_classes][n_taps_max][3] = (dh, dw, k-slab).
 int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int Hin, int Win,
                     const void* filt, int filt_rows, int cin_pad, int n_slabs,
@@ -626,7 +655,8 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   const int total_tiles = p.tiles_h * p.tiles_w * N;
   const int ytiles = n_taps * p.co_tiles * p.ci_tiles;
   int splits = (148 * 2 + ytiles - 1) / ytiles;  // about two CTAs per SM overall
-  if (splits > total_tiles) splits = total_tiles;
+  // every split adds a full set of fp32 atomics: keep >= 8 pixel tiles (K iterations) per CTA
+  if (splits > total_tiles / 8) splits = total_tiles / 8;
   if (splits < 1) splits = 1;
   p.splits = splits;
   p.stages = pick_stages(stage_bytes, (total_tiles + splits - 1) / splits);

@@ -35,19 +35,29 @@ __device__ __forceinline__ Interp interp_at(int dst, float scale, int in_size) {
   return r;
 }
 
-// Interpolated logits of one full-resolution pixel.
+// Interpolated logits of one full-resolution pixel (four corner pixels read as float4 vectors;
+// lr_ld is a multiple of 4 and the padding classes are readable).
 template <int NC>
 __device__ __forceinline__ void sample_logits(const float* __restrict__ lr, int lr_ld, int h_lr,
                                               int w_lr, int n, const Interp& ih, const Interp& iw,
                                               float (&v)[NC]) {
-  const float* p00 = lr + (((int64_t)n * h_lr + ih.i0) * w_lr + iw.i0) * lr_ld;
-  const float* p01 = lr + (((int64_t)n * h_lr + ih.i0) * w_lr + iw.i1) * lr_ld;
-  const float* p10 = lr + (((int64_t)n * h_lr + ih.i1) * w_lr + iw.i0) * lr_ld;
-  const float* p11 = lr + (((int64_t)n * h_lr + ih.i1) * w_lr + iw.i1) * lr_ld;
+  const float4* p00 = reinterpret_cast<const float4*>(lr + (((int64_t)n * h_lr + ih.i0) * w_lr + iw.i0) * lr_ld);
+  const float4* p01 = reinterpret_cast<const float4*>(lr + (((int64_t)n * h_lr + ih.i0) * w_lr + iw.i1) * lr_ld);
+  const float4* p10 = reinterpret_cast<const float4*>(lr + (((int64_t)n * h_lr + ih.i1) * w_lr + iw.i0) * lr_ld);
+  const float4* p11 = reinterpret_cast<const float4*>(lr + (((int64_t)n * h_lr + ih.i1) * w_lr + iw.i1) * lr_ld);
+  const float w00 = ih.l0 * iw.l0, w01 = ih.l0 * iw.l1, w10 = ih.l1 * iw.l0, w11 = ih.l1 * iw.l1;
+  constexpr int NV = (NC + 3) / 4;
 #pragma unroll
-  for (int c = 0; c < NC; ++c)
-    v[c] = ih.l0 * (iw.l0 * __ldg(p00 + c) + iw.l1 * __ldg(p01 + c)) +
-           ih.l1 * (iw.l0 * __ldg(p10 + c) + iw.l1 * __ldg(p11 + c));
+  for (int q = 0; q < NV; ++q) {
+    const float4 a = __ldg(p00 + q), b = __ldg(p01 + q), c = __ldg(p10 + q), d = __ldg(p11 + q);
+    const float r[4] = {w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x,
+                        w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y,
+                        w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z,
+                        w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * q + k < NC) v[4 * q + k] = r[k];
+  }
 }
 
 template <int NC>
@@ -186,6 +196,7 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
   __shared__ float s_g[TH][TW][NC + 1];
   __shared__ float s_a[TH][MAXJ][NC + 1];
   __shared__ Interp s_iw[TW], s_ih[TH];
+  __shared__ int s_xlo[MAXJ], s_xhi[MAXJ];
   const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
   const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
@@ -249,6 +260,18 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
   __syncthreads();
   const int j_min = s_iw[0].i0;
   const int i_min = s_ih[0].i0;
+  if (threadIdx.x < MAXJ) {  // columns of the tile that touch low-resolution column j (a contiguous range)
+    const int j = j_min + threadIdx.x;
+    int lo = TW, hi = 0;
+    for (int x = 0; x < TW; ++x)
+      if (s_iw[x].i0 == j || s_iw[x].i1 == j) {
+        lo = min(lo, x);
+        hi = x + 1;
+      }
+    s_xlo[threadIdx.x] = lo;
+    s_xhi[threadIdx.x] = hi;
+  }
+  __syncthreads();
   // pass A: reduce along w   -> s_a[row][j - j_min][c]
   for (int item = threadIdx.x; item < TH * MAXJ * NC; item += TH * TW) {
     const int c = item % NC;
@@ -256,7 +279,7 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
     const int r = item / (NC * MAXJ);
     const int j = j_min + jj;
     float acc = 0.f;
-    for (int x = 0; x < TW; ++x) {
+    for (int x = s_xlo[jj]; x < s_xhi[jj]; ++x) {
       const Interp iw = s_iw[x];
       float wgt = 0.f;
       if (iw.i0 == j) wgt += iw.l0;
@@ -424,6 +447,7 @@ int b200_upsample_fwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
                       const int64_t* labels, int ignore_index, double* acc, float* loss_map,
                       cudaStream_t stream) {
   if (n_classes != 19) return set_error(B200_EINVAL, "upsample_fwd: only 19 classes are compiled (got %d)", n_classes);
+  if (lr_ld % 4 || lr_ld < 20) return set_error(B200_EINVAL, "upsample_fwd: logits pixel stride %d must be a multiple of 4, >= 20", lr_ld);
   if (mode == 2 && (p_ld % 8 || p_ld > kMaxCls || p_ld < n_classes))
     return set_error(B200_EINVAL, "upsample_fwd: probability stride %d unsupported", p_ld);
   const int64_t total = (int64_t)N * H * W;
@@ -438,6 +462,7 @@ int b200_upsample_bwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
                       const float* coef_num, const double* coef_den, float coef_scale, float* d_lr,
                       cudaStream_t stream) {
   if (n_classes != 19) return set_error(B200_EINVAL, "upsample_bwd: only 19 classes are compiled (got %d)", n_classes);
+  if (lr_ld % 4 || lr_ld < 20) return set_error(B200_EINVAL, "upsample_bwd: logits pixel stride %d must be a multiple of 4, >= 20", lr_ld);
   const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
   const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
   if (sw * (TW - 1) + 2.f > (float)MAXJ || sh * (TH - 1) + 2.f > (float)MAXI)

@@ -18,6 +18,13 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
   float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ uint4 ldraw(const __nv_bfloat16* p) {
+  return *reinterpret_cast<const uint4*>(p);
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                                             pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -33,34 +40,58 @@ __device__ __forceinline__ float act_grad(float pre, int act, float slope) {
   return 1.f;
 }
 
+// All streaming kernels below share one shape: a block is (C/8 channel groups) x PY pixel rows,
+// a thread keeps its channel group for the whole kernel (per-channel parameters live in registers)
+// and walks pixels in batches of UNR independent 16-byte loads per tensor (memory-level parallelism).
+constexpr int UNR = 4;   // single-tensor kernels
+constexpr int UNR3 = 2;  // kernels streaming three tensors
+
+struct Slot {
+  int g, ty, py;
+};
+__device__ __forceinline__ Slot slot_of(int C) {
+  Slot s;
+  const int groups = C >> 3;
+  s.py = blockDim.x / groups;
+  s.g = threadIdx.x % groups;
+  s.ty = threadIdx.x / groups;
+  return s;
+}
+
 // ---------------------------------------------------------------- statistics
-// stats[0][c] += sum x, stats[1][c] += sum x^2 over all pixels.  Block = (C/8) x PY threads; each
-// thread owns 8 channels and strides over pixels; partials are combined in shared memory.
+// stats[0][c] += sum x, stats[1][c] += sum x^2 over all pixels.
 __global__ void __launch_bounds__(256)
 channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, int C, int64_t npix,
                      float* __restrict__ stats) {
   extern __shared__ float s_acc[];  // [2][C]
-  const int groups = C >> 3;
-  const int py = blockDim.x / groups;
-  const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+  const Slot t = slot_of(C);
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   float s1[8] = {0}, s2[8] = {0};
-  if (ty < py) {
-    for (int64_t p = (int64_t)blockIdx.x * py + ty; p < npix; p += (int64_t)gridDim.x * py) {
-      float v[8];
-      load8(x + p * ld + g * 8, v);
+  const int64_t step = (int64_t)gridDim.x * t.py * UNR;
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR; base < npix; base += step) {
+    float v[UNR][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += v[j];
-        s2[j] += v[j] * v[j];
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      if (p < npix) load8(x + p * ld + t.g * 8, v[u]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[g * 8 + j], s1[j]);
-      atomicAdd(&s_acc[C + g * 8 + j], s2[j]);
-    }
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += v[u][j];
+        s2[j] += v[u][j] * v[u][j];
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_acc[t.g * 8 + j], s1[j]);
+    atomicAdd(&s_acc[C + t.g * 8 + j], s2[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], s_acc[i]);
@@ -69,6 +100,25 @@ channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, int C, int64_t
 // mean / biased var from (sum, sumsq) -> scale = gamma*rstd, shift = beta - mean*scale; running
 // statistics updated with momentum (unbiased variance), exactly nn.BatchNorm2d's train step.
 // training == 0: scale/shift from the running statistics (eval mode).
+__device__ __forceinline__ void bn_coeffs(const float* stats, int C, int c, float count,
+                                          const float* gamma, const float* beta,
+                                          const float* running_mean, const float* running_var,
+                                          float eps, int training, float* mean, float* var,
+                                          float* rstd, float* scale, float* shift) {
+  if (training) {
+    *mean = stats[c] / count;
+    *var = fmaxf(stats[C + c] / count - *mean * *mean, 0.f);
+  } else {
+    *mean = running_mean[c];
+    *var = running_var[c];
+  }
+  *rstd = rsqrtf(*var + eps);
+  const float g = gamma != nullptr ? gamma[c] : 1.f;
+  const float b = beta != nullptr ? beta[c] : 0.f;
+  *scale = g * *rstd;
+  *shift = b - *mean * g * *rstd;
+}
+
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -77,56 +127,87 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float mean, var;
-  if (training) {
-    mean = stats[c] / count;
-    var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
-    if (running_mean != nullptr) {
-      const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-    }
-  } else {
-    mean = running_mean[c];
-    var = running_var[c];
+  float mean, var, rstd, sc, sh;
+  bn_coeffs(stats, C, c, count, gamma, beta, running_mean, running_var, eps, training, &mean, &var,
+            &rstd, &sc, &sh);
+  if (training && running_mean != nullptr) {
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
   }
-  const float rstd = rsqrtf(var + eps);
-  const float g = gamma != nullptr ? gamma[c] : 1.f;
-  const float b = beta != nullptr ? beta[c] : 0.f;
-  scale[c] = g * rstd;
-  shift[c] = b - mean * g * rstd;
+  scale[c] = sc;
+  shift[c] = sh;
   if (mean_out != nullptr) mean_out[c] = mean;
   if (rstd_out != nullptr) rstd_out[c] = rstd;
 }
 
 // ------------------------------------------------------------- normalise + act
-// y = act(x * scale[c] + shift[c])   (scale == nullptr: plain activation)
+// y = act(x * scale[c] + shift[c]).  Two ways to get scale/shift:
+//   stats == nullptr : read them from `scale` / `shift` (nullptr: identity)
+//   stats != nullptr : finalise BatchNorm in-kernel from (sum, sumsq) — every thread derives the
+//                      coefficients of its own 8 channels; block 0 also publishes scale / shift /
+//                      mean / rstd for the backward pass and updates the running statistics.
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
-                    int y_ld, int C, int64_t npix, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int act, float slope) {
-  const int groups = C >> 3;
-  const int64_t total = npix * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / groups;
-    const int g = (int)(i - p * groups);
-    float v[8];
-    load8(x + p * x_ld + g * 8, v);
+                    int y_ld, int C, int64_t npix, float* __restrict__ scale,
+                    float* __restrict__ shift, int act, float slope,
+                    const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ running_mean,
+                    float* __restrict__ running_var, float momentum, float eps, int training,
+                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int finalize) {
+  const Slot t = slot_of(C);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = v[j];
-      if (scale != nullptr) t = t * __ldg(scale + g * 8 + j) + __ldg(shift + g * 8 + j);
-      v[j] = act_fwd(t, act, slope);
+  for (int j = 0; j < 8; ++j) {
+    const int c = t.g * 8 + j;
+    if (finalize) {
+      float mean, var, rstd;
+      bn_coeffs(stats, C, c, count, gamma, beta, running_mean, running_var, eps, training, &mean,
+                &var, &rstd, &sc[j], &sh[j]);
+      if (blockIdx.x == 0 && t.ty == 0) {
+        if (scale != nullptr) {
+          scale[c] = sc[j];
+          shift[c] = sh[j];
+        }
+        if (mean_out != nullptr) {
+          mean_out[c] = mean;
+          rstd_out[c] = rstd;
+        }
+        if (training && running_mean != nullptr) {
+          const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+          running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+          running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+      }
+    } else {
+      sc[j] = scale != nullptr ? scale[c] : 1.f;
+      sh[j] = shift != nullptr ? shift[c] : 0.f;
     }
-    store8(y + p * y_ld + g * 8, v);
+  }
+  const int64_t step = (int64_t)gridDim.x * t.py * UNR;
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR; base < npix; base += step) {
+    float v[UNR][8];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      if (p < npix) load8(x + p * x_ld + t.g * 8, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      if (p < npix) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = act_fwd(v[u][j] * sc[j] + sh[j], act, slope);
+        store8(y + p * y_ld + t.g * 8, v[u]);
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------ backward
 // g = (dy1 + dy2) * act'(z*scale + shift);  xhat = (z - mean) * rstd
 // red[0][c] += sum g (= dbeta), red[1][c] += sum g*xhat (= dgamma)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                          const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
                          const __nv_bfloat16* __restrict__ z, int z_ld, int C, int64_t npix,
@@ -134,49 +215,55 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                          const float* __restrict__ mean, const float* __restrict__ rstd, int act,
                          float slope, float* __restrict__ red) {
   extern __shared__ float s_acc[];  // [2][C]
-  const int groups = C >> 3;
-  const int py = blockDim.x / groups;
-  const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+  const Slot t = slot_of(C);
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  if (ty < py) {
-    float sc[8], sh[8], mu[8], rs[8], a1[8] = {0}, a2[8] = {0};
+  float sc[8], sh[8], a1[8] = {0}, a2[8] = {0};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc[j] = scale[g * 8 + j];
-      sh[j] = shift[g * 8 + j];
-      mu[j] = mean[g * 8 + j];
-      rs[j] = rstd[g * 8 + j];
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[t.g * 8 + j];
+    sh[j] = shift[t.g * 8 + j];
+  }
+  const int64_t step = (int64_t)gridDim.x * t.py * UNR3;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR3; base < npix; base += step) {
+    uint4 rd[UNR3], rz[UNR3], re[UNR3];
+#pragma unroll
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      const bool ok = p < npix;
+      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;  // zero gradient: contributes nothing
+      rz[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
+      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
     }
-    for (int64_t p = (int64_t)blockIdx.x * py + ty; p < npix; p += (int64_t)gridDim.x * py) {
-      float d[8], zz[8];
-      load8(dy1 + p * dy1_ld + g * 8, d);
-      if (dy2 != nullptr) {
-        float e[8];
-        load8(dy2 + p * dy2_ld + g * 8, e);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] += e[j];
-      }
-      load8(z + p * z_ld + g * 8, zz);
+    for (int u = 0; u < UNR3; ++u) {
+      float d[8], zz[8], e[8];
+      unpack8(rd[u], d);
+      unpack8(rz[u], zz);
+      unpack8(re[u], e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float gg = d[j] * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+        const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
         a1[j] += gg;
-        a2[j] += gg * (zz[j] - mu[j]) * rs[j];
+        a2[j] += gg * zz[j];
       }
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[g * 8 + j], a1[j]);
-      atomicAdd(&s_acc[C + g * 8 + j], a2[j]);
-    }
+  for (int j = 0; j < 8; ++j)  // sum g*xhat = rstd * (sum g*z - mean * sum g)
+    a2[j] = (a2[j] - mean[t.g * 8 + j] * a1[j]) * rstd[t.g * 8 + j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_acc[t.g * 8 + j], a1[j]);
+    atomicAdd(&s_acc[C + t.g * 8 + j], a2[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[i], s_acc[i]);
 }
 
 // dz = scale * (g - red0/M - xhat * red1/M)        (train-mode BatchNorm backward)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                         const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
                         const __nv_bfloat16* __restrict__ z, int z_ld,
@@ -184,70 +271,94 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ red, float inv_count, int act, float slope) {
-  const int groups = C >> 3;
-  const int64_t total = npix * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / groups;
-    const int g = (int)(i - p * groups);
-    float d[8], zz[8], o[8];
-    load8(dy1 + p * dy1_ld + g * 8, d);
-    if (dy2 != nullptr) {
-      float e[8];
-      load8(dy2 + p * dy2_ld + g * 8, e);
+  const Slot t = slot_of(C);
+  // dz = sc*g - sc*r0 - sc*r1*rs*(z - mu) = sc*g + k1*z + k0
+  float sc[8], sh[8], k0[8], k1[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] += e[j];
-    }
-    load8(z + p * z_ld + g * 8, zz);
+  for (int j = 0; j < 8; ++j) {
+    const int c = t.g * 8 + j;
+    sc[j] = scale[c];
+    sh[j] = shift[c];
+    const float r0 = red[c] * inv_count, r1 = red[C + c] * inv_count;
+    k1[j] = -sc[j] * r1 * rstd[c];
+    k0[j] = -sc[j] * r0 - k1[j] * mean[c];
+  }
+  const int64_t step = (int64_t)gridDim.x * t.py * UNR3;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR3; base < npix; base += step) {
+    uint4 rd[UNR3], rz[UNR3], re[UNR3];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-      const float gg = d[j] * act_grad(zz[j] * sc + sh, act, slope);
-      const float xhat = (zz[j] - __ldg(mean + c)) * __ldg(rstd + c);
-      o[j] = sc * (gg - __ldg(red + c) * inv_count - xhat * __ldg(red + C + c) * inv_count);
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      const bool ok = p < npix;
+      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
+      rz[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
+      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
     }
-    store8(dz + p * dz_ld + g * 8, o);
+#pragma unroll
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      if (p < npix) {
+        float d[8], zz[8], e[8], o[8];
+        unpack8(rd[u], d);
+        unpack8(rz[u], zz);
+        unpack8(re[u], e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+          o[j] = sc[j] * gg + k1[j] * zz[j] + k0[j];
+        }
+        store8(dz + p * dz_ld + t.g * 8, o);
+      }
+    }
   }
 }
 
 // Biased conv + LeakyReLU layers (no BatchNorm): dz = (dy1+dy2) * leaky'(a) with a the stored
 // activation (sign(a) == sign(pre-activation)); dbias[c] += sum dz.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 act_bwd_bias_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                     const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
                     const __nv_bfloat16* __restrict__ a, int a_ld, __nv_bfloat16* __restrict__ dz,
                     int dz_ld, int C, int64_t npix, int act, float slope,
                     float* __restrict__ dbias) {
   extern __shared__ float s_acc[];  // [C]
-  const int groups = C >> 3;
-  const int py = blockDim.x / groups;
-  const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+  const Slot t = slot_of(C);
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  if (ty < py) {
-    float acc[8] = {0};
-    for (int64_t p = (int64_t)blockIdx.x * py + ty; p < npix; p += (int64_t)gridDim.x * py) {
-      float d[8], aa[8];
-      load8(dy1 + p * dy1_ld + g * 8, d);
-      if (dy2 != nullptr) {
-        float e[8];
-        load8(dy2 + p * dy2_ld + g * 8, e);
+  float acc[8] = {0};
+  const int64_t step = (int64_t)gridDim.x * t.py * UNR3;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR3; base < npix; base += step) {
+    uint4 rd[UNR3], ra[UNR3], re[UNR3];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] += e[j];
-      }
-      load8(a + p * a_ld + g * 8, aa);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        d[j] *= act_grad(aa[j], act, slope);
-        acc[j] += d[j];
-      }
-      store8(dz + p * dz_ld + g * 8, d);
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      const bool ok = p < npix;
+      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
+      ra[u] = ok ? ldraw(a + p * a_ld + t.g * 8) : zero4;
+      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
     }
-    if (dbias != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[g * 8 + j], acc[j]);
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      if (p < npix) {
+        float d[8], aa[8], e[8];
+        unpack8(rd[u], d);
+        unpack8(ra[u], aa);
+        unpack8(re[u], e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          d[j] = (d[j] + e[j]) * act_grad(aa[j], act, slope);
+          acc[j] += d[j];
+        }
+        store8(dz + p * dz_ld + t.g * 8, d);
+      }
     }
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[t.g * 8 + j], acc[j]);
   }
   __syncthreads();
   if (dbias != nullptr)
@@ -264,9 +375,9 @@ cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
   }
 }
 
-static int reduce_grid(int64_t npix, int py) {
-  int64_t blocks = (npix + py * 8 - 1) / (py * 8);  // >= 8 pixels per thread
-  if (blocks > 148 * 4) blocks = 148 * 4;
+static int reduce_grid(int64_t npix, int py, int cap = 148 * 8) {
+  int64_t blocks = (npix + py * UNR3 - 1) / (py * UNR3);
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
 }
@@ -298,7 +409,7 @@ int b200_channel_stats(const void* x, int ld, int C, int64_t npix, float* stats,
   int rc = check_c(C, "channel_stats");
   if (rc) return rc;
   const int threads = block_for(C);
-  channel_stats_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 2 * C * sizeof(float), stream>>>(
+  channel_stats_kernel<<<reduce_grid(npix, threads / (C / 8), 148 * 4), threads, 2 * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(x), ld, C, npix, stats);
   return check_launch("channel_stats");
 }
@@ -318,10 +429,30 @@ int b200_bn_act_apply(const void* x, int x_ld, void* y, int y_ld, int C, int64_t
                       cudaStream_t stream) {
   int rc = check_c(C, "bn_act_apply");
   if (rc) return rc;
-  bn_act_apply_kernel<<<stream_grid(npix * (C / 8)), 256, 0, stream>>>(
+  const int threads = block_for(C);
+  bn_act_apply_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<__nv_bfloat16*>(y), y_ld, C, npix,
-      scale, shift, act, slope);
+      const_cast<float*>(scale), const_cast<float*>(shift), act, slope, nullptr, 1.f, nullptr, nullptr,
+      nullptr, nullptr, 0.f, 0.f, 1, nullptr, nullptr, 0);
   return check_launch("bn_act_apply");
+}
+
+// BatchNorm finalisation fused into the normalise+activate pass (one launch per layer): see
+// bn_act_apply_kernel.  scale/shift/mean_out/rstd_out receive the coefficients for the backward.
+int b200_bn_norm_act(const void* x, int x_ld, void* y, int y_ld, int C, int64_t npix,
+                     const float* stats, float count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     int training, int act, float slope, float* scale, float* shift,
+                     float* mean_out, float* rstd_out, cudaStream_t stream) {
+  int rc = check_c(C, "bn_norm_act");
+  if (rc) return rc;
+  if (training && stats == nullptr) return set_error(B200_EINVAL, "bn_norm_act: training needs stats");
+  const int threads = block_for(C);
+  bn_act_apply_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), x_ld, static_cast<__nv_bfloat16*>(y), y_ld, C, npix, scale,
+      shift, act, slope, training ? stats : nullptr, count, gamma, beta, running_mean, running_var,
+      momentum, eps, training, mean_out, rstd_out, 1);
+  return check_launch("bn_norm_act");
 }
 
 int b200_bn_act_bwd_reduce(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
@@ -331,7 +462,7 @@ int b200_bn_act_bwd_reduce(const void* dy1, int dy1_ld, const void* dy2, int dy2
   int rc = check_c(C, "bn_act_bwd_reduce");
   if (rc) return rc;
   const int threads = block_for(C);
-  bn_act_bwd_reduce_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 2 * C * sizeof(float), stream>>>(
+  bn_act_bwd_reduce_kernel<<<reduce_grid(npix, threads / (C / 8), 148 * 4), threads, 2 * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(dy1), dy1_ld, static_cast<const __nv_bfloat16*>(dy2), dy2_ld,
       static_cast<const __nv_bfloat16*>(z), z_ld, C, npix, scale, shift, mean, rstd, act, slope, red);
   return check_launch("bn_act_bwd_reduce");
@@ -344,7 +475,8 @@ int b200_bn_act_bwd_apply(const void* dy1, int dy1_ld, const void* dy2, int dy2_
                           cudaStream_t stream) {
   int rc = check_c(C, "bn_act_bwd_apply");
   if (rc) return rc;
-  bn_act_bwd_apply_kernel<<<stream_grid(npix * (C / 8)), 256, 0, stream>>>(
+  const int threads = block_for(C);
+  bn_act_bwd_apply_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(dy1), dy1_ld, static_cast<const __nv_bfloat16*>(dy2), dy2_ld,
       static_cast<const __nv_bfloat16*>(z), z_ld, static_cast<__nv_bfloat16*>(dz), dz_ld, C, npix,
       scale, shift, mean, rstd, red, inv_count, act, slope);
@@ -363,7 +495,7 @@ int b200_act_bwd_bias(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, 
   int rc = check_c(C, "act_bwd_bias");
   if (rc) return rc;
   const int threads = block_for(C);
-  act_bwd_bias_kernel<<<reduce_grid(npix, threads / (C / 8)), threads, C * sizeof(float), stream>>>(
+  act_bwd_bias_kernel<<<reduce_grid(npix, threads / (C / 8), 148 * 4), threads, C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(dy1), dy1_ld, static_cast<const __nv_bfloat16*>(dy2), dy2_ld,
       static_cast<const __nv_bfloat16*>(a), a_ld, static_cast<__nv_bfloat16*>(dz), dz_ld, C, npix,
       act, slope, dbias);

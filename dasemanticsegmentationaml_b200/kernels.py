@@ -214,6 +214,16 @@ def bn_act_apply(x, y, scale, shift, act, slope=0.0):
          nbytes=4.0 * npix * c, tag="px%d C%d" % (npix, c))
 
 
+def bn_norm_act(x, y, stats, count, gamma, beta, running_mean, running_var, training, act, slope,
+                scale, shift, mean, rstd, momentum=0.1, eps=1e-5):
+    npix, c, x_ld = _pix(x)
+    call("b200_bn_norm_act", ptr(x), c_int(x_ld), ptr(y), c_int(y.stride(2)), c_int(c), c_int64(npix),
+         ptr(stats), c_float(count), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+         c_float(momentum), c_float(eps), c_int(1 if training else 0), c_int(act), c_float(slope),
+         ptr(scale), ptr(shift), ptr(mean), ptr(rstd), stream(), nbytes=4.0 * npix * c,
+         tag="px%d C%d" % (npix, c))
+
+
 def bn_act_bwd_reduce(dy1, dy2, z, scale, shift, mean, rstd, act, slope, red):
     npix, c, z_ld = _pix(z)
     call("b200_bn_act_bwd_reduce", 

@@ -10,6 +10,7 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
+from .. import ops
 
 BF16 = torch.bfloat16
 _pending_nbt = []
@@ -105,6 +106,7 @@ def run_module(module, *inputs):
         raise _lib.B200Error("%s only runs on a B200 (got a %s tensor); there is no CPU fallback"
                              % (type(module).__name__, dev.type))
     _lib.ensure_device(dev.index or 0)
+    ops.refresh_packs(module)
     out = _ModuleFunction.apply(module, len(inputs), *inputs, *module_params(module))
     flush_nbt()
     return out

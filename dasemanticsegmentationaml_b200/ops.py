@@ -44,6 +44,40 @@ def packed_filter(weight, transpose):
     return buf
 
 
+def refresh_packs(module):
+    """Re-pack, in ONE launch, every cached filter packing of `module` whose fp32 master changed
+    (called at the top of a forward; after an optimizer step that is all of them)."""
+    weights = getattr(module, "_b200_conv_weights", None)
+    if weights is None:
+        weights = [p for p in module.parameters() if p.dim() == 4]
+        object.__setattr__(module, "_b200_conv_weights", weights)
+    stale = []
+    for w in weights:
+        cache = getattr(w, "_b200_pack", None)
+        if not cache:
+            continue
+        ver, ptr_now = w._version, w.data_ptr()
+        for tr, (v, pw, buf) in cache.items():
+            if v != ver or pw != ptr_now or FORCE_REPACK:
+                stale.append((w, tr, buf))
+    if not stale:
+        return 0
+    key = tuple((w.data_ptr(), tr, buf.data_ptr()) for w, tr, buf in stale)
+    tab = getattr(module, "_b200_pack_table", None)
+    if tab is None or tab[0] != key:
+        rows = []
+        for w, tr, buf in stale:
+            cout, cin, r, s = w.shape
+            rows.append([w.data_ptr(), buf.data_ptr(), cout, cin, r * s, buf.shape[0], buf.shape[2], 1 if tr else 0])
+        dev = torch.tensor(rows, dtype=torch.int64).to(stale[0][0].device)
+        tab = (key, dev)
+        object.__setattr__(module, "_b200_pack_table", tab)
+    K.call("b200_pack_filters_batched", K.ptr(tab[1]), K.c_int(len(stale)), K.stream())
+    for w, tr, buf in stale:
+        w._b200_pack[tr] = (w._version, w.data_ptr(), buf)
+    return len(stale)
+
+
 def clear_caches():
     pass
 
@@ -62,9 +96,9 @@ def bn_act_fwd(z, stats, bn, training, act, slope=0.0, out=None):
     n, h, w, c = z.shape
     gamma, beta, rm, rv = bn
     buf = torch.empty((4, c), dtype=F32, device=z.device)
-    K.bn_finalize(stats, float(n * h * w), gamma, beta, rm, rv, training, buf[0], buf[1], buf[2], buf[3])
     a = out if out is not None else torch.empty_like(z)
-    K.bn_act_apply(z, a, buf[0], buf[1], act, slope)
+    K.bn_norm_act(z, a, stats, float(n * h * w), gamma, beta, rm, rv, training, act, slope,
+                  buf[0], buf[1], buf[2], buf[3])
     ctx = BNCtx()
     ctx.z, ctx.scale, ctx.shift, ctx.mean, ctx.rstd = z, buf[0], buf[1], buf[2], buf[3]
     ctx.act, ctx.slope, ctx.training = act, slope, training

@@ -54,6 +54,10 @@ int b200_check_device(void);
 int b200_pack_filter(const float* w, void* out_bf16, int Cout, int Cin, int RS, int rows_pad,
                      int inner_pad, int transpose, cudaStream_t stream);
 
+/* The same for many filters in one launch: table_dev = int64 [n][8] on the device =
+ * {src, dst, Cout, Cin, RS, rows_pad, inner_pad, transpose} (repacking after an optimizer step). */
+int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStream_t stream);
+
 /* Implicit-GEMM convolution on the 5th-gen tensor cores (TMA-fed, TMEM accumulators):
  *   out[n, (h*os+oa), (w*os+ob), co] = act(bias[co] + sum_{tap, ci} in[n, h*is+dh, w*is+dw, ci] * filt[co, slab, ci])
  * `taps` = [n_classes][taps_stride][3] = (dh, dw, slab).  One class with is = conv stride is the
@@ -97,6 +101,13 @@ int b200_bn_finalize(const float* stats, int C, float count, const float* gamma,
 int b200_bn_act_apply(const void* x, int x_ld, void* y, int y_ld, int C, int64_t npix,
                       const float* scale, const float* shift, int act, float slope,
                       cudaStream_t stream);
+/* b200_bn_finalize + b200_bn_act_apply in one launch (coefficients derived in-kernel; block 0
+ * publishes scale/shift/mean/rstd for the backward and updates the running statistics). */
+int b200_bn_norm_act(const void* x, int x_ld, void* y, int y_ld, int C, int64_t npix,
+                     const float* stats, float count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     int training, int act, float slope, float* scale, float* shift,
+                     float* mean_out, float* rstd_out, cudaStream_t stream);
 int b200_bn_act_bwd_reduce(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
                            int z_ld, int C, int64_t npix, const float* scale, const float* shift,
                            const float* mean, const float* rstd, int act, float slope, float* red,

@@ -151,14 +151,24 @@ def test_discriminator_forward_backward(cuda_lib, kind):
     print(kind, "out rel-L2", rel_l2(y, yo), "loss", loss.item(), loss_o.item())
     assert rel_l2(y, yo) < 2e-2
     assert abs(loss.item() - loss_o.item()) < 2e-3 * max(1.0, abs(loss_o.item()))
+    # yard-stick: torch's own bf16 autocast on the oracle graph.  Gate = 0.995, or the yard-stick
+    # minus 0.03 where bf16 itself cannot do better (the 8-BatchNorm variant; parameters whose exact
+    # gradient is zero -- a bias or a scale in front of a scale-invariant BatchNorm -- are pure noise
+    # for both and are skipped when the yard-stick is below 0.5).
+    osd2 = to_device(sd, DEV, True)
+    po2 = pq.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = O.discriminator_forward(kind, osd2, po2, training=True)
+    O.bce_with_logits_const(y2.float(), 0.0).backward()
+    names = dict(d.named_parameters())
     for k, v in osd.items():
         if v.requires_grad:
-            if kind == "dwsep_bn" and k.endswith(".bias") and k.startswith("conv"):
-                continue  # a bias in front of a train-mode BatchNorm has an exactly-zero gradient (noise only)
-            pg = dict(d.named_parameters())[k].grad
-            c = cosine(pg, v.grad)
-            assert c > (0.95 if kind == "dwsep_bn" else 0.995), (k, c)
-    assert cosine(pin.grad, po.grad) > (0.95 if kind == "dwsep_bn" else 0.995)
+            yard = cosine(osd2[k].grad, v.grad)
+            if yard < 0.5:
+                continue
+            c = cosine(names[k].grad, v.grad)
+            assert c > min(0.995, yard - 0.03), (k, c, yard)
+    assert cosine(pin.grad, po.grad) > min(0.995, cosine(po2.grad, po.grad) - 0.03)
 
 
 def test_fused_losses_against_torch(cuda_lib):
