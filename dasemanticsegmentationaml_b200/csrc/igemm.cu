@@ -654,10 +654,24 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   const int stage_bytes = (2 + p.BNW / 64) * kpix * 128;
   const int total_tiles = p.tiles_h * p.tiles_w * N;
   const int ytiles = n_taps * p.co_tiles * p.ci_tiles;
-  int splits = (148 * 2 + ytiles - 1) / ytiles;  // about two CTAs per SM overall
-  // every split adds a full set of fp32 atomics: keep >= 8 pixel tiles (K iterations) per CTA
-  if (splits > total_tiles / 8) splits = total_tiles / 8;
-  if (splits < 1) splits = 1;
+  // Pixel-range splits: each split adds a full set of fp32 atomics (out_elems of them, ~170 G/s
+  // chip-wide measured) but shortens the serial K loop; pick the split count minimising
+  //   waves(s) * iterations(s) * t_iter + out_elems * s / atomic_rate
+  // with t_iter ~ the L2-bound time of one 64-pixel K step (measured ~0.86 us at BNW = 256).
+  const double t_iter_us = 0.22 + 0.64 * (double)p.BNW / 256.0;
+  const double out_elems = (double)n_taps * p.co_tiles * 128.0 * p.ci_tiles * p.BNW;
+  int splits = 1;
+  double best = 1e30;
+  for (int s = 1; s <= total_tiles && s <= 64; ++s) {
+    const int ctas = ytiles * s;
+    const int waves = (ctas + 147) / 148;
+    const int iters = (total_tiles + s - 1) / s;
+    const double t = (double)waves * iters * t_iter_us + out_elems * s / 170e3;
+    if (t < best) {
+      best = t;
+      splits = s;
+    }
+  }
   p.splits = splits;
   p.stages = pick_stages(stage_bytes, (total_tiles + splits - 1) / splits);
   p.dw = dw;

@@ -89,62 +89,74 @@ stem_fwd_kernel(const float* __restrict__ img, int N, int H, int W, const float*
 }
 
 // dw[co][ci][r][s] += sum_pixels dz[pixel][co] * img[ci][2*ho + r - 1][2*wo + s - 1]
-// One thread = one pixel x 4 output channels (8 threads per pixel), 108 accumulators, grid-stride
-// over pixels, block-level reduction in shared memory, then one atomic per filter element.
-__global__ void __launch_bounds__(256)
+// A [32 x 27] = dz^T [32 x P] * xcol [P x 27] product on the CUDA cores, tiled through shared
+// memory: a block stages 64 pixels (dz as fp32, the 27-tap input column as fp32), then 288 threads
+// = 4 pixel groups x (8 co-quads x 9 tap-triples) accumulate 4x3 register tiles; block totals go
+// to the global gradient with one atomic per filter element.
+constexpr int kSwP = 64;       // pixels per stage
+constexpr int kSwThreads = 288;
+__global__ void __launch_bounds__(kSwThreads)
 stem_wgrad_kernel(const float* __restrict__ img, int N, int H, int W,
                   const __nv_bfloat16* __restrict__ dz, int dz_ld, int Ho, int Wo,
                   float* __restrict__ dw) {
+  __shared__ float s_dz[kSwP][kStemCout + 1];
+  __shared__ float s_x[kSwP][28];
   __shared__ float s_acc[kStemCout * 27];
-  for (int i = threadIdx.x; i < kStemCout * 27; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
-  const int q = threadIdx.x & 7;  // channel quad
-  float acc[27][4];
+  for (int i = threadIdx.x; i < kStemCout * 27; i += kSwThreads) s_acc[i] = 0.f;
+  const int grp = threadIdx.x / 72;          // pixel group 0..3
+  const int lt = threadIdx.x % 72;
+  const int cq = lt & 7;                     // co quad: co = cq*4 .. +3
+  const int tt = lt >> 3;                    // tap triple: t = tt*3 .. +2
+  float acc[4][3];
 #pragma unroll
-  for (int t = 0; t < 27; ++t)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
-  const int64_t npix = (int64_t)N * Ho * Wo;
-  for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < npix;
-       p += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    const int wo = (int)(p % Wo);
-    const int ho = (int)((p / Wo) % Ho);
-    const int n = (int)(p / ((int64_t)Wo * Ho));
-    const uint2 u = *reinterpret_cast<const uint2*>(dz + p * dz_ld + q * 4);
-    const float2 d01 = unpack_bf16(u.x), d23 = unpack_bf16(u.y);
-#pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
-      const float* plane = img + ((int64_t)n * 3 + ci) * H * W;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int h = ho * 2 + r - 1;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int ww = wo * 2 + s - 1;
-          float v = 0.f;
-          if (h >= 0 && h < H && ww >= 0 && ww < W)
-            v = __bfloat162float(__float2bfloat16(__ldg(plane + (int64_t)h * W + ww)));
-          const int t = ci * 9 + r * 3 + s;
-          acc[t][0] += v * d01.x;
-          acc[t][1] += v * d01.y;
-          acc[t][2] += v * d23.x;
-          acc[t][3] += v * d23.y;
-        }
+    for (int b = 0; b < 3; ++b) acc[a][b] = 0.f;
+  const int npix = N * Ho * Wo;
+  for (int base = blockIdx.x * kSwP; base < npix; base += gridDim.x * kSwP) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSwP * kStemCout / 2; i += kSwThreads) {
+      const int px = i / (kStemCout / 2), c2 = i % (kStemCout / 2);
+      float2 v = make_float2(0.f, 0.f);
+      if (base + px < npix)
+        v = unpack_bf16(*reinterpret_cast<const uint32_t*>(dz + (size_t)(base + px) * dz_ld + c2 * 2));
+      s_dz[px][c2 * 2] = v.x;
+      s_dz[px][c2 * 2 + 1] = v.y;
+    }
+    for (int i = threadIdx.x; i < kSwP * 27; i += kSwThreads) {
+      const int px = i / 27, t = i % 27;
+      float v = 0.f;
+      const int p = base + px;
+      if (p < npix) {
+        const int wo = p % Wo, ho = (p / Wo) % Ho, n = p / (Wo * Ho);
+        const int ci = t / 9, r = (t % 9) / 3, sx = t % 3;
+        const int h = ho * 2 + r - 1, ww = wo * 2 + sx - 1;
+        if (h >= 0 && h < H && ww >= 0 && ww < W)
+          v = __bfloat162float(__float2bfloat16(__ldg(img + ((size_t)(n * 3 + ci) * H + h) * W + ww)));
       }
+      s_x[px][t] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = grp; px < kSwP; px += 4) {
+      float d[4], x[3];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) d[a] = s_dz[px][cq * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) x[b] = s_x[px][tt * 3 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc[a][b] += d[a] * x[b];
     }
   }
-  // lanes with equal (lane & 7) hold the same channel quad: reduce over xor 8, 16
-#pragma unroll
-  for (int t = 0; t < 27; ++t)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v = acc[t][j];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(q * 4 + j) * 27 + t], v);
-    }
   __syncthreads();
-  for (int i = threadIdx.x; i < kStemCout * 27; i += blockDim.x) atomicAdd(&dw[i], s_acc[i]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) atomicAdd(&s_acc[(cq * 4 + a) * 27 + tt * 3 + b], acc[a][b]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kStemCout * 27; i += kSwThreads) atomicAdd(&dw[i], s_acc[i]);
 }
 
 }  // namespace b200
@@ -167,11 +179,10 @@ int b200_stem_fwd(const float* img, int N, int H, int W, const float* w, void* z
 int b200_stem_wgrad(const float* img, int N, int H, int W, const void* dz, int dz_ld, float* dw,
                     cudaStream_t stream) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int64_t threads = (int64_t)N * Ho * Wo * 8;
-  int64_t blocks = (threads + 256 * 16 - 1) / (256 * 16);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  int64_t blocks = ((int64_t)N * Ho * Wo + kSwP - 1) / kSwP;
+  if (blocks > 148 * 6) blocks = 148 * 6;
   if (blocks < 1) blocks = 1;
-  stem_wgrad_kernel<<<(int)blocks, 256, 0, stream>>>(img, N, H, W, static_cast<const __nv_bfloat16*>(dz), dz_ld, Ho, Wo, dw);
+  stem_wgrad_kernel<<<(int)blocks, kSwThreads, 0, stream>>>(img, N, H, W, static_cast<const __nv_bfloat16*>(dz), dz_ld, Ho, Wo, dw);
   return check_launch("stem_wgrad");
 }
 
