@@ -12,6 +12,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include <stdlib.h>
+
 #include "igemm.cuh"
 #include "ptx.cuh"
 #include "status.h"
@@ -87,7 +89,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if ((int)blockIdx.x >= tiles_per_img * p.n_img) return;  // class with a smaller sub-grid
   const int n_img = blockIdx.x / tiles_per_img;
   const int t_in = blockIdx.x - n_img * tiles_per_img;
-  const int h0 = (t_in / p.tiles_w[z]) * p.th;
+  const int h0 = (t_in / p.tiles_w[z]) * p.th * p.mt;
   const int w0 = (t_in % p.tiles_w[z]) * p.tw;
   const int n0 = blockIdx.y * p.BN;
 
@@ -95,8 +97,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = 128u * p.KC * 2u;
+  const uint32_t a_sub = 128u * p.KC * 2u;            // one sub-tile of A
+  const uint32_t a_bytes = a_sub * p.mt;              // the TMA box spans all sub-tiles
   const uint32_t b_bytes = (uint32_t)p.BN * p.KC * 2u;
+  const uint32_t tmem_cols = (uint32_t)(p.mt * p.BN) <= 32 ? 32u : (p.mt * p.BN <= 64 ? 64u : (p.mt * p.BN <= 128 ? 128u : (p.mt * p.BN <= 256 ? 256u : 512u)));
   const uint32_t stage_bytes = a_bytes + b_bytes;  // both multiples of 1024
   const int cin_blocks = p.cin_pad / p.KC;
   const int nk = p.n_taps[z] * cin_blocks;
@@ -113,7 +117,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars.tmem_base), p.BN < 32 ? 32 : p.BN);
+    tmem_alloc(smem_u32(&bars.tmem_base), tmem_cols);
     tmem_relinquish();
   }
   if (warp == 0 && lane == 0) {
@@ -160,9 +164,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t sa = smem_base + s * stage_bytes;
         const uint32_t sb = sa + a_bytes;
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, layout);
           const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
-          umma_f16(tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < p.mt; ++j) {
+            const uint64_t da = make_smem_desc(sa + j * a_sub + k * 32, 16, sbo, layout);
+            umma_f16(tmem + j * p.BN, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(smem_u32(&bars.empty[s]));  // frees the stage once these MMAs retire
       }
@@ -173,54 +179,56 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int hl = row / p.tw, wl = row - hl * p.tw;
-    const int h = h0 + hl, w = w0 + wl;
-    const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
-    const size_t pix =
-        ((size_t)n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
-    const size_t obase = pix * p.out_ld + p.out_coff + n0;
 
     mbar_wait(smem_u32(&bars.accum), 0);
     tc_fence_after();
-    for (int c = 0; c < p.BN; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, r);
-      tmem_ld_wait();
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(r[j]);
-        if (p.bias != nullptr) x += __ldg(p.bias + n0 + c + j);
-        v[j] = apply_act(x, p.act, p.slope);
-      }
-      if (valid) {
-        if (p.out_f32) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c);
-          o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                            pack_bf16(v[6], v[7]));
-          o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-        }
-      }
-      if (p.stats != nullptr) {
-        float s1[16], s2[16];
+    for (int sub = 0; sub < p.mt; ++sub) {
+      const int h = h0 + sub * p.th + hl, w = w0 + wl;
+      const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+      const size_t pix =
+          ((size_t)n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
+      const size_t obase = pix * p.out_ld + p.out_coff + n0;
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + sub * p.BN + c, r);
+        tmem_ld_wait();
+        float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          // statistics of the values as stored (bf16-rounded), so mean/var describe the tensor
-          // the normalisation pass will read
-          float x = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]))) : 0.f;
-          s1[j] = x;
-          s2[j] = x * x;
+          float x = __uint_as_float(r[j]);
+          if (p.bias != nullptr) x += __ldg(p.bias + n0 + c + j);
+          v[j] = apply_act(x, p.act, p.slope);
         }
-        const float t1 = column_sums16(s1, lane);
-        const float t2 = column_sums16(s2, lane);
-        if ((lane & 1) == 0) {
-          const int col = c + column_of_lane(lane);
-          atomicAdd(&s_stats[0][col], t1);
-          atomicAdd(&s_stats[1][col], t2);
+        if (valid) {
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c);
+            o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                              pack_bf16(v[6], v[7]));
+            o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                              pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          }
+        }
+        if (p.stats != nullptr) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // statistics of the values as stored (bf16-rounded), so mean/var describe the tensor
+            // the normalisation pass will read
+            float x = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]))) : 0.f;
+            s1[j] = x;
+            s2[j] = x * x;
+          }
+          const float t1 = column_sums16(s1, lane);
+          const float t2 = column_sums16(s2, lane);
+          if ((lane & 1) == 0) {
+            const int col = c + column_of_lane(lane);
+            atomicAdd(&s_stats[0][col], t1);
+            atomicAdd(&s_stats[1][col], t2);
+          }
         }
       }
     }
@@ -238,7 +246,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, p.BN < 32 ? 32 : p.BN);
+    tmem_dealloc(tmem, tmem_cols);
   }
 }
 
@@ -497,19 +505,20 @@ static int pick_bn(int cout_pad, int m_tiles) {
 // Pipeline depth: prefer <= 110 KB so that two CTAs share an SM (one's epilogue overlaps the
 // other's main loop); fall back to the whole 190 KB for the widest tiles.
 static int pick_stages(int stage_bytes, int nk) {
-  int s = (110 * 1024) / stage_bytes;
-  if (s < 3) s = (190 * 1024) / stage_bytes;
-  if (s > kMaxStages) s = kMaxStages;
-  if (s > nk) s = nk < 2 ? 2 : nk;
+  (void)nk;
+  // two stages: with <= 96 KB per CTA two CTAs co-reside on an SM, which measured faster than any
+  // deeper pipeline with a single resident CTA
+  int s = 2;
+  while (s > 2 && s * stage_bytes > 110 * 1024) --s;
   return s;
 }
 
 static int g_smem_optin_done = 0;
 static int ensure_smem_optin() {
   if (g_smem_optin_done) return B200_OK;
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e != cudaSuccess) return set_error(B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   g_smem_optin_done = 1;
   return B200_OK;
@@ -546,7 +555,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
                     int n_classes, const int* class_Ho, const int* class_Wo, const int* class_oa,
                     const int* class_ob, const int* class_ntaps, const int* taps, int taps_stride,
                     int in_stride, int out_stride, const float* bias, int act, float slope,
-                    float* stats, int stats_ld, int bn_override, cudaStream_t stream) {
+                    float* stats, int stats_ld, int tune, cudaStream_t stream) {
+  // tune = BN | (mt << 12) | (stages << 16); a zero field = choose automatically
+  const int bn_override = tune & 0xFFF, mt_override = (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
   if (n_classes < 1 || n_classes > kMaxClasses) return set_error(B200_EINVAL, "conv_igemm: bad class count %d", n_classes);
   if (cin_pad % 32) return set_error(B200_EINVAL, "conv_igemm: cin_pad %d not a multiple of 32", cin_pad);
   if (in_ld % 8 || in_coff % 8 || out_ld % 8 || out_coff % 8)
@@ -561,16 +572,54 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   int max_wo = 0;
   for (int z = 0; z < n_classes; ++z) max_wo = class_Wo[z] > max_wo ? class_Wo[z] : max_wo;
   pick_patch(max_wo, &p.th, &p.tw, 128);
+  int max_nk = 0;
+  for (int z = 0; z < n_classes; ++z) {
+    if (class_ntaps[z] > kMaxTaps) return set_error(B200_EINVAL, "conv_igemm: too many taps");
+    max_nk = class_ntaps[z] > max_nk ? class_ntaps[z] : max_nk;
+  }
+  max_nk *= cin_pad / p.KC;
+
+  // Tile shape (measured with scripts/tune_conv.py, profiles/r1_tile_sweep.txt): what matters most
+  // is that TWO CTAs share an SM -- one's prologue/epilogue overlaps the other's main loop -- so the
+  // pipeline is kept at 2 stages (<= 96 KB) and BN is the widest tile that divides Cout; a second
+  // 128-pixel sub-tile (mt = 2) pays off only for BN = 128 with a long K loop.
+  int best_bn = 0, best_mt = 1;
+  const int bn_cands[5] = {256, 128, 64, 32, 16};
+  long m_tiles = 0;
+  for (int z = 0; z < n_classes; ++z)
+    m_tiles += (long)((class_Ho[z] + p.th - 1) / p.th) * ((class_Wo[z] + p.tw - 1) / p.tw) * N;
+  for (int bi = 0; bi < 5 && best_bn == 0; ++bi) {
+    const int bn = bn_cands[bi];
+    if (filt_rows % bn) continue;
+    if (bn_override > 0 && bn != bn_override) continue;
+    // keep at least ~one wave of CTAs unless nothing smaller divides Cout
+    if (m_tiles * (filt_rows / bn) < 148 && bn > 32) continue;
+    best_bn = bn;
+  }
+  if (best_bn == 0) best_bn = (bn_override > 0 && filt_rows % bn_override == 0) ? bn_override : (filt_rows % 32 == 0 ? 32 : 16);
+  if (best_bn == 128 && max_nk >= 16 && m_tiles * (filt_rows / best_bn) >= 1184 && p.th * 2 * in_stride <= 256)
+    best_mt = 2;
+  if (mt_override > 0) best_mt = mt_override;
+  if (best_bn == 0) return set_error(B200_EINVAL, "conv_igemm: no tile shape for %d output channels", filt_rows);
+  // tuning knobs (scripts/tune_conv.py): B200_BN / B200_MT / B200_STAGES override the choice
+  const char* e_bn = getenv("B200_BN");
+  const char* e_mt = getenv("B200_MT");
+  const char* e_st = getenv("B200_STAGES");
+  if (e_bn && atoi(e_bn) > 0 && filt_rows % atoi(e_bn) == 0) best_bn = atoi(e_bn);
+  if (e_mt && atoi(e_mt) > 0) best_mt = atoi(e_mt);
+  if (best_mt * best_bn > 512) best_mt = 512 / best_bn;
+  while (best_mt > 1 && p.th * best_mt * in_stride > 256) best_mt >>= 1;
+  p.BN = best_bn;
+  p.mt = best_mt;
   int max_tiles = 0;
   for (int z = 0; z < n_classes; ++z) {
     p.Ho[z] = class_Ho[z];
     p.Wo[z] = class_Wo[z];
-    p.tiles_h[z] = (class_Ho[z] + p.th - 1) / p.th;
+    p.tiles_h[z] = (class_Ho[z] + p.th * p.mt - 1) / (p.th * p.mt);
     p.tiles_w[z] = (class_Wo[z] + p.tw - 1) / p.tw;
     p.oa[z] = class_oa[z];
     p.ob[z] = class_ob[z];
     p.n_taps[z] = class_ntaps[z];
-    if (class_ntaps[z] > kMaxTaps) return set_error(B200_EINVAL, "conv_igemm: too many taps");
     for (int t = 0; t < class_ntaps[z]; ++t) {
       const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
       p.tap_dh[z][t] = (int8_t)tp[0];
@@ -584,14 +633,23 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   p.n_img = N;
   p.in_stride = in_stride;
   p.cin_pad = cin_pad;
-  p.BN = bn_override > 0 ? bn_override : pick_bn(filt_rows, max_tiles);
-  if (filt_rows % p.BN) return set_error(B200_EINVAL, "conv_igemm: BN %d does not divide %d", p.BN, filt_rows);
-  const int stage_bytes = 128 * p.KC * 2 + p.BN * p.KC * 2;
-  int max_nk = 0;
-  for (int z = 0; z < n_classes; ++z) max_nk = class_ntaps[z] > max_nk ? class_ntaps[z] : max_nk;
-  max_nk *= cin_pad / p.KC;
-  p.stages = pick_stages(stage_bytes, max_nk);
-  if (p.stages < 2) return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
+  const int stage_bytes = p.mt * 128 * p.KC * 2 + p.BN * p.KC * 2;
+  {
+    // few CTAs (<= one per SM): nothing to co-schedule, so go deep; plenty: two stages, many CTAs/SM
+    const long ctas = (long)max_tiles * n_classes * (filt_rows / p.BN);
+    const int budget = ctas <= 148 ? 220 * 1024 : (ctas <= 296 ? 110 * 1024 : 2 * stage_bytes);
+    int st = budget / stage_bytes;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st > max_nk) st = max_nk;
+    if (st < 2) st = 2;
+    p.stages = st;
+  }
+  if (st_override >= 2) p.stages = st_override;
+  if (e_st && atoi(e_st) >= 2) {
+    p.stages = atoi(e_st);
+    while (p.stages > 2 && p.stages * stage_bytes > 220 * 1024) --p.stages;
+  }
+  if (p.stages < 2 || p.stages * stage_bytes > 222 * 1024) return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
   p.out = out;
   p.out_ld = out_ld;
   p.out_coff = out_coff;
@@ -606,7 +664,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   p.stats_ld = stats_ld;
 
   CUtensorMap tmA, tmB;
-  rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th, in_stride, p.KC * 2);
+  rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
   if (rc) return rc;
   rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);
   if (rc) return rc;
@@ -621,7 +679,10 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
 int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int Ho, int Wo,
                     const void* x, int x_ld, int x_coff, int Cin, int Hin, int Win,
                     int n_taps, const int* taps /* [n_taps][3] = dh, dw, rs */, int RS,
-                    int in_stride, float* dw, cudaStream_t stream) {
+                    int in_stride, float* dw, int tune, cudaStream_t stream) {
+  // tune = BNW | (stages << 12) | (splits << 16) | (kpix/64 << 28); a zero field = automatic
+  const int bnw_override = tune & 0xFFF, st_override = (tune >> 12) & 0xF;
+  const int sp_override = (tune >> 16) & 0xFFF, kp_override = (tune >> 28) & 0x3;
   if (n_taps < 1 || n_taps > kMaxTaps) return set_error(B200_EINVAL, "conv_wgrad: bad tap count");
   if (dz_ld % 8 || dz_coff % 8 || x_ld % 8 || x_coff % 8)
     return set_error(B200_EINVAL, "conv_wgrad: channel strides/offsets must be multiples of 8");
@@ -629,7 +690,7 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   if (rc) return rc;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  pick_patch(Wo, &p.th, &p.tw, 64);
+  pick_patch(Wo, &p.th, &p.tw, kp_override == 2 ? 128 : 64);
   p.Ho = Ho;
   p.Wo = Wo;
   p.tiles_h = (Ho + p.th - 1) / p.th;
@@ -649,6 +710,7 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   const int cin64 = ((Cin + 63) / 64) * 64;
   // ci per CTA: a multiple of 64 (one TMA box each) up to 256 that tiles cin64 with least waste
   p.BNW = cin64 <= 256 ? cin64 : ((cin64 % 256 == 0) ? 256 : (cin64 % 192 == 0 ? 192 : 128));
+  if (bnw_override >= 64 && bnw_override <= 256 && bnw_override % 64 == 0) p.BNW = bnw_override;
   p.ci_tiles = (cin64 + p.BNW - 1) / p.BNW;
   const int kpix = p.th * p.tw;
   const int stage_bytes = (2 + p.BNW / 64) * kpix * 128;
@@ -672,8 +734,20 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
       splits = s;
     }
   }
+  if (sp_override > 0) splits = sp_override > total_tiles ? total_tiles : sp_override;
   p.splits = splits;
-  p.stages = pick_stages(stage_bytes, (total_tiles + splits - 1) / splits);
+  {
+    int st = (110 * 1024) / stage_bytes;
+    if (st < 3) st = (190 * 1024) / stage_bytes;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 2) st = 2;
+    p.stages = st;
+  }
+  if (st_override >= 2) {
+    p.stages = st_override;
+    while (p.stages > 2 && p.stages * stage_bytes > 220 * 1024) --p.stages;
+  }
+  if (p.stages * stage_bytes > 222 * 1024) return set_error(B200_EINVAL, "conv_wgrad: tile does not fit shared memory");
   p.dw = dw;
 
   CUtensorMap tmDZ, tmX;

@@ -21,7 +21,9 @@ struct ConvParams {
   int8_t tap_k[kMaxClasses][kMaxTaps];  // index of the tap's K-slab in the packed filter
   int oa[kMaxClasses], ob[kMaxClasses];  // output pixel offset of the class
   int n_img;
-  int th, tw;        // patch of th*tw == 128 output pixels per CTA
+  int th, tw;        // sub-tile patch: th*tw == 128 output pixels (one M=128 accumulator)
+  int mt;            // sub-tiles per CTA, stacked along h: the CTA covers (th*mt) x tw pixels and
+                     // reuses each filter tile for mt accumulators (less L2 traffic per FLOP)
   int in_stride;     // traversal stride over the input
   int cin_pad;       // K elements per tap in the packed filter (multiple of KC)
   int KC;            // channels per pipeline stage: 64 (128B swizzle) or 32 (64B swizzle)

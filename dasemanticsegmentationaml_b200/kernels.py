@@ -50,7 +50,8 @@ def pack_filter(weight, transpose=False):
 class Geometry(object):
     """Tap tables of one implicit-GEMM launch, with the ctypes arrays pre-built (cached per shape)."""
 
-    def __init__(self, classes, in_stride, out_stride, hout, wout):
+    def __init__(self, classes, in_stride, out_stride, hout, wout, key=""):
+        self.key = key
         self.classes, self.in_stride, self.out_stride, self.Hout, self.Wout = classes, in_stride, out_stride, hout, wout
         self.tmax = max(len(c["taps"]) for c in classes)
         flat = []
@@ -80,7 +81,8 @@ def fwd_geometry(hin, win, r, s, stride, pad):
         ho = (hin + 2 * pad - r) // stride + 1
         wo = (win + 2 * pad - s) // stride + 1
         taps = [(i - pad, j - pad, i * s + j) for i in range(r) for j in range(s)]
-        g = _geom_cache[key] = Geometry([dict(Ho=ho, Wo=wo, oa=0, ob=0, taps=taps)], stride, 1, ho, wo)
+        g = _geom_cache[key] = Geometry([dict(Ho=ho, Wo=wo, oa=0, ob=0, taps=taps)], stride, 1, ho, wo,
+                                        "f%dx%ds%dp%d" % (r, s, stride, pad))
     return g
 
 
@@ -93,7 +95,8 @@ def dgrad_geometry(hin, win, r, s, stride, pad):
         return g
     if stride == 1:
         taps = [(pad - i, pad - j, i * s + j) for i in range(r) for j in range(s)]
-        g = Geometry([dict(Ho=hin, Wo=win, oa=0, ob=0, taps=taps)], 1, 1, hin, win)
+        g = Geometry([dict(Ho=hin, Wo=win, oa=0, ob=0, taps=taps)], 1, 1, hin, win,
+                     "d%dx%ds%dp%d" % (r, s, stride, pad))
     else:
         assert stride == 2
         classes = []
@@ -107,12 +110,40 @@ def dgrad_geometry(hin, win, r, s, stride, pad):
                     raise ValueError("strided dgrad class without taps (1x1 stride-2 conv?)")
                 if hc > 0 and wc > 0:
                     classes.append(dict(Ho=hc, Wo=wc, oa=a, ob=b, taps=taps))
-        g = Geometry(classes, 1, 2, hin, win)
+        g = Geometry(classes, 1, 2, hin, win, "d%dx%ds%dp%d" % (r, s, stride, pad))
     _geom_cache[key] = g
     return g
 
 
-def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_tile=0, k_real=None, n_real=None):
+# ------------------------------------------------------------------ tuned tile table
+# Produced on a B200 by scripts/tune_conv.py (exhaustive sweep per layer shape); a missing key falls
+# back to the launcher's heuristic.  RECORD, when a list, collects the keys a workload touches.
+TUNED = {}
+RECORD = None
+
+
+def load_tuned(path=None):
+    import json
+    import os
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned_tiles.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            TUNED.update({k: int(v) for k, v in json.load(f).items()})
+
+
+load_tuned()
+
+
+def conv_key(n, hin, win, cin_pad, rows_pad, geom, f32, stats):
+    return "conv %d %d %d c%d r%d %s%s%s" % (n, hin, win, cin_pad, rows_pad, geom.key, " f32" if f32 else "",
+                                              " st" if stats else "")
+
+
+def wgrad_key(n, ho, wo, cout, cin, r, s, stride):
+    return "wgrad %d %d %d co%d ci%d %dx%ds%d" % (n, ho, wo, cout, cin, r, s, stride)
+
+
+def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_tile=None, k_real=None, n_real=None):
     """out[N,Hout,Wout,rows_pad] = implicit-GEMM conv of x with a packed filter (see pack_filter).
     k_real / n_real: un-padded reduction / output channel counts (for the algorithmic FLOP count)."""
     n, hin, win, cin, in_ld = _nhwc_meta(x)
@@ -127,6 +158,13 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.dim() == 2 and stats.shape[0] == 2
     flops = 2.0 * geom.px_taps * n * (k_real or min(cin, cin_pad)) * (n_real or rows_pad)
+    if bn_tile is None:
+        key = conv_key(n, hin, win, cin_pad, rows_pad, geom, out_f32, stats is not None)
+        bn_tile = TUNED.get(key, 0)
+        if RECORD is not None:
+            RECORD.append(("conv", key, dict(n=n, hin=hin, win=win, cin=cin, in_ld=in_ld, rows=rows_pad, cin_pad=cin_pad,
+                                              n_slabs=n_slabs, geom=geom, f32=out_f32, stats=stats is not None,
+                                              bias=bias is not None, out_ld=out_ld, flops=flops)))
     call("b200_conv_igemm",
          ptr(x), c_int(in_ld), c_int(0), c_int(cin), c_int(n), c_int(hin), c_int(win),
          ptr(filt), c_int(rows_pad), c_int(cin_pad), c_int(n_slabs),
@@ -142,7 +180,7 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
 _wgrad_taps = {}
 
 
-def conv_wgrad(dz, x, dw, r, s, stride, pad):
+def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None):
     """dw[Cout,Cin,R,S] (fp32) += sum_pixels dz (x) x ; dz [N,Ho,Wo,>=Cout], x [N,Hin,Win,>=Cin]."""
     n, ho, wo, _, dz_ld = _nhwc_meta(dz)
     n2, hin, win, _, x_ld = _nhwc_meta(x)
@@ -155,10 +193,16 @@ def conv_wgrad(dz, x, dw, r, s, stride, pad):
             for j in range(s):
                 flat += [i - pad, j - pad, i * s + j]
         taps = _wgrad_taps[(r, s, pad)] = int_array(flat)
-    call("b200_conv_wgrad", 
+    if tune is None:
+        key = wgrad_key(n, ho, wo, cout, cin, r, s, stride)
+        tune = TUNED.get(key, 0)
+        if RECORD is not None:
+            RECORD.append(("wgrad", key, dict(n=n, ho=ho, wo=wo, cout=cout, cin=cin, r=r, s=s, stride=stride, pad=pad,
+                                               hin=hin, win=win, dz_c=dz.shape[3], x_c=x.shape[3], dz_ld=dz_ld, x_ld=x_ld)))
+    call("b200_conv_wgrad",
         ptr(dz), c_int(dz_ld), c_int(0), c_int(cout), c_int(n), c_int(ho), c_int(wo),
         ptr(x), c_int(x_ld), c_int(0), c_int(cin), c_int(hin), c_int(win),
-        c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), stream(),
+        c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), c_int(tune), stream(),
         flops=2.0 * n * ho * wo * r * s * cout * cin, tag="px%d co%d ci%d taps%d s%d" % (n * ho * wo, cout, cin, r * s, stride))
     return dw
 

@@ -36,10 +36,12 @@ def allreduce_grads(params, world=None):
     if not grads:
         return
     flat = torch._utils._flatten_dense_tensors(grads)
-    dist.all_reduce(flat)
-    flat.div_(world)
-    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-        g.copy_(f)
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world)
+    torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
 
 
 def supervised_loss(model, images, labels, loss="ce", ohem_threshold=0.3567, ohem_keep=None):

@@ -65,20 +65,22 @@ int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStrea
  * with the transposed filter and (for stride 2) the four output-parity classes it is the data
  * gradient autograd derives for the same layers.  Out-of-bounds input is read as zero (padding).
  * stats != NULL: adds per-channel sum / sum of squares of the stored values to stats[0][.] /
- * stats[1][.] (train-mode BatchNorm, stdcnet.py:10,14).  bn_override: 0 = auto N tile. */
+ * stats[1][.] (train-mode BatchNorm, stdcnet.py:10,14).  tune: 0 = automatic tile, else
+ * BN | (sub-tiles << 12) | (pipeline stages << 16) from the tuned table. */
 int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int Hin, int Win,
                     const void* filt, int filt_rows, int cin_pad, int n_slabs, void* out, int out_ld,
                     int out_coff, int Hout, int Wout, int out_f32, int n_classes, const int* class_Ho,
                     const int* class_Wo, const int* class_oa, const int* class_ob,
                     const int* class_ntaps, const int* taps, int taps_stride, int in_stride,
                     int out_stride, const float* bias, int act, float slope, float* stats,
-                    int stats_ld, int bn_override, cudaStream_t stream);
+                    int stats_ld, int tune, cudaStream_t stream);
 
 /* Weight gradient dW[Cout][Cin][RS] (fp32, PyTorch layout, accumulated) of the same convolutions:
- * dW[co][ci][rs] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]; taps = [n_taps][3] = (dh, dw, rs). */
+ * dW[co][ci][rs] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]; taps = [n_taps][3] = (dh, dw, rs).
+ * tune: 0 = automatic, else ci-tile | (stages << 12) | (pixel splits << 16) | (K pixels / 64 << 28). */
 int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int Ho, int Wo,
                     const void* x, int x_ld, int x_coff, int Cin, int Hin, int Win, int n_taps,
-                    const int* taps, int RS, int in_stride, float* dw, cudaStream_t stream);
+                    const int* taps, int RS, int in_stride, float* dw, int tune, cudaStream_t stream);
 
 /* Stem ConvX(3, 32, 3, 2) (stdcnet.py:171) straight from the fp32 NCHW image: z = conv (bf16 NHWC,
  * raw, pre-BatchNorm) + BatchNorm statistics; and its filter gradient. */

@@ -1,0 +1,170 @@
+"""Auto-tuner for the implicit-GEMM tile knobs (run on a B200).
+
+Records every distinct conv / wgrad launch shape of the DA train step (all three discriminator
+variants; optionally the 720x1280 supervised step), sweeps the tile configurations of each shape
+with synthetic tensors (CUDA events, best of 2 x 10 launches) and writes
+
+    dasemanticsegmentationaml_b200/tuned_tiles.json     {shape key: packed tune word}
+    gpurun_out/tile_sweep.txt                           human-readable report (copy into profiles/)
+
+Usage: python scripts/tune_conv.py [--supervised] [--batch 8]
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from dasemanticsegmentationaml_b200 import build, kernels as K, train as T
+from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, DepthWiseSepFCDiscriminator,
+                                                  DepthWiseSepBNFCDiscriminator)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--supervised", action="store_true")
+ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(K.__file__)), "tuned_tiles.json"))
+args = ap.parse_args()
+
+build.build()
+dev = torch.device("cuda", 0)
+BF = torch.bfloat16
+report = []
+
+
+def log(*a):
+    line = " ".join(str(x) for x in a)
+    print(line, flush=True)
+    report.append(line)
+
+
+# ----------------------------------------------------------------------------- record shapes
+K.TUNED.clear()
+K.RECORD = []
+torch.manual_seed(0)
+nb = args.batch
+model = BiSeNet("STDCNet813", 19).to(dev)
+opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+g = torch.Generator().manual_seed(1)
+x = torch.randn(nb, 3, 512, 1024, generator=g).to(dev)
+xt = torch.randn(nb, 3, 512, 1024, generator=g).to(dev)
+lab = torch.randint(0, 19, (nb, 512, 1024), generator=g).to(dev)
+for cls in (FCDiscriminator, DepthWiseSepFCDiscriminator, DepthWiseSepBNFCDiscriminator):
+    disc = cls(19).to(dev)
+    opt_d = torch.optim.Adam(disc.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    T.train_da_step(model, disc, opt, opt_d, x, lab, xt)
+    del disc, opt_d
+if args.supervised:
+    xs = torch.randn(nb, 3, 720, 1280, generator=g).to(dev)
+    ls = torch.randint(0, 19, (nb, 720, 1280), generator=g).to(dev)
+    T.train_step(model, opt, xs, ls)
+    del xs, ls
+torch.cuda.synchronize()
+records = {}
+for kind, key, meta in K.RECORD:
+    records.setdefault(key, (kind, meta))
+K.RECORD = None
+del model, opt, x, xt, lab
+torch.cuda.empty_cache()
+log("distinct shapes:", len(records))
+
+
+def timeit(fn, reps=10):
+    best = 1e9
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / reps * 1e3)
+    return best
+
+
+tuned = {}
+total_before = total_after = 0.0
+for key, (kind, m) in sorted(records.items()):
+    try:
+        if kind == "conv":
+            geom = m["geom"]
+            xbuf = torch.randn(m["n"], m["hin"], m["win"], m["in_ld"], device=dev).to(BF)
+            xin = xbuf[..., :m["cin"]]
+            filt = (torch.randn(m["rows"], m["n_slabs"], m["cin_pad"], device=dev) * 0.05).to(BF)
+            obuf = torch.empty((m["n"], geom.Hout, geom.Wout, m["out_ld"]), device=dev,
+                               dtype=torch.float32 if m["f32"] else BF)
+            out = obuf[..., :m["rows"]]
+            stats = torch.zeros(2, m["rows"], device=dev) if m["stats"] else None
+            bias = torch.zeros(m["rows"], device=dev) if m["bias"] else None
+            kc = 64 if m["cin_pad"] % 64 == 0 else 32
+            results = []
+
+            def run(tune):
+                K.conv_igemm(xin, filt, out, geom, bias=bias, act=2 if bias is not None else 0, slope=0.2,
+                             stats=stats, bn_tile=tune)
+
+            run(0)
+            base = timeit(lambda: run(0))
+            for bn, mt, st in itertools.product((256, 128, 64, 32, 16), (1, 2), (2, 3, 4, 6)):
+                if m["rows"] % bn or bn * mt > 512:
+                    continue
+                stage = mt * 128 * kc * 2 + bn * kc * 2
+                if st * stage > 216 * 1024:
+                    continue
+                tune = bn | (mt << 12) | (st << 16)
+                try:
+                    run(tune)
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d MT%d S%d" % (bn, mt, st)))
+                except Exception as ex:  # a configuration the launcher rejects
+                    continue
+        else:
+            dz = torch.randn(m["n"], m["ho"], m["wo"], m["dz_ld"], device=dev).to(BF)[..., :m["dz_c"]]
+            xx = torch.randn(m["n"], m["hin"], m["win"], m["x_ld"], device=dev).to(BF)[..., :m["x_c"]]
+            dw = torch.zeros(m["cout"], m["cin"], m["r"], m["s"], device=dev)
+            results = []
+
+            def run(tune):
+                K.conv_wgrad(dz, xx, dw, m["r"], m["s"], m["stride"], m["pad"], tune=tune)
+
+            run(0)
+            base = timeit(lambda: run(0))
+            cin64 = (m["cin"] + 63) // 64 * 64
+            total_px = m["n"] * m["ho"] * m["wo"]
+            for bnw, st, sp, kp in itertools.product((64, 128, 192, 256), (2, 3, 4), (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48),
+                                                     (1, 2)):
+                if bnw > cin64 or (bnw == 192 and cin64 % 192):
+                    continue
+                if (2 + bnw // 64) * (64 * kp) * 128 * st > 216 * 1024:
+                    continue
+                if sp > max(1, total_px // (64 * kp)):
+                    continue
+                tune = bnw | (st << 12) | (sp << 16) | (kp << 28)
+                try:
+                    run(tune)
+                    results.append((timeit(lambda: run(tune), 6), tune, "BNW%d S%d split%d kpix%d" % (bnw, st, sp, 64 * kp)))
+                except Exception:
+                    continue
+        results.sort()
+        best_us, best_tune, best_name = results[0]
+        if best_us < 0.97 * base:
+            tuned[key] = best_tune
+        total_before += base
+        total_after += min(base, best_us)
+        log("%-58s auto %8.1f us | best %8.1f us %-26s | 2nd %s %.1f" % (key, base, best_us, best_name,
+                                                                       results[1][2] if len(results) > 1 else "-",
+                                                                       results[1][0] if len(results) > 1 else 0))
+    except Exception as ex:
+        log("%-58s FAILED %r" % (key, ex))
+    torch.cuda.empty_cache()
+
+log("sum of per-shape times: auto %.1f us -> tuned %.1f us (each shape counted once)" % (total_before, total_after))
+with open(args.out, "w") as f:
+    json.dump(tuned, f, indent=0, sort_keys=True)
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/tile_sweep.txt", "w") as f:
+    f.write("\n".join(report) + "\n")
+with open("gpurun_out/tuned_tiles.json", "w") as f:
+    json.dump(tuned, f, indent=0, sort_keys=True)
+print("wrote", len(tuned), "tuned entries")
