@@ -11,6 +11,23 @@ LIB_PATH = os.path.join(_HERE, "libb200seg.so")
 
 _lib = None
 _checked_devices = set()
+_arity = None          # {entry point: parameter count}, parsed from include/b200seg.h
+_arity_checked = set()
+
+
+def _load_arity():
+    """Parameter counts of every prototype in include/b200seg.h: ctypes cannot see C prototypes, so
+    a wrapper that drifts from the header would otherwise corrupt the call frame silently."""
+    import re
+    global _arity
+    _arity = {}
+    header = os.path.join(os.path.dirname(_HERE), "include", "b200seg.h")
+    if not os.path.exists(header):
+        return
+    text = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    for m in re.finditer(r"\b(b200_\w+)\s*\(([^)]*)\)\s*;", text):
+        params = m.group(2).strip()
+        _arity[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
 
 
 class B200Error(RuntimeError):
@@ -51,6 +68,13 @@ def call(name, *args, flops=0.0, nbytes=0.0, tag=None):
     profiling, bracket it with CUDA events on the launching stream."""
     global launch_count
     fn = getattr(lib(), name)
+    if name not in _arity_checked:
+        if _arity is None:
+            _load_arity()
+        want = _arity.get(name)
+        if want is not None and want != len(args):
+            raise B200Error("%s: wrapper passes %d arguments, include/b200seg.h declares %d" % (name, len(args), want))
+        _arity_checked.add(name)
     if _profile is None:
         rc = fn(*args)
     else:

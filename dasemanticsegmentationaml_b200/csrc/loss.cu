@@ -192,8 +192,10 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
                     int mode, const void* __restrict__ grad_in, int grad_is_bf16, int p_ld,
                     const int64_t* __restrict__ labels, int ignore_index,
                     const float* __restrict__ pixel_weight, const float* __restrict__ coef_num,
-                    const double* __restrict__ coef_den, float coef_scale, float* __restrict__ d_lr) {
+                    const double* __restrict__ coef_den, float coef_scale, float* __restrict__ d_lr,
+                    double* __restrict__ loss_acc) {
   __shared__ float s_g[TH][TW][NC + 1];
+  __shared__ float s_loss[2][TH];
   __shared__ float s_a[TH][MAXJ][NC + 1];
   __shared__ Interp s_iw[TW], s_ih[TH];
   __shared__ int s_xlo[MAXJ], s_xhi[MAXJ];
@@ -210,6 +212,7 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
   __syncthreads();
   const int h = h_base + ty, w = w_base + tx;
   float g[NC];
+  float my_loss = 0.f, my_valid = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c) g[c] = 0.f;
   if (h < H && w < W) {
@@ -229,11 +232,17 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
     } else {
       float v[NC];
       sample_logits<NC>(lr, lr_ld, h_lr, w_lr, n, s_ih[ty], s_iw[tx], v);
+      float tgt = 0.f;
+      const int64_t lab_ce = (mode == 1) ? labels[p] : -1;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) tgt = (c == lab_ce) ? v[c] : tgt;
       float lse;
       softmax_inplace<NC>(v, &lse);
       if (mode == 1) {
-        const int64_t lab = labels[p];
+        const int64_t lab = lab_ce;
         if (lab != ignore_index) {
+          my_loss = fmaxf(lse - tgt, 0.f);
+          my_valid = 1.f;
           float cf = coef_scale * (coef_num != nullptr ? *coef_num : 1.f);
           if (coef_den != nullptr) cf /= (float)fmax(*coef_den, 1e-30);
           if (pixel_weight != nullptr) cf *= pixel_weight[p];
@@ -257,7 +266,25 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) s_g[ty][tx][c] = g[c];
+  if (loss_acc != nullptr) {  // fused forward: this tile's loss sum and valid-pixel count
+    const float wl = warp_sum(my_loss), wv = warp_sum(my_valid);
+    if (tx == 0) {
+      s_loss[0][ty] = wl;
+      s_loss[1][ty] = wv;
+    }
+  }
   __syncthreads();
+  if (loss_acc != nullptr && threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < TH; ++i) {
+      a += s_loss[0][i];
+      b += s_loss[1][i];
+    }
+    if (b > 0.0) {
+      atomicAdd(&loss_acc[0], a);
+      atomicAdd(&loss_acc[1], b);
+    }
+  }
   const int j_min = s_iw[0].i0;
   const int i_min = s_ih[0].i0;
   if (threadIdx.x < MAXJ) {  // columns of the tile that touch low-resolution column j (a contiguous range)
@@ -429,6 +456,20 @@ bce_const_bwd_kernel(const float* __restrict__ x, int count, float target,
   }
 }
 
+// y = x * (*num) * mul / (*den)      (applies the upstream gradient and 1/#valid to a fused CE gradient)
+__global__ void __launch_bounds__(256)
+scale_f32_kernel(const float* __restrict__ x, int64_t count4, const float* __restrict__ num,
+                 const double* __restrict__ den, float mul, float* __restrict__ y) {
+  float cf = mul * (num != nullptr ? *num : 1.f);
+  if (den != nullptr) cf /= (float)fmax(*den, 1e-30);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= cf; v.y *= cf; v.z *= cf; v.w *= cf;
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
+
 static int grid1d(int64_t total, int cap) {
   int64_t b = (total + 255) / 256;
   if (b > cap) b = cap;
@@ -460,7 +501,7 @@ int b200_upsample_bwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
                       int n_classes, int mode, const void* grad_in, int grad_is_bf16, int p_ld,
                       const int64_t* labels, int ignore_index, const float* pixel_weight,
                       const float* coef_num, const double* coef_den, float coef_scale, float* d_lr,
-                      cudaStream_t stream) {
+                      double* loss_acc, cudaStream_t stream) {
   if (n_classes != 19) return set_error(B200_EINVAL, "upsample_bwd: only 19 classes are compiled (got %d)", n_classes);
   if (lr_ld % 4 || lr_ld < 20) return set_error(B200_EINVAL, "upsample_bwd: logits pixel stride %d must be a multiple of 4, >= 20", lr_ld);
   const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
@@ -470,7 +511,8 @@ int b200_upsample_bwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
   const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * N;
   upsample_bwd_kernel<19><<<tiles, TH * TW, 0, stream>>>(lr, lr_ld, N, h_lr, w_lr, H, W, mode, grad_in,
                                                         grad_is_bf16, p_ld, labels, ignore_index,
-                                                        pixel_weight, coef_num, coef_den, coef_scale, d_lr);
+                                                        pixel_weight, coef_num, coef_den, coef_scale, d_lr,
+                                                        loss_acc);
   return check_launch("upsample_bwd");
 }
 
@@ -501,6 +543,13 @@ int b200_ohem_reduce(const float* x, int64_t count, const uint32_t* state, float
 int b200_ohem_weights(const float* x, int64_t count, const float* sel, float* wout, cudaStream_t stream) {
   ohem_weights_kernel<<<grid1d(count, 148 * 8), 256, 0, stream>>>(x, count, sel, wout);
   return check_launch("ohem_weights");
+}
+
+int b200_scale_f32(const float* x, int64_t count, const float* num, const double* den, float mul,
+                   float* y, cudaStream_t stream) {
+  if (count % 4) return set_error(B200_EINVAL, "scale_f32: count must be a multiple of 4");
+  scale_f32_kernel<<<grid1d(count / 4, 148 * 8), 256, 0, stream>>>(x, count / 4, num, den, mul, y);
+  return check_launch("scale_f32");
 }
 
 int b200_bce_const_fwd(const float* x, int count, float target, float* out, cudaStream_t stream) {

@@ -391,12 +391,12 @@ def upsample_fwd(lr, H, W, n_classes, mode, out=None, out_flag=0, p_ld=0, labels
 
 
 def upsample_bwd(lr, H, W, n_classes, mode, d_lr, grad_in=None, grad_is_bf16=0, p_ld=0, labels=None,
-                 ignore_index=255, pixel_weight=None, coef_num=None, coef_den=None, coef_scale=1.0):
+                 ignore_index=255, pixel_weight=None, coef_num=None, coef_den=None, coef_scale=1.0, loss_acc=None):
     n, h_lr, w_lr, ld = lr.shape
     call("b200_upsample_bwd", 
         ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
         c_int(mode), ptr(grad_in), c_int(grad_is_bf16), c_int(p_ld), ptr(labels), c_int(ignore_index),
-        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), stream())
+        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), ptr(loss_acc), stream())
 
 
 def radix_select_desc(x, rank, state, hist):
@@ -444,4 +444,9 @@ def classifier_wgrad(dout, x, dw, dbias):
 def cast_f32_bf16(x, y):
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
     call("b200_cast_f32_bf16", ptr(x), ptr(y), c_int64(x.numel()), stream())
+    return y
+
+
+def scale_f32(x, num, den, mul, y):
+    call("b200_scale_f32", ptr(x), c_int64(x.numel()), ptr(num), ptr(den), c_float(mul), ptr(y), stream())
     return y

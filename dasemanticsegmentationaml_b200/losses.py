@@ -15,6 +15,7 @@ for it.  Loss composition mirrors the reference:
 import torch
 
 from . import kernels as K
+from . import ops
 
 F32 = torch.float32
 BF16 = torch.bfloat16
@@ -34,7 +35,7 @@ class _UpsampleLogits(torch.autograd.Function):
     def backward(ctx, dout):
         (lr,) = ctx.saved_tensors
         H, W, n_classes = ctx.meta
-        d_lr = torch.zeros_like(lr)
+        d_lr = ops.zeros_f32(lr.shape, lr.device)
         dout = dout.contiguous()
         if dout.dtype not in (F32, BF16):
             dout = dout.float()
@@ -49,21 +50,27 @@ def upsample_logits(lr, H, W, n_classes=19, dtype=F32):
 
 
 class _UpsampleCE(torch.autograd.Function):
+    """Training: ONE pass computes the loss and the un-normalised gradient w.r.t. the low-resolution
+    logits (the interpolation + softmax of every pixel is needed for both); backward only scales it
+    by grad_out / #valid.  Without grad: the forward-only kernel."""
+
     @staticmethod
     def forward(ctx, lr, labels, H, W, n_classes, ignore_index):
         acc = torch.zeros(2, dtype=torch.float64, device=lr.device)
-        K.upsample_fwd(lr, H, W, n_classes, K.UP_CE, labels=labels, ignore_index=ignore_index, acc=acc)
-        ctx.save_for_backward(lr, labels, acc)
-        ctx.meta = (H, W, n_classes, ignore_index)
+        if ctx.needs_input_grad[0]:
+            d_lr = ops.zeros_f32(lr.shape, lr.device)
+            K.upsample_bwd(lr, H, W, n_classes, K.UP_CE, d_lr, labels=labels, ignore_index=ignore_index,
+                           loss_acc=acc)
+            ctx.save_for_backward(d_lr, acc)
+        else:
+            K.upsample_fwd(lr, H, W, n_classes, K.UP_CE, labels=labels, ignore_index=ignore_index, acc=acc)
         return (acc[0] / acc[1]).to(F32)
 
     @staticmethod
     def backward(ctx, g):
-        lr, labels, acc = ctx.saved_tensors
-        H, W, n_classes, ignore_index = ctx.meta
-        d_lr = torch.zeros_like(lr)
-        K.upsample_bwd(lr, H, W, n_classes, K.UP_CE, d_lr, labels=labels, ignore_index=ignore_index,
-                       coef_num=g.to(F32).contiguous(), coef_den=acc[1:])
+        d_unscaled, acc = ctx.saved_tensors
+        d_lr = torch.empty_like(d_unscaled)
+        K.scale_f32(d_unscaled, g.to(F32).contiguous(), acc[1:], 1.0, d_lr)
         return d_lr, None, None, None, None, None
 
 
@@ -99,7 +106,7 @@ class _UpsampleSoftmax(torch.autograd.Function):
         H, W, n_classes = ctx.meta
         from .model._glue import to_nhwc
         d = to_nhwc(dp)
-        d_lr = torch.zeros_like(lr)
+        d_lr = ops.zeros_f32(lr.shape, lr.device)
         K.upsample_bwd(lr, H, W, n_classes, K.UP_SOFTMAX, d_lr, grad_in=d, grad_is_bf16=1, p_ld=d.stride(2))
         return d_lr, None, None, None
 
@@ -159,7 +166,7 @@ class _UpsampleOhemCE(torch.autograd.Function):
         H, W, n_classes = ctx.meta
         weights = torch.empty_like(loss_map)
         K.ohem_weights(loss_map, sel, weights)
-        d_lr = torch.zeros_like(lr)
+        d_lr = ops.zeros_f32(lr.shape, lr.device)
         K.upsample_bwd(lr, H, W, n_classes, K.UP_CE, d_lr, labels=labels, ignore_index=-1,
                        pixel_weight=weights, coef_num=g.to(F32).contiguous())
         return d_lr, None, None, None, None, None, None

@@ -82,7 +82,11 @@ class _ModuleFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, n_inputs, *args):
         inputs = args[:n_inputs]
-        outs, saved = module._fwd_api(*inputs)
+        ops.ARENA.begin((id(module), "f"), inputs[0].device)
+        try:
+            outs, saved = module._fwd_api(*inputs)
+        finally:
+            ops.ARENA.end()
         ctx.module, ctx.saved, ctx.n_inputs, ctx.params = module, saved, n_inputs, args[n_inputs:]
         ctx.single = not isinstance(outs, tuple)
         return outs
@@ -91,7 +95,12 @@ class _ModuleFunction(torch.autograd.Function):
     def backward(ctx, *douts):
         needs_in = ctx.needs_input_grad[2:2 + ctx.n_inputs]
         needs_p = ctx.needs_input_grad[2 + ctx.n_inputs:]
-        dins, grads = ctx.module._bwd_api(ctx.saved, *douts, need_dx=any(needs_in), need_dw=any(needs_p))
+        dev = next(d.device for d in douts if d is not None)
+        ops.ARENA.begin((id(ctx.module), "b", tuple(d is not None for d in douts), any(needs_p)), dev)
+        try:
+            dins, grads = ctx.module._bwd_api(ctx.saved, *douts, need_dx=any(needs_in), need_dw=any(needs_p))
+        finally:
+            ops.ARENA.end()
         ctx.saved = None
         if not isinstance(dins, (tuple, list)):
             dins = (dins,)

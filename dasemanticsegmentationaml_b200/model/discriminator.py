@@ -49,8 +49,8 @@ class _Classifier:
         K.classifier_dgrad(dout, conv.weight.detach(), da)
         grads = {}
         if need_dw:
-            dw = torch.zeros(conv.weight.shape, dtype=F32, device=a.device)
-            db = torch.zeros((1,), dtype=F32, device=a.device)
+            dw = ops.zeros_f32(conv.weight.shape, a.device)
+            db = ops.zeros_f32((1,), a.device)
             K.classifier_wgrad(dout, a, dw, db)
             grads = {conv.weight: dw, conv.bias: db}
         return da, grads
@@ -126,7 +126,7 @@ class _DepthWiseSepBase(_DiscriminatorBase):
         if c == cpad:
             w, b = conv.weight.detach(), conv.bias.detach()
         else:
-            w = torch.zeros((cpad, 1, 4, 4), dtype=F32, device=conv.weight.device)
+            w = ops.zeros_f32((cpad, 1, 4, 4), conv.weight.device)
             w[:c].copy_(conv.weight.detach())
             b = _pad_vec(conv.bias, cpad)
         bn = None
@@ -159,7 +159,7 @@ class _DepthWiseSepBase(_DiscriminatorBase):
             if self._use_bn:
                 m = getattr(self, "bn%d_p" % i)
                 cout = conv_p.weight.shape[0]
-                stats = torch.zeros((2, cout), dtype=F32, device=x.device) if self.training else None
+                stats = ops.zeros_f32((2, cout), x.device) if self.training else None
                 z = ops.conv_raw_fwd(a, conv_p.weight, 1, 1, stats=stats, bias=conv_p.bias.detach())
                 p, cb = ops.bn_act_fwd(z, stats, bn_tuple(m, self.training), self.training, K.ACT_LEAKY, SLOPE)
                 ctxs.append((cd, ("bn", cb, a)))
@@ -182,7 +182,7 @@ class _DepthWiseSepBase(_DiscriminatorBase):
                 if need_dw:
                     grads[m.weight], grads[m.bias] = dg, db
                     grads[conv_p.weight] = ops.conv_wgrad(dz, a, conv_p.weight, 1, 1)
-                    st = torch.zeros((2, dz.shape[3]), dtype=F32, device=dz.device)
+                    st = ops.zeros_f32((2, dz.shape[3]), dz.device)
                     K.channel_stats(dz, st)
                     grads[conv_p.bias] = st[0]
                 d = ops.conv_dgrad(dz, conv_p.weight, 1, 1, a.shape[1], a.shape[2])

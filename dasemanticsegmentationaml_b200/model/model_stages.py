@@ -119,7 +119,7 @@ class BiSeNetOutput(B200Module):
 
     def _bwd_api(self, ctx, dout, need_dx=True, need_dw=True):
         n, c, h, w = dout.shape
-        d = torch.zeros((n, h, w, 32), dtype=F32, device=dout.device)
+        d = ops.zeros_f32((n, h, w, 32), dout.device)
         d[..., :c].copy_(dout.permute(0, 2, 3, 1))
         dx, g = self._bwd(ctx, d, need_dx)
         return (None if dx is None else dx.permute(0, 3, 1, 2)), g
@@ -159,8 +159,8 @@ class AttentionRefinementModule(B200Module):
         feat, att = ctx["feat"], ctx["att"]
         n, h, w, c = feat.shape
         dev = feat.device
-        d_att = torch.zeros((n, c), dtype=F32, device=dev)
-        d_vec = torch.zeros((n, c), dtype=F32, device=dev) if ctx["has_vec"] else None
+        d_att = ops.zeros_f32((n, c), dev)
+        d_vec = ops.zeros_f32((n, c), dev) if ctx["has_vec"] else None
         same = dout.shape[1] == h and dout.shape[2] == w
         dsum = dout if same else ops.empty_act(n, h, w, c, dev)
         K.upsum_dot_reduce(dout, feat, None if same else dsum, h, w, d_att, d_vec)
@@ -276,7 +276,7 @@ class FeatureFusionModule(B200Module):
     def _bwd_cat(self, ctx, dout, need_dx=True):
         feat, att = ctx["feat"], ctx["att"]
         n, h, w, c = feat.shape
-        d_att = torch.zeros((n, c), dtype=F32, device=feat.device)
+        d_att = ops.zeros_f32((n, c), feat.device)
         K.upsum_dot_reduce(dout, feat, None, h, w, d_att, None)
         d_a1, dw2, _, _ = ops.fc_bwd(ctx["fc2"], d_att)
         d_pooled, dw1, _, _ = ops.fc_bwd(ctx["fc1"], d_a1)

@@ -82,6 +82,47 @@ def clear_caches():
     pass
 
 
+class _ZeroArena(object):
+    """fp32 zero-initialised scratch carved out of ONE torch.zeros per module forward / backward
+    (instead of one memset launch per BatchNorm statistic, gradient accumulator, ...).  Every
+    begin() starts a fresh allocation, so tensors handed out earlier (e.g. parameter gradients kept
+    by autograd) are never recycled; the size needed per (module, phase) is remembered."""
+
+    def __init__(self):
+        self.hint = {}
+        self.stack = []
+
+    def begin(self, tag, device):
+        self.stack.append([tag, device, None, 0, 0])  # tag, device, chunk, offset, requested
+
+    def end(self):
+        tag, _, _, _, requested = self.stack.pop()
+        self.hint[tag] = max(self.hint.get(tag, 0), requested)
+
+    def zeros(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if not self.stack or self.stack[-1][1] != device:
+            return torch.zeros(shape, dtype=F32, device=device)
+        st = self.stack[-1]
+        size = (n + 63) // 64 * 64
+        st[4] += size
+        if st[2] is None or st[3] + size > st[2].numel():
+            st[2] = torch.zeros(max(size, self.hint.get(st[0], 0) - (st[4] - size), 1 << 16), dtype=F32, device=device)
+            st[3] = 0
+        out = st[2][st[3]:st[3] + n].view(shape)
+        st[3] += size
+        return out
+
+
+ARENA = _ZeroArena()
+
+
+def zeros_f32(shape, device):
+    return ARENA.zeros(tuple(shape) if not isinstance(shape, int) else (shape,), device)
+
+
 def empty_act(n, h, w, c, device):
     return torch.empty((n, h, w, c), dtype=BF16, device=device)
 
@@ -110,7 +151,7 @@ def bn_act_bwd(ctx, dy1, dy2=None):
     if not ctx.training:
         raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference's training path")
     c = ctx.z.shape[3]
-    red = torch.zeros((2, c), dtype=F32, device=ctx.z.device)
+    red = zeros_f32((2, c), ctx.z.device)
     K.bn_act_bwd_reduce(dy1, dy2, ctx.z, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, ctx.act, ctx.slope, red)
     dz = torch.empty(ctx.z.shape, dtype=BF16, device=ctx.z.device)
     K.bn_act_bwd_apply(dy1, dy2, ctx.z, dz, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, red, ctx.act, ctx.slope)
@@ -148,7 +189,7 @@ def conv_dgrad(dz, weight, stride, pad, hin, win):
 
 def conv_wgrad(dz, x, weight, stride, pad):
     cout, cin, r, s = weight.shape
-    dw = torch.zeros((cout, cin, r, s), dtype=F32, device=dz.device)
+    dw = zeros_f32((cout, cin, r, s), dz.device)
     K.conv_wgrad(dz, x, dw, r, s, stride, pad)
     return dw
 
@@ -157,7 +198,7 @@ def conv_bn_act_fwd(x, weight, bn, stride, pad, training, act=K.ACT_RELU, slope=
     """ConvX / ConvBNReLU: bias-free conv -> BatchNorm2d -> activation (stdcnet.py:6-15,
     model_stages.py:11-29).  `x` is an NHWC bf16 view, or the fp32 NCHW image for the 3-channel stem."""
     cout = weight.shape[0]
-    stats = torch.zeros((2, cout), dtype=F32, device=weight.device) if training else None
+    stats = zeros_f32((2, cout), weight.device) if training else None
     ctx = ConvCtx()
     ctx.stem_img = None
     if x.dim() == 4 and x.dtype == F32 and x.shape[1] == 3 and weight.shape[1] == 3:
@@ -180,7 +221,7 @@ def conv_bn_act_bwd(ctx, dy1, dy2=None, need_dx=True):
     """-> (dx or None, dW, dgamma, dbeta)"""
     dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy1, dy2)
     if ctx.stem_img is not None:
-        dw = torch.zeros(ctx.weight.shape, dtype=F32, device=dz.device)
+        dw = zeros_f32(ctx.weight.shape, dz.device)
         K.stem_wgrad(ctx.stem_img, dz, dw)
         return None, dw, dgamma, dbeta
     dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad)
@@ -207,7 +248,7 @@ def conv_bias_act_bwd(ctx, dy1, dy2=None, need_dx=True, need_dw=True):
     """-> (dx, dW, dbias)"""
     c = ctx.a.shape[3]
     dz = torch.empty(ctx.a.shape, dtype=BF16, device=ctx.a.device)
-    dbias = torch.zeros((c,), dtype=F32, device=ctx.a.device) if need_dw else None
+    dbias = zeros_f32((c,), ctx.a.device) if need_dw else None
     K.act_bwd_bias(dy1, dy2, ctx.a, dz, ctx.act, ctx.slope, dbias)
     dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad) if need_dw else None
     dx = None
@@ -245,9 +286,9 @@ def fc_bwd(ctx, dout, need_din=True):
     co = ctx.W.shape[0]
     dev = dout.device
     scratch = torch.empty((n, co), dtype=F32, device=dev)
-    dW = torch.zeros((co, cin), dtype=F32, device=dev)
+    dW = zeros_f32((co, cin), dev)
     has_bn = ctx.bn is not None
-    dgb = torch.zeros((2, co), dtype=F32, device=dev) if has_bn else None
+    dgb = zeros_f32((2, co), dev) if has_bn else None
     din = torch.empty((n, cin), dtype=F32, device=dev) if need_din else None
     K.fc_small_bwd(dout, ctx.out, ctx.pre, ctx.inp, ctx.in_scale, ctx.W, has_bn, ctx.training,
                    ctx.bn[0] if has_bn else None, ctx.mean, ctx.rstd, ctx.act, scratch, dW,
@@ -256,7 +297,7 @@ def fc_bwd(ctx, dout, need_din=True):
 
 
 def pool_sum(x):
-    out = torch.zeros((x.shape[0], x.shape[3]), dtype=F32, device=x.device)
+    out = zeros_f32((x.shape[0], x.shape[3]), x.device)
     K.pool_sum(x, out)
     return out
 
@@ -277,7 +318,7 @@ def dw_bn_fwd(x, weight, bn, training, pool_out=None, act=K.ACT_NONE, slope=0.0,
     ctx.x, ctx.weight, ctx.k, ctx.act, ctx.slope, ctx.has_pool, ctx.bias = x, weight, k, act, slope, pool_out is not None, bias
     if bn is not None:
         z = empty_act(n, ho, wo, c, x.device)
-        stats = torch.zeros((2, c), dtype=F32, device=x.device) if training else None
+        stats = zeros_f32((2, c), x.device) if training else None
         K.dwconv_s2_fwd(x, k, wflat, bias, z, pool_out, K.ACT_NONE, 0.0, stats)
         a, ctx.bn = bn_act_fwd(z, stats, bn, training, act, slope)
         ctx.z, ctx.a = z, a
@@ -296,12 +337,12 @@ def dw_bn_bwd(ctx, dy, dpool=None, need_dx=True):
     if ctx.bn is not None:
         dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy)
         if ctx.bias is not None:
-            dbias = torch.zeros((c,), dtype=F32, device=dev)
+            dbias = zeros_f32((c,), dev)
     else:
         dz = torch.empty(ctx.a.shape, dtype=BF16, device=dev)
-        dbias = torch.zeros((c,), dtype=F32, device=dev) if ctx.bias is not None else None
+        dbias = zeros_f32((c,), dev) if ctx.bias is not None else None
         K.act_bwd_bias(dy, None, ctx.a, dz, ctx.act, ctx.slope, None)
-    dw = torch.zeros((c * ctx.k * ctx.k,), dtype=F32, device=dev)
+    dw = zeros_f32((c * ctx.k * ctx.k,), dev)
     K.dwconv_s2_wgrad(dz, ctx.x, ctx.k, dw, dbias)
     dx = None
     if need_dx:

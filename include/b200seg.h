@@ -178,7 +178,11 @@ int b200_upsample_bwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
                       int n_classes, int mode, const void* grad_in, int grad_is_bf16, int p_ld,
                       const int64_t* labels, int ignore_index, const float* pixel_weight,
                       const float* coef_num, const double* coef_den, float coef_scale, float* d_lr,
-                      cudaStream_t stream);
+                      double* loss_acc, cudaStream_t stream);
+/* loss_acc != NULL (mode 1): the same pass also accumulates the forward loss sum / valid count, so a
+ * training step needs no separate forward kernel; b200_scale_f32 then applies grad_out / #valid. */
+int b200_scale_f32(const float* x, int64_t count, const float* num, const double* den, float mul,
+                   float* y, cudaStream_t stream);
 /* OHEM_CrossEntroy_Loss (utils.py:263-271) without torch.sort: k-th largest by radix select over the
  * fp32 bit patterns, then the thresholded / top-k mean and the per-pixel gradient weights. */
 int b200_radix_select_desc(const float* x, int64_t count, int64_t rank, uint32_t* state,

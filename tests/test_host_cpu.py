@@ -105,3 +105,24 @@ def test_poly_lr_and_per_class_iu_host_side():
     assert opt.param_groups[0]["lr"] == O.poly_lr(0.01, 3, 50)
     h = np.arange(361).reshape(19, 19)
     assert np.array_equal(U.per_class_iu(h), O.per_class_iu(h))
+
+
+def test_ctypes_wrappers_match_header_arity():
+    """ctypes sees no prototypes: every `call("b200_*", ...)` site must pass exactly as many positional
+    arguments as include/b200seg.h declares (a drift is a corrupted call frame on the GPU box)."""
+    import ast
+    from dasemanticsegmentationaml_b200 import _lib
+    _lib._load_arity()
+    assert len(_lib._arity) >= 35
+    pkg = os.path.join(ROOT, "dasemanticsegmentationaml_b200")
+    seen = set()
+    for fname in ("kernels.py", "ops.py"):
+        tree = ast.parse(open(os.path.join(pkg, fname)).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and getattr(node.func, "id", getattr(node.func, "attr", None)) == "call" \
+                    and node.args and isinstance(node.args[0], ast.Constant) and str(node.args[0].value).startswith("b200_"):
+                name = node.args[0].value
+                assert name in _lib._arity, name
+                assert len(node.args) - 1 == _lib._arity[name], (fname, name, len(node.args) - 1, _lib._arity[name])
+                seen.add(name)
+    assert len(seen) >= 30
