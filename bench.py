@@ -25,9 +25,12 @@ WORKLOADS = {
     "da_dwsep": "config[3]: DA train step, DepthWiseSepFCDiscriminator, 512x1024, batch 8/GPU",
     "da_dwsep_bn": "config[3]: DA train step, DepthWiseSepBNFCDiscriminator, 512x1024, batch 8/GPU",
     "supervised": "config[1]: supervised train step (3x CE), 720x1280, batch 8",
+    "supervised_ohem": "config[1]: supervised train step (3x OHEM CE, radix select), 720x1280, batch 8",
+    "eval": "config[4]: full-resolution eval (forward + fused argmax + 19x19 confusion matrix), 1024x2048",
 }
 # algorithmic dense-conv FLOPs per (source, target) pair / image
-GFLOP_PER_UNIT = {"da_dense": 444.87, "da_dwsep": 226.0, "da_dwsep_bn": 226.0, "supervised": 186.14}
+GFLOP_PER_UNIT = {"da_dense": 444.87, "da_dwsep": 226.0, "da_dwsep_bn": 226.0, "supervised": 186.14,
+                  "supervised_ohem": 186.14, "eval": 141.04}
 
 
 def parse():
@@ -191,13 +194,13 @@ def run_b200(args):
     steps = args.steps or 20
     warmup = max(3, args.warmup if args.warmup is not None else 5)
     nb = args.batch
-    h, w = (720, 1280) if args.workload == "supervised" else (H, W)
+    h, w = {"supervised": (720, 1280), "supervised_ohem": (720, 1280), "eval": (1024, 2048)}.get(args.workload, (H, W))
 
     torch.manual_seed(0)  # identical initial weights on every rank
     model = BiSeNet("STDCNet813", NCLS).to(dev)
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
     model_d = opt_d = None
-    if args.workload != "supervised":
+    if args.workload.startswith("da_"):
         cls = {"da_dense": FCDiscriminator, "da_dwsep": DepthWiseSepFCDiscriminator,
                "da_dwsep_bn": DepthWiseSepBNFCDiscriminator}[args.workload]
         model_d = cls(NCLS).to(dev)
@@ -209,10 +212,19 @@ def run_b200(args):
         "labels": torch.randint(0, NCLS + 1, (nb, h, w), generator=g).pin_memory(),
         "images_t": torch.randn(nb, 3, h, w, generator=g).pin_memory(),
     }
-    host["labels"][host["labels"] == NCLS] = 255
+    if args.workload == "supervised_ohem":
+        host["labels"].clamp_(max=NCLS - 1)  # the reference's OHEM has no ignore_index
+    else:
+        host["labels"][host["labels"] == NCLS] = 255
     devbuf = {k: v.to(dev) for k, v in host.items()}
+    eval_hist = [None]
 
     def step(buf):
+        if args.workload == "eval":
+            eval_hist[0], _ = T.eval_batch(model, buf["images"], buf["labels"], NCLS, eval_hist[0])
+            return (eval_hist[0].sum().float(),)
+        if args.workload == "supervised_ohem":
+            return (T.train_step(model, opt, buf["images"], buf["labels"], loss="ohem"),)
         if model_d is None:
             return (T.train_step(model, opt, buf["images"], buf["labels"]),)
         return T.train_da_step(model, model_d, opt, opt_d, buf["images"], buf["labels"], buf["images_t"])
@@ -282,7 +294,7 @@ def run_b200(args):
     unit_per_step = nb * world
     value = unit_per_step * steps / (ms_total / 1e3)
     line = {
-        "metric": "da_train_step_img_per_s" if model_d is not None else "train_step_img_per_s",
+        "metric": "da_train_step_img_per_s" if model_d is not None else ("eval_img_per_s" if args.workload == "eval" else "train_step_img_per_s"),
         "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
@@ -318,7 +330,7 @@ def run_b200(args):
         if args.profile_json:
             with open(args.profile_json, "w") as f:
                 json.dump({"by_kernel": prof, "by_shape": _lib.last_profile_detail}, f, indent=1)
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and (args.workload.startswith("da_") or args.workload == "supervised"):
         try:
             rate, cms, threads = cpu_da_step_rate(args.workload, 2, 1, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
