@@ -405,17 +405,16 @@ __global__ void pack_filters_batched_kernel(const long long* __restrict__ table)
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t[1]);
   const int Cout = (int)t[2], Cin = (int)t[3], RS = (int)t[4], rows_pad = (int)t[5], inner_pad = (int)t[6];
   const int transpose = (int)t[7];
-  const size_t total = (size_t)rows_pad * RS * inner_pad;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int inner = i % inner_pad;
-    const int tt = (i / inner_pad) % RS;
-    const int row = i / ((size_t)inner_pad * RS);
+  // one thread = one (row, inner) pair: RS consecutive source floats, RS coalesced stores
+  const int pairs = rows_pad * inner_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += gridDim.x * blockDim.x) {
+    const int row = i / inner_pad, inner = i - row * inner_pad;
     const int co = transpose ? inner : row;
     const int ci = transpose ? row : inner;
-    float v = 0.f;
-    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * RS + tt];
-    out[i] = __float2bfloat16(v);
+    const bool ok = co < Cout && ci < Cin;
+    const float* src = w + ((size_t)co * Cin + ci) * RS;
+    __nv_bfloat16* dst = out + (size_t)row * RS * inner_pad + inner;
+    for (int tt = 0; tt < RS; ++tt) dst[(size_t)tt * inner_pad] = __float2bfloat16(ok ? __ldg(src + tt) : 0.f);
   }
 }
 

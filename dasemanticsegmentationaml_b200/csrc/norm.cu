@@ -5,6 +5,7 @@
 //
 // A "view" is (base pointer, pixel stride ld in elements): channels [0, C) of each of `npix`
 // pixels.  All C are multiples of 8.
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #include "ptx.cuh"
@@ -314,6 +315,102 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
   }
 }
 
+// Both backward passes in ONE cooperative launch: reductions, grid-wide barrier, then dz.  The
+// second pass walks the pixels in reverse so that it starts on the lines the first pass touched
+// last (for all but the largest layers dy and z are still L2-resident: no second HBM read).
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
+                        const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
+                        const __nv_bfloat16* __restrict__ z, int z_ld,
+                        __nv_bfloat16* __restrict__ dz, int dz_ld, int C, int64_t npix,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        float* red, float inv_count, int act, float slope) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const Slot t = slot_of(C);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float sc[8], sh[8], a1[8] = {0}, a2[8] = {0};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[t.g * 8 + j];
+    sh[j] = shift[t.g * 8 + j];
+  }
+  const int64_t step = (int64_t)gridDim.x * t.py * UNR3;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  int64_t last_base = -1;
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR3; base < npix; base += step) {
+    last_base = base;
+    uint4 rd[UNR3], rz[UNR3], re[UNR3];
+#pragma unroll
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      const bool ok = p < npix;
+      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
+      rz[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
+      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR3; ++u) {
+      float d[8], zz[8], e[8];
+      unpack8(rd[u], d);
+      unpack8(rz[u], zz);
+      unpack8(re[u], e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+        a1[j] += gg;
+        a2[j] += gg * zz[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a2[j] = (a2[j] - mean[t.g * 8 + j] * a1[j]) * rstd[t.g * 8 + j];
+    atomicAdd(&s_acc[t.g * 8 + j], a1[j]);
+    atomicAdd(&s_acc[C + t.g * 8 + j], a2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[i], s_acc[i]);
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  float k0[8], k1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = t.g * 8 + j;
+    const float r0 = __ldcg(red + c) * inv_count, r1 = __ldcg(red + C + c) * inv_count;
+    k1[j] = -sc[j] * r1 * rstd[c];
+    k0[j] = -sc[j] * r0 - k1[j] * mean[c];
+  }
+  for (int64_t base = last_base; base >= 0; base -= step) {
+    uint4 rd[UNR3], rz[UNR3], re[UNR3];
+#pragma unroll
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      const bool ok = p < npix;
+      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
+      rz[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
+      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
+    }
+#pragma unroll
+    for (int u = 0; u < UNR3; ++u) {
+      const int64_t p = base + u * t.py + t.ty;
+      if (p < npix) {
+        float d[8], zz[8], e[8], o[8];
+        unpack8(rd[u], d);
+        unpack8(rz[u], zz);
+        unpack8(re[u], e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+          o[j] = sc[j] * gg + k1[j] * zz[j] + k0[j];
+        }
+        store8(dz + p * dz_ld + t.g * 8, o);
+      }
+    }
+  }
+}
+
 // Biased conv + LeakyReLU layers (no BatchNorm): dz = (dy1+dy2) * leaky'(a) with a the stored
 // activation (sign(a) == sign(pre-activation)); dbias[c] += sum dz.
 __global__ void __launch_bounds__(256, 2)
@@ -481,6 +578,41 @@ int b200_bn_act_bwd_apply(const void* dy1, int dy1_ld, const void* dy2, int dy2_
       static_cast<const __nv_bfloat16*>(z), z_ld, static_cast<__nv_bfloat16*>(dz), dz_ld, C, npix,
       scale, shift, mean, rstd, red, inv_count, act, slope);
   return check_launch("bn_act_bwd_apply");
+}
+
+// b200_bn_act_bwd_reduce + b200_bn_act_bwd_apply in one cooperative launch; red must be zeroed.
+int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
+                          int z_ld, void* dz, int dz_ld, int C, int64_t npix, const float* scale,
+                          const float* shift, const float* mean, const float* rstd, float* red,
+                          float inv_count, int act, float slope, cudaStream_t stream) {
+  int rc = check_c(C, "bn_act_bwd_fused");
+  if (rc) return rc;
+  const int threads = block_for(C);
+  const size_t smem = 2 * C * sizeof(float);
+  static int max_blocks_per_sm[2049] = {0};  // indexed by C (block shape and smem depend on C only)
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (max_blocks_per_sm[C] == 0) {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bn_act_bwd_fused_kernel, threads, smem);
+    if (nb < 1) return set_error(B200_ECUDA, "bn_act_bwd_fused: kernel does not fit an SM");
+    max_blocks_per_sm[C] = nb;
+  }
+  int grid = reduce_grid(npix, threads / (C / 8), n_sm * max_blocks_per_sm[C]);
+  const __nv_bfloat16* a0 = static_cast<const __nv_bfloat16*>(dy1);
+  const __nv_bfloat16* a1 = static_cast<const __nv_bfloat16*>(dy2);
+  const __nv_bfloat16* a2 = static_cast<const __nv_bfloat16*>(z);
+  __nv_bfloat16* a3 = static_cast<__nv_bfloat16*>(dz);
+  void* args[] = {&a0, &dy1_ld, &a1, &dy2_ld, &a2, &z_ld, &a3, &dz_ld, &C, &npix, &scale, &shift,
+                  &mean, &rstd, &red, &inv_count, &act, &slope};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_act_bwd_fused_kernel, dim3(grid), dim3(threads),
+                                              args, smem, stream);
+  if (e != cudaSuccess) return set_error(B200_ECUDA, "bn_act_bwd_fused: %s", cudaGetErrorString(e));
+  return check_launch("bn_act_bwd_fused");
 }
 
 int b200_cast_f32_bf16(const float* x, void* y, int64_t count, cudaStream_t stream) {

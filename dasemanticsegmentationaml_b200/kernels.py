@@ -286,6 +286,15 @@ def bn_act_bwd_apply(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope)
         stream(), nbytes=(6.0 if dy2 is None else 8.0) * npix * c, tag="px%d C%d%s" % (npix, c, "" if dy2 is None else " +dy2"))
 
 
+def bn_act_bwd_fused(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope):
+    npix, c, z_ld = _pix(z)
+    call("b200_bn_act_bwd_fused",
+         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
+         ptr(z), c_int(z_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), ptr(scale),
+         ptr(shift), ptr(mean), ptr(rstd), ptr(red), c_float(1.0 / npix), c_int(act), c_float(slope),
+         stream(), nbytes=(6.0 if dy2 is None else 8.0) * npix * c, tag="px%d C%d%s" % (npix, c, "" if dy2 is None else " +dy2"))
+
+
 def act_bwd_bias(dy1, dy2, a, dz, act, slope, dbias):
     npix, c, a_ld = _pix(a)
     call("b200_act_bwd_bias", 

@@ -152,9 +152,8 @@ def bn_act_bwd(ctx, dy1, dy2=None):
         raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference's training path")
     c = ctx.z.shape[3]
     red = zeros_f32((2, c), ctx.z.device)
-    K.bn_act_bwd_reduce(dy1, dy2, ctx.z, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, ctx.act, ctx.slope, red)
     dz = torch.empty(ctx.z.shape, dtype=BF16, device=ctx.z.device)
-    K.bn_act_bwd_apply(dy1, dy2, ctx.z, dz, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, red, ctx.act, ctx.slope)
+    K.bn_act_bwd_fused(dy1, dy2, ctx.z, dz, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, red, ctx.act, ctx.slope)
     return dz, red[1], red[0]
 
 

@@ -119,6 +119,11 @@ int b200_bn_act_bwd_apply(const void* dy1, int dy1_ld, const void* dy2, int dy2_
                           const float* shift, const float* mean, const float* rstd,
                           const float* red, float inv_count, int act, float slope,
                           cudaStream_t stream);
+/* reduce + apply in one cooperative launch (grid-wide barrier in between; `red` zeroed by the caller). */
+int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
+                          int z_ld, void* dz, int dz_ld, int C, int64_t npix, const float* scale,
+                          const float* shift, const float* mean, const float* rstd, float* red,
+                          float inv_count, int act, float slope, cudaStream_t stream);
 /* LeakyReLU backward + bias gradient of the biased discriminator convs (discriminator.py:18-25). */
 int b200_act_bwd_bias(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* a,
                       int a_ld, void* dz, int dz_ld, int C, int64_t npix, int act, float slope,
