@@ -198,13 +198,15 @@ def run_b200(args):
 
     torch.manual_seed(0)  # identical initial weights on every rank
     model = BiSeNet("STDCNet813", NCLS).to(dev)
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    # same optimizers and hyper-parameters as train.py:170-172; fused=True only changes how torch
+    # launches the update (one multi-tensor kernel per step)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
     model_d = opt_d = None
     if args.workload.startswith("da_"):
         cls = {"da_dense": FCDiscriminator, "da_dwsep": DepthWiseSepFCDiscriminator,
                "da_dwsep_bn": DepthWiseSepBNFCDiscriminator}[args.workload]
         model_d = cls(NCLS).to(dev)
-        opt_d = torch.optim.Adam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99))
+        opt_d = torch.optim.Adam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True)
 
     g = torch.Generator().manual_seed(100 + rank)  # rank-dependent data
     host = {

@@ -198,7 +198,6 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
   __shared__ float s_loss[2][TH];
   __shared__ float s_a[TH][MAXJ][NC + 1];
   __shared__ Interp s_iw[TW], s_ih[TH];
-  __shared__ int s_xlo[MAXJ], s_xhi[MAXJ];
   const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
   const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
@@ -285,54 +284,55 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
       atomicAdd(&loss_acc[1], b);
     }
   }
+  // Separable transposed interpolation.  Source indices are non-decreasing along a row / column,
+  // so each (row, class) thread streams over the 32 columns keeping two running sums (for the
+  // current low-resolution column and the next one) and flushes when the source index advances.
   const int j_min = s_iw[0].i0;
-  const int i_min = s_ih[0].i0;
-  if (threadIdx.x < MAXJ) {  // columns of the tile that touch low-resolution column j (a contiguous range)
-    const int j = j_min + threadIdx.x;
-    int lo = TW, hi = 0;
-    for (int x = 0; x < TW; ++x)
-      if (s_iw[x].i0 == j || s_iw[x].i1 == j) {
-        lo = min(lo, x);
-        hi = x + 1;
-      }
-    s_xlo[threadIdx.x] = lo;
-    s_xhi[threadIdx.x] = hi;
-  }
-  __syncthreads();
-  // pass A: reduce along w   -> s_a[row][j - j_min][c]
-  for (int item = threadIdx.x; item < TH * MAXJ * NC; item += TH * TW) {
-    const int c = item % NC;
-    const int jj = (item / NC) % MAXJ;
-    const int r = item / (NC * MAXJ);
-    const int j = j_min + jj;
-    float acc = 0.f;
-    for (int x = s_xlo[jj]; x < s_xhi[jj]; ++x) {
+  for (int t = threadIdx.x; t < TH * NC; t += TH * TW) {
+    const int r = t / NC, c = t - r * NC;
+    float acc0 = 0.f, acc1 = 0.f;
+    int j_cur = j_min;
+    for (int x = 0; x < TW; ++x) {
       const Interp iw = s_iw[x];
-      float wgt = 0.f;
-      if (iw.i0 == j) wgt += iw.l0;
-      if (iw.i1 == j) wgt += iw.l1;
-      acc += wgt * s_g[r][x][c];
+      while (iw.i0 != j_cur) {
+        s_a[r][j_cur - j_min][c] = acc0;
+        acc0 = acc1;
+        acc1 = 0.f;
+        ++j_cur;
+      }
+      const float gv = s_g[r][x][c];
+      acc0 += iw.l0 * gv;
+      if (iw.i1 != iw.i0) acc1 += iw.l1 * gv;
+      else acc0 += iw.l1 * gv;
     }
-    s_a[r][jj][c] = acc;
+    s_a[r][j_cur - j_min][c] = acc0;
+    if (j_cur + 1 - j_min < MAXJ) s_a[r][j_cur + 1 - j_min][c] = acc1;
+    for (int jj = j_cur + 2 - j_min; jj < MAXJ; ++jj) s_a[r][jj][c] = 0.f;
   }
   __syncthreads();
-  // pass B: reduce along h and add to the global low-resolution gradient
-  for (int item = threadIdx.x; item < MAXI * MAXJ * NC; item += TH * TW) {
-    const int c = item % NC;
-    const int jj = (item / NC) % MAXJ;
-    const int ii = item / (NC * MAXJ);
-    const int i = i_min + ii, j = j_min + jj;
-    if (i >= h_lr || j >= w_lr) continue;
-    float acc = 0.f;
-#pragma unroll
+  const int i_min = s_ih[0].i0;
+  for (int t = threadIdx.x; t < MAXJ * NC; t += TH * TW) {
+    const int jj = t / NC, c = t - jj * NC;
+    const int j = j_min + jj;
+    if (j >= w_lr) continue;
+    float acc0 = 0.f, acc1 = 0.f;
+    int i_cur = i_min;
+    float* dst = d_lr + ((int64_t)n * h_lr * w_lr + j) * lr_ld + c;
     for (int y = 0; y < TH; ++y) {
       const Interp ih = s_ih[y];
-      float wgt = 0.f;
-      if (ih.i0 == i) wgt += ih.l0;
-      if (ih.i1 == i) wgt += ih.l1;
-      acc += wgt * s_a[y][jj][c];
+      while (ih.i0 != i_cur) {
+        if (acc0 != 0.f) atomicAdd(dst + (int64_t)i_cur * w_lr * lr_ld, acc0);
+        acc0 = acc1;
+        acc1 = 0.f;
+        ++i_cur;
+      }
+      const float av = s_a[y][jj][c];
+      acc0 += ih.l0 * av;
+      if (ih.i1 != ih.i0) acc1 += ih.l1 * av;
+      else acc0 += ih.l1 * av;
     }
-    if (acc != 0.f) atomicAdd(&d_lr[(((int64_t)n * h_lr + i) * w_lr + j) * lr_ld + c], acc);
+    if (acc0 != 0.f) atomicAdd(dst + (int64_t)i_cur * w_lr * lr_ld, acc0);
+    if (acc1 != 0.f && i_cur + 1 < h_lr) atomicAdd(dst + (int64_t)(i_cur + 1) * w_lr * lr_ld, acc1);
   }
 }
 

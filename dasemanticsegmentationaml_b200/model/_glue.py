@@ -95,6 +95,7 @@ class _ModuleFunction(torch.autograd.Function):
     def backward(ctx, *douts):
         needs_in = ctx.needs_input_grad[2:2 + ctx.n_inputs]
         needs_p = ctx.needs_input_grad[2 + ctx.n_inputs:]
+        object.__setattr__(ctx.module, "_b200_dirty", True)  # an optimizer step is about to follow
         dev = next(d.device for d in douts if d is not None)
         ops.ARENA.begin((id(ctx.module), "b", tuple(d is not None for d in douts), any(needs_p)), dev)
         try:
@@ -115,7 +116,8 @@ def run_module(module, *inputs):
         raise _lib.B200Error("%s only runs on a B200 (got a %s tensor); there is no CPU fallback"
                              % (type(module).__name__, dev.type))
     _lib.ensure_device(dev.index or 0)
-    ops.refresh_packs(module)
+    ops.refresh_packs(module, force=module.training or getattr(module, "_b200_dirty", False))
+    object.__setattr__(module, "_b200_dirty", False)
     out = _ModuleFunction.apply(module, len(inputs), *inputs, *module_params(module))
     flush_nbt()
     return out

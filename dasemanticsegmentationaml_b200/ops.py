@@ -44,9 +44,15 @@ def packed_filter(weight, transpose):
     return buf
 
 
-def refresh_packs(module):
+def refresh_packs(module, force=False):
     """Re-pack, in ONE launch, every cached filter packing of `module` whose fp32 master changed
-    (called at the top of a forward; after an optimizer step that is all of them)."""
+    (called at the top of a forward; after an optimizer step that is all of them).
+
+    Staleness cannot rely on tensor version counters alone: torch's fused optimizers update
+    parameters without bumping them.  So `force` is set by the caller whenever the weights may have
+    been stepped since the last packing: always in training mode, and after any backward pass
+    through the module (see _glue.run_module).  Out-of-band edits through ``.data`` need
+    ``invalidate_packs(module)``."""
     weights = getattr(module, "_b200_conv_weights", None)
     if weights is None:
         weights = [p for p in module.parameters() if p.dim() == 4]
@@ -58,7 +64,7 @@ def refresh_packs(module):
             continue
         ver, ptr_now = w._version, w.data_ptr()
         for tr, (v, pw, buf) in cache.items():
-            if v != ver or pw != ptr_now or FORCE_REPACK:
+            if v != ver or pw != ptr_now or FORCE_REPACK or force:
                 stale.append((w, tr, buf))
     if not stale:
         return 0
@@ -76,6 +82,11 @@ def refresh_packs(module):
     for w, tr, buf in stale:
         w._b200_pack[tr] = (w._version, w.data_ptr(), buf)
     return len(stale)
+
+
+def invalidate_packs(module):
+    """Force the next forward of `module` to re-pack every filter (after editing weights in place)."""
+    object.__setattr__(module, "_b200_dirty", True)
 
 
 def clear_caches():

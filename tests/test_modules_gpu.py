@@ -270,3 +270,24 @@ def test_da_step_matches_oracle_losses(cuda_lib, kind):
     assert abs(got[0] - want[0]) / want[0] < 3e-2
     for a, b in zip(got[1:], want[1:]):
         assert abs(a - b) < 0.1 * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_weight_updates_reach_the_packed_filters(cuda_lib, fused):
+    """torch's fused optimizers do not bump tensor version counters; the bf16 filter packings must
+    still follow the fp32 masters (train -> train and train -> eval)."""
+    from dasemanticsegmentationaml_b200.model import ConvX
+    torch.manual_seed(0)
+    m = ConvX(64, 64, 3, 1).to(DEV).train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5, fused=fused)
+    x = torch.randn(2, 64, 16, 16, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    for _ in range(2):
+        opt.zero_grad()
+        m(x).float().square().mean().backward()
+        opt.step()
+    m.eval()
+    with torch.no_grad():
+        y = m(x)
+        ref = F.relu(F.batch_norm(F.conv2d(x.float(), bf16_round(m.conv.weight), None, 1, 1), m.bn.running_mean,
+                                  m.bn.running_var, m.bn.weight, m.bn.bias, False, 0.1, 1e-5))
+    assert rel_l2(y, ref) < 1e-2
