@@ -259,16 +259,38 @@ def run_b200(args):
     loss_vals = [float(v) for v in losses]
 
     # ---- timed region 2: end to end from pinned host buffers -------------------------------------
-    stage = {k: torch.empty_like(v) for k, v in devbuf.items()}
-    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if model_d is not None or k != "images_t")
+    # Every step copies ITS inputs host->device (pinned memory, a dedicated copy stream, double
+    # buffered so that the copy of step i+1 overlaps the compute of step i) and reads the step's
+    # losses back to the host (one D2H + sync per step, as train.py's .item() calls do).
+    names = [k for k in devbuf if not (model_d is None and k == "images_t")]
+    stage = [{k: torch.empty_like(devbuf[k]) for k in names} for _ in range(2)]
+    for sbuf in stage:
+        if "images_t" not in sbuf:
+            sbuf["images_t"] = devbuf["images_t"]
+    h2d = sum(host[k].numel() * host[k].element_size() for k in names)
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])      # the step that last used this slot is done
+            for k in names:
+                stage[slot][k].copy_(host[k], non_blocking=True)
+            ready[slot].record(copy_stream)
+
     sync_all()
+    for ev in consumed:
+        ev.record()
     e0.record()
-    for _ in range(steps):
-        for k in stage:
-            if model_d is None and k == "images_t":
-                continue
-            stage[k].copy_(host[k], non_blocking=True)
-        out = step(stage)
+    issue_copy(0)
+    for i in range(steps):
+        slot = i & 1
+        if i + 1 < steps:
+            issue_copy(slot ^ 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        out = step(stage[slot])
+        consumed[slot].record()
         host_losses = torch.stack([o.float() for o in out]).cpu()  # D2H read of the step's result
     e1.record()
     sync_all()

@@ -132,3 +132,26 @@ def test_conv_wgrad(cuda_lib, case):
     torch.cuda.synchronize()
     err = rel_l2(dw, wf.grad)
     assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("case", [(2, 19, 64, 128, 256, 4, 2, 1), (2, 32, 64, 96, 160, 3, 2, 1), (1, 32, 32, 128, 192, 3, 1, 1),
+                                  (2, 19, 160, 64, 160, 4, 2, 1)])
+def test_conv_wgrad_thin_input_all_taps(cuda_lib, case):
+    """Cin <= 32 with many pixels takes the all-taps-resident kernel; the input is a 19/32-channel
+    view of a 32-channel buffer as produced by upsample_softmax."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = case
+    x, wgt = make_case(*case)
+    buf = torch.zeros(n, h, w, 32, device="cuda", dtype=torch.bfloat16)
+    buf[..., :cin] = x
+    wf = wgt.clone().requires_grad_(True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wf, stride=stride, padding=pad)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dz = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+    y.backward(dz.float())
+    dz_nhwc = dz.permute(0, 2, 3, 1).contiguous()
+    dw = torch.zeros_like(wgt)
+    K.conv_wgrad(dz_nhwc, buf[..., :cin], dw, r, r, stride, pad)
+    torch.cuda.synchronize()
+    err = rel_l2(dw, wf.grad)
+    assert err < 1e-3, err
