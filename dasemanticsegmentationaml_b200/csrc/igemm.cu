@@ -250,6 +250,245 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------- persistent forward / dgrad
+// Same math as conv_igemm_kernel, but a CTA is resident and walks tiles  t = blockIdx.x, +gridDim.x, ...
+// (tile index = n_tile * M_total + m_tile, so a CTA mostly stays on one filter tile).  The TMA and
+// MMA pipelines run across tile boundaries and TMEM holds TWO accumulator buffers: while the
+// epilogue warps drain buffer b (bias / activation / BN statistics / stores) the MMA warp is
+// already filling buffer b^1 with the next tile -- prologue, TMEM allocation and barrier set-up are
+// paid once per SM instead of once per 128 pixels.
+struct PersistBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+
+struct TileCoord {
+  int z, n_img, h0, w0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int m_total) {
+  TileCoord t;
+  const int n_tile = tile / m_total;
+  int rem = tile - n_tile * m_total;
+  t.n0 = n_tile * p.BN;
+  t.z = 0;
+#pragma unroll
+  for (int z = 0; z < kMaxClasses - 1; ++z) {
+    const int cnt = p.tiles_h[t.z] * p.tiles_w[t.z] * p.n_img;
+    if (rem >= cnt && p.n_taps[t.z + 1] > 0) {
+      rem -= cnt;
+      ++t.z;
+    }
+  }
+  const int per_img = p.tiles_h[t.z] * p.tiles_w[t.z];
+  t.n_img = rem / per_img;
+  const int t_in = rem - t.n_img * per_img;
+  t.h0 = (t_in / p.tiles_w[t.z]) * p.th * p.mt;
+  t.w0 = (t_in % p.tiles_w[t.z]) * p.tw;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const __grid_constant__ ConvParams p, int m_total, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PersistBarriers bars;
+  __shared__ float s_stats[2][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_sub = 128u * p.KC * 2u;
+  const uint32_t a_bytes = a_sub * p.mt;
+  const uint32_t b_bytes = (uint32_t)p.BN * p.KC * 2u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int cin_blocks = p.cin_pad / p.KC;
+  const uint32_t acc_cols = (uint32_t)(p.mt * p.BN);          // one accumulator buffer
+  const uint32_t want = 2u * acc_cols;
+  const uint32_t tmem_cols = want <= 32 ? 32u : (want <= 64 ? 64u : (want <= 128 ? 128u : (want <= 256 ? 256u : 512u)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), 1);
+      mbar_init(smem_u32(&bars.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars.tfull[b]), 1);
+      mbar_init(smem_u32(&bars.tempty[b]), 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars.tmem_base), tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, m_total);
+        for (int t = 0; t < p.n_taps[tc.z]; ++t) {
+          const int hh = tc.h0 * p.in_stride + p.tap_dh[tc.z][t];
+          const int ww = tc.w0 * p.in_stride + p.tap_dw[tc.z][t];
+          const int kb = p.tap_k[tc.z][t] * p.cin_pad;
+          for (int cb = 0; cb < cin_blocks; ++cb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
+            const uint32_t full = smem_u32(&bars.full[s]);
+            mbar_expect_tx(full, stage_bytes);
+            const uint32_t sa = smem_base + s * stage_bytes;
+            tma_load_4d(sa, &tmA, full, cb * p.KC, ww, hh, tc.n_img);
+            tma_load_2d(sa + a_bytes, &tmB, full, kb + cb * p.KC, tc.n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t layout = (p.KC == 64) ? 2u : 4u;
+      const uint32_t sbo = 8u * p.KC * 2u;
+      const int ksteps = p.KC / 16;
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const TileCoord tc = decode_tile(p, tile, m_total);
+        const int buf = lt & 1;
+        const uint32_t acc = tmem + buf * acc_cols;
+        mbar_wait(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // epilogue drained this buffer
+        tc_fence_after();
+        const int nk = p.n_taps[tc.z] * cin_blocks;
+        for (int kit = 0; kit < nk; ++kit, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(smem_u32(&bars.full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
+            for (int j = 0; j < p.mt; ++j) {
+              const uint64_t da = make_smem_desc(sa + j * a_sub + k * 32, 16, sbo, layout);
+              umma_f16(acc + j * p.BN, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&bars.empty[s]));
+        }
+        umma_commit(smem_u32(&bars.tfull[buf]));
+      }
+    }
+  } else {
+    // ----------------------------------------------------------------- epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int hl = row / p.tw, wl = row - hl * p.tw;
+    int lt = 0, cur_n0 = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord tc = decode_tile(p, tile, m_total);
+      const int z = tc.z;
+      if (p.stats != nullptr && tc.n0 != cur_n0) {
+        if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int t = threadIdx.x - 64;
+          for (int col = t; col < p.BN; col += 128) {
+            atomicAdd(p.stats + cur_n0 + col, s_stats[0][col]);
+            atomicAdd(p.stats + p.stats_ld + cur_n0 + col, s_stats[1][col]);
+            s_stats[0][col] = 0.f;
+            s_stats[1][col] = 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        cur_n0 = tc.n0;
+      }
+      const int buf = lt & 1;
+      const uint32_t acc = tmem + buf * acc_cols;
+      mbar_wait(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      for (int sub = 0; sub < p.mt; ++sub) {
+        const int h = tc.h0 + sub * p.th + hl, w = tc.w0 + wl;
+        const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+        const size_t pix =
+            ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
+        const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
+        for (int c = 0; c < p.BN; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(acc + ((uint32_t)(q * 32) << 16) + sub * p.BN + c, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias != nullptr) x += __ldg(p.bias + tc.n0 + c + j);
+            v[j] = apply_act(x, p.act, p.slope);
+          }
+          if (valid) {
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c);
+              o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                pack_bf16(v[6], v[7]));
+              o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
+                                pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            }
+          }
+          if (p.stats != nullptr) {
+            float s1[16], s2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]))) : 0.f;
+              s1[j] = x;
+              s2[j] = x * x;
+            }
+            const float t1 = column_sums16(s1, lane);
+            const float t2 = column_sums16(s2, lane);
+            if ((lane & 1) == 0) {
+              const int col = c + column_of_lane(lane);
+              atomicAdd(&s_stats[0][col], t1);
+              atomicAdd(&s_stats[1][col], t2);
+            }
+          }
+        }
+      }
+      // this warp is done reading the buffer: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars.tempty[buf]));
+    }
+    if (p.stats != nullptr && cur_n0 >= 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;
+      for (int col = t; col < p.BN; col += 128) {
+        atomicAdd(p.stats + cur_n0 + col, s_stats[0][col]);
+        atomicAdd(p.stats + p.stats_ld + cur_n0 + col, s_stats[1][col]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------ wgrad
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX,
@@ -657,6 +896,8 @@ static int ensure_smem_optin() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_alltaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e != cudaSuccess) return set_error(B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   g_smem_optin_done = 1;
@@ -696,6 +937,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
                     int in_stride, int out_stride, const float* bias, int act, float slope,
                     float* stats, int stats_ld, int tune, cudaStream_t stream) {
   // tune = BN | (mt << 12) | (stages << 16); a zero field = choose automatically
+  // (bit 20: persistent kernel)
   const int bn_override = tune & 0xFFF, mt_override = (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
   if (n_classes < 1 || n_classes > kMaxClasses) return set_error(B200_EINVAL, "conv_igemm: bad class count %d", n_classes);
   if (cin_pad % 32) return set_error(B200_EINVAL, "conv_igemm: cin_pad %d not a multiple of 32", cin_pad);
@@ -808,8 +1050,25 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);
   if (rc) return rc;
 
-  dim3 grid(max_tiles, filt_rows / p.BN, n_classes);
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const char* e_ps = getenv("B200_PERSIST");
+  const int persist = e_ps ? atoi(e_ps) : ((tune >> 20) & 1);
+  if (persist && 2 * p.mt * p.BN <= 512) {
+    int m_total = 0;
+    for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
+    const int total_tiles = m_total * (filt_rows / p.BN);
+    // resident CTAs: as many per SM as shared memory and TMEM (2 accumulator buffers each) allow
+    int per_sm = (int)((227 * 1024 - 4096) / (smem + 3 * 1024));
+    const int tmem_need = 2 * p.mt * p.BN <= 32 ? 32 : (2 * p.mt * p.BN <= 64 ? 64 : (2 * p.mt * p.BN <= 128 ? 128 : (2 * p.mt * p.BN <= 256 ? 256 : 512)));
+    if (per_sm > 512 / tmem_need) per_sm = 512 / tmem_need;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int grid_p = 148 * per_sm;
+    if (grid_p > total_tiles) grid_p = total_tiles;
+    conv_igemm_persistent_kernel<<<grid_p, kThreads, smem, stream>>>(tmA, tmB, p, m_total, total_tiles);
+    return check_launch("conv_igemm(persistent)");
+  }
+  dim3 grid(max_tiles, filt_rows / p.BN, n_classes);
   conv_igemm_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
   return check_launch("conv_igemm");
 }

@@ -107,16 +107,18 @@ for key, (kind, m) in sorted(records.items()):
 
             run(0)
             base = timeit(lambda: run(0))
-            for bn, mt, st in itertools.product((256, 128, 64, 32, 16), (1, 2), (2, 3, 4, 6)):
+            for bn, mt, st, ps in itertools.product((256, 128, 64, 32, 16), (1, 2), (2, 3, 4, 6), (0, 1)):
                 if m["rows"] % bn or bn * mt > 512:
                     continue
-                stage = mt * 128 * kc * 2 + bn * kc * 2
-                if st * stage > 216 * 1024:
+                if ps and 2 * bn * mt > 512:
                     continue
-                tune = bn | (mt << 12) | (st << 16)
+                stage = mt * 128 * kc * 2 + bn * kc * 2
+                if st * stage > 208 * 1024:
+                    continue
+                tune = bn | (mt << 12) | (st << 16) | (ps << 20)
                 try:
                     run(tune)
-                    results.append((timeit(lambda: run(tune)), tune, "BN%d MT%d S%d" % (bn, mt, st)))
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d MT%d S%d%s" % (bn, mt, st, " P" if ps else "")))
                 except Exception as ex:  # a configuration the launcher rejects
                     continue
         else:

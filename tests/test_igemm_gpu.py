@@ -134,8 +134,8 @@ def test_conv_wgrad(cuda_lib, case):
     assert err < 1e-3, err
 
 
-@pytest.mark.parametrize("case", [(2, 19, 64, 128, 256, 4, 2, 1), (2, 32, 64, 96, 160, 3, 2, 1), (1, 32, 32, 128, 192, 3, 1, 1),
-                                  (2, 19, 160, 64, 160, 4, 2, 1)])
+@pytest.mark.parametrize("case", [(2, 19, 64, 1024, 512, 4, 2, 1), (2, 32, 64, 96, 160, 3, 2, 1), (1, 32, 32, 128, 192, 3, 1, 1),
+                                  (1, 19, 160, 1024, 1026, 4, 2, 1)])
 def test_conv_wgrad_thin_input_all_taps(cuda_lib, case):
     """Cin <= 32 with many pixels takes the all-taps-resident kernel; the input is a 19/32-channel
     view of a 32-channel buffer as produced by upsample_softmax."""
