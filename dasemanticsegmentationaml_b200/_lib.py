@@ -127,14 +127,30 @@ def ensure_device(index):
     _checked_devices.add(index)
 
 
+def set_device_index(index):
+    """Device whose current stream the launches go to (one process drives one GPU)."""
+    global _device_index
+    _device_index = int(index)
+
+
 def ptr(t):
     """Raw device pointer of a tensor (or None)."""
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+_raw_stream = None
+_device_index = 0
+
+
 def stream():
-    import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw cudaStream_t of torch's current stream (the capture stream while a CUDA graph records)."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if _raw_stream is None:
+            _raw_stream = lambda dev: torch.cuda.current_stream(dev).cuda_stream  # noqa: E731
+    return ctypes.c_void_p(_raw_stream(_device_index))
 
 
 def int_array(values):

@@ -116,6 +116,7 @@ def run_module(module, *inputs):
         raise _lib.B200Error("%s only runs on a B200 (got a %s tensor); there is no CPU fallback"
                              % (type(module).__name__, dev.type))
     _lib.ensure_device(dev.index or 0)
+    _lib.set_device_index(dev.index or 0)
     ops.refresh_packs(module, force=module.training or getattr(module, "_b200_dirty", False))
     object.__setattr__(module, "_b200_dirty", False)
     out = _ModuleFunction.apply(module, len(inputs), *inputs, *module_params(module))

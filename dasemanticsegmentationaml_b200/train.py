@@ -147,3 +147,41 @@ def val(model, batches, n_classes=19):
     h = hist.cpu().numpy().reshape(n_classes, n_classes).astype(np.float64)
     miou_list = per_class_iu(h)
     return float(np.mean(precisions)), float(np.mean(miou_list))
+
+
+class GraphedStep(object):
+    """A whole train step captured once into a CUDA graph and replayed.
+
+    At B200 speeds the step is host-bound in eager mode (about a thousand launches plus the Python
+    that issues them take as long as the kernels themselves), so the forward, the hand-written
+    backward, the NCCL gradient all-reduces and the fused optimizer updates are recorded into ONE
+    graph with static input buffers; a replay costs a single launch.  `fn(**inputs)` must be free
+    of host synchronisation (train_step / train_da_step are) and is warmed up on a side stream first
+    (lazy state: packed filters, momentum buffers, NCCL communicators).  Optimizers must be
+    capture-safe (``fused=True``; Adam additionally ``capturable=True``).
+    """
+
+    def __init__(self, fn, example_inputs, warmup=3):
+        self.fn = fn
+        self.static = {k: v.clone() for k, v in example_inputs.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(**self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn(**self.static)
+
+    def load(self, **inputs):
+        """Copy new inputs into the graph's static buffers (device or pinned-host tensors)."""
+        for k, v in inputs.items():
+            self.static[k].copy_(v, non_blocking=True)
+
+    def __call__(self, **inputs):
+        if inputs:
+            self.load(**inputs)
+        self.graph.replay()
+        return self.outputs

@@ -291,3 +291,40 @@ def test_weight_updates_reach_the_packed_filters(cuda_lib, fused):
         ref = F.relu(F.batch_norm(F.conv2d(x.float(), bf16_round(m.conv.weight), None, 1, 1), m.bn.running_mean,
                                   m.bn.running_var, m.bn.weight, m.bn.bias, False, 0.1, 1e-5))
     assert rel_l2(y, ref) < 1e-2
+
+
+def test_graphed_da_step_matches_eager(cuda_lib):
+    """The CUDA-graph replay of the DA step must train exactly like the eager launches."""
+    from dasemanticsegmentationaml_b200 import train as T
+    from dasemanticsegmentationaml_b200.model import BiSeNet, FCDiscriminator
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 3, 128, 256, generator=g).to(DEV)
+    xt = torch.randn(2, 3, 128, 256, generator=g).to(DEV)
+    labels = torch.randint(0, 19, (2, 128, 256), generator=g).to(DEV)
+    runs = []
+    for graphed in (False, True):
+        sd = O.make_bisenet_state(seed=21)
+        dsd = O.make_discriminator_state("dense", seed=4)
+        m = load_oracle_state(BiSeNet("STDCNet813", 19), sd).to(DEV)
+        d = load_oracle_state(FCDiscriminator(19), dsd).to(DEV)
+        opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
+        opt_d = torch.optim.Adam(d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
+
+        def fn(images, labels, images_t):
+            return T.train_da_step(m, d, opt, opt_d, images, labels, images_t)
+
+        losses = []
+        if graphed:
+            gs = T.GraphedStep(fn, dict(images=x, labels=labels, images_t=xt), warmup=0)
+            for _ in range(4):
+                losses.append([float(v) for v in gs()])
+        else:
+            for _ in range(4):
+                losses.append([float(v) for v in fn(x, labels, xt)])
+        runs.append(losses)
+    print("eager  ", runs[0])
+    print("graphed", runs[1])
+    for a, b in zip(runs[0], runs[1]):
+        for u, v in zip(a, b):
+            assert abs(u - v) < 2e-2 * max(1.0, abs(u)), (runs[0], runs[1])
+    assert runs[1][3][0] != runs[1][0][0]  # the weights do move between replays
