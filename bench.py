@@ -361,8 +361,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     peaks = measured_peaks()
@@ -415,8 +414,16 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (ex,)}
     print(json.dumps(line))
+    _finish(world)
+
+
+def _finish(world):
+    """Leave without tearing NCCL down: destroying a communicator that a live CUDA graph still
+    references can block forever, and the process is exiting anyway."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():

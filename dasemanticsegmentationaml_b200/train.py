@@ -167,7 +167,7 @@ class GraphedStep(object):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):  # at least once: lazy state must exist before capture
                 fn(**self.static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
