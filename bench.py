@@ -62,8 +62,12 @@ def cpu_da_step_rate(workload, batch, steps, warmup, threads=None):
     """Oracle port of the reference step (fp32, CPU, all host threads): images per second."""
     import torch
     from oracle import segnet_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1: override it)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     kind = {"da_dense": "dense", "da_dwsep": "dwsep", "da_dwsep_bn": "dwsep_bn"}.get(workload)
     h, w = (720, 1280) if workload == "supervised" else (H, W)
     g = torch.Generator().manual_seed(0)

@@ -262,16 +262,16 @@ struct PersistBarriers {
   uint64_t empty[kMaxStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t bfull;
   uint32_t tmem_base;
 };
 
 struct TileCoord {
   int z, n_img, h0, w0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int m_total) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int n_tile, int m) {
   TileCoord t;
-  const int n_tile = tile / m_total;
-  int rem = tile - n_tile * m_total;
+  int rem = m;
   t.n0 = n_tile * p.BN;
   t.z = 0;
 #pragma unroll
@@ -292,7 +292,8 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                             const __grid_constant__ ConvParams p, int m_total, int total_tiles) {
+                             const __grid_constant__ ConvParams p, int m_total, int n_tiles, int b_resident,
+                             int n_slabs) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PersistBarriers bars;
   __shared__ float s_stats[2][256];
@@ -303,8 +304,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   const uint32_t a_sub = 128u * p.KC * 2u;
   const uint32_t a_bytes = a_sub * p.mt;
   const uint32_t b_bytes = (uint32_t)p.BN * p.KC * 2u;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
   const int cin_blocks = p.cin_pad / p.KC;
+  // b_resident: the CTA's whole filter tile (n_slabs x cin_blocks blocks of BN x KC) is loaded once
+  // and stays in shared memory; only the activation tiles stream through the pipeline.
+  const uint32_t stage_bytes = b_resident ? a_bytes : a_bytes + b_bytes;
+  const uint32_t bres_bytes = b_resident ? (uint32_t)(n_slabs * cin_blocks) * b_bytes : 0u;
+  const uint32_t stage_base = smem_base + bres_bytes;
+  // a CTA keeps ONE filter tile: CTA c works on n_tile = c % n_tiles and on the pixel tiles
+  // m = c / n_tiles, + gridDim.x / n_tiles, ...
+  const int my_n = blockIdx.x % n_tiles;
+  const int m_first = blockIdx.x / n_tiles, m_step = gridDim.x / n_tiles;
   const uint32_t acc_cols = (uint32_t)(p.mt * p.BN);          // one accumulator buffer
   const uint32_t want = 2u * acc_cols;
   const uint32_t tmem_cols = want <= 32 ? 32u : (want <= 64 ? 64u : (want <= 128 ? 128u : (want <= 256 ? 256u : 512u)));
@@ -318,6 +327,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       mbar_init(smem_u32(&bars.tfull[b]), 1);
       mbar_init(smem_u32(&bars.tempty[b]), 4);  // one arrival per epilogue warp
     }
+    mbar_init(smem_u32(&bars.bfull), 1);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
@@ -338,8 +348,14 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile, m_total);
+      if (b_resident) {
+        const uint32_t bf = smem_u32(&bars.bfull);
+        mbar_expect_tx(bf, bres_bytes);
+        for (int kb = 0; kb < n_slabs * cin_blocks; ++kb)
+          tma_load_2d(smem_base + kb * b_bytes, &tmB, bf, kb * p.KC, my_n * p.BN);
+      }
+      for (int m = m_first; m < m_total; m += m_step) {
+        const TileCoord tc = decode_tile(p, my_n, m);
         for (int t = 0; t < p.n_taps[tc.z]; ++t) {
           const int hh = tc.h0 * p.in_stride + p.tap_dh[tc.z][t];
           const int ww = tc.w0 * p.in_stride + p.tap_dw[tc.z][t];
@@ -350,9 +366,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
             const uint32_t full = smem_u32(&bars.full[s]);
             mbar_expect_tx(full, stage_bytes);
-            const uint32_t sa = smem_base + s * stage_bytes;
+            const uint32_t sa = stage_base + s * stage_bytes;
             tma_load_4d(sa, &tmA, full, cb * p.KC, ww, hh, tc.n_img);
-            tma_load_2d(sa + a_bytes, &tmB, full, kb + cb * p.KC, tc.n0);
+            if (!b_resident) tma_load_2d(sa + a_bytes, &tmB, full, kb + cb * p.KC, tc.n0);
           }
         }
       }
@@ -365,8 +381,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       const uint32_t sbo = 8u * p.KC * 2u;
       const int ksteps = p.KC / 16;
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-        const TileCoord tc = decode_tile(p, tile, m_total);
+      if (b_resident) mbar_wait(smem_u32(&bars.bfull), 0);
+      for (int m = m_first; m < m_total; m += m_step, ++lt) {
+        const TileCoord tc = decode_tile(p, my_n, m);
         const int buf = lt & 1;
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // epilogue drained this buffer
@@ -377,8 +394,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(smem_u32(&bars.full[s]), ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t sa = stage_base + s * stage_bytes;
+          const uint32_t sb = b_resident
+                                  ? smem_base + (uint32_t)(p.tap_k[tc.z][kit / cin_blocks] * cin_blocks + kit % cin_blocks) * b_bytes
+                                  : sa + a_bytes;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
             for (int j = 0; j < p.mt; ++j) {
@@ -397,8 +416,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     const int row = q * 32 + lane;
     const int hl = row / p.tw, wl = row - hl * p.tw;
     int lt = 0, cur_n0 = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord tc = decode_tile(p, tile, m_total);
+    for (int m = m_first; m < m_total; m += m_step, ++lt) {
+      const TileCoord tc = decode_tile(p, my_n, m);
       const int z = tc.z;
       if (p.stats != nullptr && tc.n0 != cur_n0) {
         if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
@@ -1050,9 +1069,19 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);
   if (rc) return rc;
 
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024;
   const char* e_ps = getenv("B200_PERSIST");
   const int persist = e_ps ? atoi(e_ps) : ((tune >> 20) & 1);
+  // bit 21: keep the CTA's filter tile resident in shared memory (persistent kernel only)
+  int b_res = (tune >> 21) & 1;
+  const size_t bres_bytes = (size_t)n_slabs * cin_pad * p.BN * 2;
+  if (b_res && (!persist || bres_bytes > 128 * 1024)) b_res = 0;
+  if (b_res) {
+    const int a_stage = p.mt * 128 * p.KC * 2;
+    while (p.stages > 2 && bres_bytes + (size_t)p.stages * a_stage > 208 * 1024) --p.stages;
+    if (bres_bytes + (size_t)p.stages * a_stage > 208 * 1024) b_res = 0;
+    else smem = bres_bytes + (size_t)p.stages * a_stage + 1024;
+  }
   if (persist && 2 * p.mt * p.BN <= 512) {
     int m_total = 0;
     for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
@@ -1065,7 +1094,10 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     if (per_sm < 1) per_sm = 1;
     int grid_p = 148 * per_sm;
     if (grid_p > total_tiles) grid_p = total_tiles;
-    conv_igemm_persistent_kernel<<<grid_p, kThreads, smem, stream>>>(tmA, tmB, p, m_total, total_tiles);
+    const int n_tiles = filt_rows / p.BN;
+    grid_p = (grid_p / n_tiles) * n_tiles;  // every CTA keeps one filter tile
+    if (grid_p < n_tiles) grid_p = n_tiles;
+    conv_igemm_persistent_kernel<<<grid_p, kThreads, smem, stream>>>(tmA, tmB, p, m_total, n_tiles, b_res, n_slabs);
     return check_launch("conv_igemm(persistent)");
   }
   dim3 grid(max_tiles, filt_rows / p.BN, n_classes);

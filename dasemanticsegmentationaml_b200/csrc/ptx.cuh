@@ -150,6 +150,14 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint
   d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
+// Same with the 3-bit "matrix base offset" (bits [49,52)): needed when the start address is not
+// aligned to the swizzle pattern repeat (1024 B for 128B swizzle), e.g. a window that starts a few
+// 128-byte rows into an atom; base_offset = (start_address >> 7) & 7.
+__host__ __device__ __forceinline__ uint64_t make_smem_desc_off(uint32_t saddr, uint32_t lbo_bytes,
+                                                                uint32_t sbo_bytes, uint32_t layout,
+                                                                uint32_t base_offset) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes, layout) | ((uint64_t)(base_offset & 7) << 49);
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c fmt (1 = f32)  [7,10) a fmt (1 = bf16)  [10,13) b fmt  [15] a MN-major  [16] b MN-major
 //   [17,23) N >> 3   [24,29) M >> 4

@@ -107,10 +107,12 @@ for key, (kind, m) in sorted(records.items()):
 
             run(0)
             base = timeit(lambda: run(0))
-            for bn, mt, st, ps in itertools.product((256, 128, 64, 32, 16), (1, 2), (2, 3, 4, 6), (0, 1)):
+            for bn, mt, st, ps in itertools.product((256, 128, 64, 32, 16), (1, 2), (2, 3, 4, 6), (0, 1, 3)):
                 if m["rows"] % bn or bn * mt > 512:
                     continue
                 if ps and 2 * bn * mt > 512:
+                    continue
+                if ps == 3 and m["n_slabs"] * m["cin_pad"] * bn * 2 > 128 * 1024:
                     continue
                 stage = mt * 128 * kc * 2 + bn * kc * 2
                 if st * stage > 208 * 1024:
@@ -118,7 +120,7 @@ for key, (kind, m) in sorted(records.items()):
                 tune = bn | (mt << 12) | (st << 16) | (ps << 20)
                 try:
                     run(tune)
-                    results.append((timeit(lambda: run(tune)), tune, "BN%d MT%d S%d%s" % (bn, mt, st, " P" if ps else "")))
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d MT%d S%d%s" % (bn, mt, st, {0: "", 1: " P", 3: " PB"}[ps])))
                 except Exception as ex:  # a configuration the launcher rejects
                     continue
         else:
