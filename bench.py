@@ -411,9 +411,12 @@ def run_b200(args):
                 json.dump({"by_kernel": prof, "by_shape": _lib.last_profile_detail}, f, indent=1)
     if not args.no_cpu_baseline and world == 1 and (args.workload.startswith("da_") or args.workload == "supervised"):
         try:
-            rate, cms, threads = cpu_da_step_rate(args.workload, 2, 1, 1)
+            cb_batch, cb_steps = 4, 4
+            rate, cms, threads = cpu_da_step_rate(args.workload, cb_batch, cb_steps, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
-                                    "sample": "one 2-image step of the oracle port (fp32 torch CPU) after one warm-up step, %.1f s" % (cms / 1e3)}
+                                    "sample": "%d steps of %d source + %d target images (same %dx%d workload, reduced batch) "
+                                              "of the oracle port, fp32 torch CPU, after one warm-up step; %.1f s per step"
+                                              % (cb_steps, cb_batch, cb_batch, h, w, cms / 1e3)}
         except Exception as ex:  # the baseline is informational; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (ex,)}
