@@ -78,6 +78,50 @@ __device__ __forceinline__ float softmax_inplace(float (&v)[NC], float* lse) {
   return inv;
 }
 
+// Fast-path staging for up-sampling factors >= 7 (every configuration of the reference: 64x128 ->
+// 512x1024, 90x160 -> 720x1280, 128x256 -> 1024x2048).  The low-resolution pixels under a CTA's
+// tile are loaded once into shared memory (coalesced float4) and every full-resolution pixel
+// reads its four corners from there as broadcast LDS.128 (a 32-pixel row touches <= 6 distinct
+// low-resolution columns).  Both fast kernels were instruction-issue bound in ncu, so the
+// per-pixel instruction count is what these helpers are written for.
+constexpr int LJ = 6;        // low-res columns under a 32-pixel wide tile: 31 * sw + 2 <= 6
+constexpr int LI_ROW = 3;    // low-res rows under 8 full-resolution rows:   7 * sh + 2 <= 3
+constexpr int SH_ROWS = 64;  // rows of a backward strip (8 warps x 8 rows)
+constexpr int LI = 11;       // low-res rows under a strip:                 63 * sh + 2 <= 11
+constexpr int kLP = 20;      // floats per staged low-res pixel (19 classes, float4 aligned)
+
+template <int ROWS>
+__device__ __forceinline__ void stage_lowres(const float* __restrict__ lr, int lr_ld, int h_lr, int w_lr, int n,
+                                             int i_min, int j_min, float* s_lr) {
+  for (int idx = threadIdx.x; idx < ROWS * LJ * 5; idx += blockDim.x) {
+    const int q = idx % 5, pix = idx / 5, jj = pix % LJ, ii = pix / LJ;
+    const int i = min(i_min + ii, h_lr - 1), j = min(j_min + jj, w_lr - 1);
+    reinterpret_cast<float4*>(s_lr)[pix * 5 + q] =
+        __ldg(reinterpret_cast<const float4*>(lr + (((int64_t)n * h_lr + i) * w_lr + j) * lr_ld) + q);
+  }
+}
+template <int NC>
+__device__ __forceinline__ void sample_smem(const float* s_lr, const Interp& ih, const Interp& iw, int i_min,
+                                            int j_min, float (&v)[NC]) {
+  const float4* p00 = reinterpret_cast<const float4*>(s_lr + ((ih.i0 - i_min) * LJ + iw.i0 - j_min) * kLP);
+  const float4* p01 = reinterpret_cast<const float4*>(s_lr + ((ih.i0 - i_min) * LJ + iw.i1 - j_min) * kLP);
+  const float4* p10 = reinterpret_cast<const float4*>(s_lr + ((ih.i1 - i_min) * LJ + iw.i0 - j_min) * kLP);
+  const float4* p11 = reinterpret_cast<const float4*>(s_lr + ((ih.i1 - i_min) * LJ + iw.i1 - j_min) * kLP);
+  const float w00 = ih.l0 * iw.l0, w01 = ih.l0 * iw.l1, w10 = ih.l1 * iw.l0, w11 = ih.l1 * iw.l1;
+  constexpr int NV = (NC + 3) / 4;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const float4 a = p00[q], b = p01[q], c = p10[q], d = p11[q];
+    const float r[4] = {w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x,
+                        w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y,
+                        w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z,
+                        w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4 * q + k < NC) v[4 * q + k] = r[k];
+  }
+}
+
 // ------------------------------------------------------------------ forward
 // mode 0: full-resolution logits, NCHW (fp32 or bf16)        -> out_full
 // mode 1: cross-entropy: acc[0] += sum loss, acc[1] += #valid; optional per-pixel loss map
@@ -138,8 +182,10 @@ upsample_fwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
         const float b = (2 * c + 1 < NC) ? v[2 * c + 1 < NC ? 2 * c + 1 : 0] : 0.f;
         pk[c] = pack_bf16(a, b);
       }
-      for (int c = 0; c < p_ld / 8; ++c)
-        reinterpret_cast<uint4*>(q)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+#pragma unroll
+      for (int c = 0; c < kMaxCls / 8; ++c)
+        if (c < p_ld / 8)
+          reinterpret_cast<uint4*>(q)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
     } else {
       int best = 0;
       float bv = v[0];
@@ -177,6 +223,113 @@ upsample_fwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
   }
 }
 
+// Tiled variant of the forward (one CTA = one 8 x 32 pixel tile, same modes), used whenever the
+// up-sampling factor is >= 7 so that a tile's low-resolution footprint fits LI_ROW x LJ.
+template <int NC>
+__global__ void __launch_bounds__(TH * TW)
+upsample_fwd_tiled_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, int w_lr, int H, int W,
+                          int mode, void* __restrict__ out, int out_is_bf16_or_u8, int p_ld,
+                          const int64_t* __restrict__ labels, int ignore_index,
+                          double* __restrict__ acc, float* __restrict__ loss_map) {
+  __shared__ __align__(16) float s_lr[LI_ROW * LJ * kLP];
+  __shared__ Interp s_iw[TW], s_ih[TH];
+  __shared__ float s_part[2][TH];
+  const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
+  const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  const int n = blockIdx.x / (tiles_w * tiles_h);
+  const int t_in = blockIdx.x - n * tiles_w * tiles_h;
+  const int h_base = (t_in / tiles_w) * TH, w_base = (t_in % tiles_w) * TW;
+  const int tx = threadIdx.x % TW, ty = threadIdx.x / TW;
+  if (threadIdx.x < TW) s_iw[threadIdx.x] = interp_at(min(w_base + threadIdx.x, W - 1), sw, w_lr);
+  if (threadIdx.x >= TW && threadIdx.x < TW + TH)
+    s_ih[threadIdx.x - TW] = interp_at(min(h_base + threadIdx.x - TW, H - 1), sh, h_lr);
+  __syncthreads();
+  stage_lowres<LI_ROW>(lr, lr_ld, h_lr, w_lr, n, s_ih[0].i0, s_iw[0].i0, s_lr);
+  __syncthreads();
+  const int h = h_base + ty, w = w_base + tx;
+  float loss = 0.f, valid = 0.f;
+  if (h < H && w < W) {
+    const int64_t p = ((int64_t)n * H + h) * W + w;
+    float v[NC];
+    sample_smem<NC>(s_lr, s_ih[ty], s_iw[tx], s_ih[0].i0, s_iw[0].i0, v);
+    if (mode == 0) {
+      const int64_t plane = (int64_t)H * W;
+      const int64_t o = (int64_t)n * NC * plane + (int64_t)h * W + w;
+      if (out_is_bf16_or_u8) {
+        __nv_bfloat16* q = static_cast<__nv_bfloat16*>(out);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) q[o + c * plane] = __float2bfloat16(v[c]);
+      } else {
+        float* q = static_cast<float*>(out);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) q[o + c * plane] = v[c];
+      }
+    } else if (mode == 1) {
+      const int64_t lab = labels[p];
+      float l = 0.f;
+      if (lab != ignore_index) {
+        float tgt = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) tgt = (c == lab) ? v[c] : tgt;
+        float lse;
+        softmax_inplace<NC>(v, &lse);
+        l = fmaxf(lse - tgt, 0.f);
+        loss = l;
+        valid = 1.f;
+      }
+      if (loss_map != nullptr) loss_map[p] = l;
+    } else if (mode == 2) {
+      float lse;
+      softmax_inplace<NC>(v, &lse);
+      __nv_bfloat16* q = static_cast<__nv_bfloat16*>(out) + p * p_ld;
+      uint32_t pk[kMaxCls / 2];
+#pragma unroll
+      for (int c = 0; c < kMaxCls / 2; ++c) {
+        const float a = (2 * c < NC) ? v[2 * c < NC ? 2 * c : 0] : 0.f;
+        const float b = (2 * c + 1 < NC) ? v[2 * c + 1 < NC ? 2 * c + 1 : 0] : 0.f;
+        pk[c] = pack_bf16(a, b);
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxCls / 8; ++c)
+        if (c < p_ld / 8)
+          reinterpret_cast<uint4*>(q)[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    } else {
+      int best = 0;
+      float bv = v[0];
+#pragma unroll
+      for (int c = 1; c < NC; ++c)
+        if (v[c] > bv) {
+          bv = v[c];
+          best = c;
+        }
+      if (out_is_bf16_or_u8)
+        static_cast<uint8_t*>(out)[p] = (uint8_t)best;
+      else
+        static_cast<int64_t*>(out)[p] = best;
+    }
+  }
+  if (mode == 1) {
+    const float wl = warp_sum(loss), wv = warp_sum(valid);
+    if (tx == 0) {
+      s_part[0][ty] = wl;
+      s_part[1][ty] = wv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int i = 0; i < TH; ++i) {
+        a += s_part[0][i];
+        b += s_part[1][i];
+      }
+      if (b > 0.0) {
+        atomicAdd(&acc[0], a);
+        atomicAdd(&acc[1], b);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ backward
 // d_lr[n, i, j, c] += sum over full-resolution pixels of  wh(h, i) * ww(w, j) * G[n, h, w, c]
 // with G produced per pixel according to `mode`:
@@ -194,7 +347,7 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
                     const float* __restrict__ pixel_weight, const float* __restrict__ coef_num,
                     const double* __restrict__ coef_den, float coef_scale, float* __restrict__ d_lr,
                     double* __restrict__ loss_acc) {
-  __shared__ float s_g[TH][TW][NC + 1];
+  __shared__ float s_g[TH][TW][NC + 2];
   __shared__ float s_loss[2][TH];
   __shared__ float s_a[TH][MAXJ][NC + 1];
   __shared__ Interp s_iw[TW], s_ih[TH];
@@ -333,6 +486,196 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
     }
     if (acc0 != 0.f) atomicAdd(dst + (int64_t)i_cur * w_lr * lr_ld, acc0);
     if (acc1 != 0.f && i_cur + 1 < h_lr) atomicAdd(dst + (int64_t)(i_cur + 1) * w_lr * lr_ld, acc1);
+  }
+}
+
+// Fast backward (up-sampling factor >= 7): one CTA = a strip of SH_ROWS x TW pixels; warp w owns
+// rows 8w .. 8w+7 and a lane owns one column.  A thread walks its 8 pixels and folds their class
+// gradients, weighted by the vertical interpolation weights, into <= 3 low-resolution rows held in
+// registers (the transposed interpolation along h costs 2 FMAs per class and pixel, no shared
+// memory).  The per-column partials are added into a CTA-wide shared buffer, reduced along w with
+// a precomputed weight table, and one atomicAdd per touched low-resolution value leaves the CTA:
+// ~1/6 of the global atomics and ~1/5 of the instructions of the generic tile kernel.
+template <int NC>
+__global__ void __launch_bounds__(256)
+upsample_bwd_strip_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, int w_lr, int H, int W,
+                          int mode, const void* __restrict__ grad_in, int grad_is_bf16, int p_ld,
+                          const int64_t* __restrict__ labels, int ignore_index,
+                          const float* __restrict__ pixel_weight, const float* __restrict__ coef_num,
+                          const double* __restrict__ coef_den, float coef_scale, float* __restrict__ d_lr,
+                          double* __restrict__ loss_acc) {
+  __shared__ __align__(16) float s_lr[LI * LJ * kLP];
+  __shared__ float s_v[LI][TW][NC];   // vertical partials: [low-res row][column][class]
+  __shared__ float s_wx[LJ][TW];      // weight of column x on low-res column jj
+  __shared__ int s_xlo[LJ], s_xhi[LJ];
+  __shared__ Interp s_iw[TW], s_ih[SH_ROWS];
+  __shared__ float s_loss[2][8];
+  const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
+  const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + SH_ROWS - 1) / SH_ROWS;
+  const int n = blockIdx.x / (tiles_w * tiles_h);
+  const int t_in = blockIdx.x - n * tiles_w * tiles_h;
+  const int h_base = (t_in / tiles_w) * SH_ROWS, w_base = (t_in % tiles_w) * TW;
+  const int tx = threadIdx.x % TW, wp = threadIdx.x / TW;
+  if (threadIdx.x < TW) s_iw[threadIdx.x] = interp_at(min(w_base + threadIdx.x, W - 1), sw, w_lr);
+  if (threadIdx.x >= TW && threadIdx.x < TW + SH_ROWS)
+    s_ih[threadIdx.x - TW] = interp_at(min(h_base + threadIdx.x - TW, H - 1), sh, h_lr);
+  for (int i = threadIdx.x; i < LI * TW * NC; i += 256) (&s_v[0][0][0])[i] = 0.f;
+  __syncthreads();
+  const int i_min = s_ih[0].i0, j_min = s_iw[0].i0;
+  if (mode != 0) stage_lowres<LI>(lr, lr_ld, h_lr, w_lr, n, i_min, j_min, s_lr);
+  if (threadIdx.x < LJ * TW) {  // weight table of the transposed interpolation along w
+    const int jj = threadIdx.x / TW, x = threadIdx.x % TW;
+    const Interp iw = s_iw[x];
+    float wgt = 0.f;
+    if (w_base + x < W) wgt = (iw.i0 - j_min == jj ? iw.l0 : 0.f) + (iw.i1 - j_min == jj ? iw.l1 : 0.f);
+    s_wx[jj][x] = wgt;
+    const unsigned nz = __ballot_sync(0xffffffffu, wgt != 0.f);
+    if (x == 0) {
+      s_xlo[jj] = nz ? __ffs(nz) - 1 : 0;
+      s_xhi[jj] = nz ? 32 - __clz(nz) : 0;
+    }
+  }
+  __syncthreads();
+
+  const Interp iw = s_iw[tx];
+  const int w = w_base + tx;
+  const int i_w = s_ih[wp * 8].i0;  // first low-resolution row this warp touches
+  float acc0[NC], acc1[NC], acc2[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc0[c] = acc1[c] = acc2[c] = 0.f;
+  float my_loss = 0.f, my_valid = 0.f;
+  float cf0 = coef_scale * (coef_num != nullptr ? *coef_num : 1.f);
+  if (coef_den != nullptr) cf0 /= (float)fmax(*coef_den, 1e-30);
+  const int64_t plane = (int64_t)H * W;
+#pragma unroll 1
+  for (int r = 0; r < 8; ++r) {
+    const int h = h_base + wp * 8 + r;
+    if (h >= H) break;
+    const Interp ih = s_ih[wp * 8 + r];
+    float g[NC];
+    bool live = w < W;
+    if (live) {
+      const int64_t p = ((int64_t)n * H + h) * W + w;
+      if (mode == 0) {
+        const int64_t o = (int64_t)n * NC * plane + (int64_t)h * W + w;
+        if (grad_is_bf16) {
+          const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(grad_in);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) g[c] = __bfloat162float(q[o + c * plane]);
+        } else {
+          const float* q = static_cast<const float*>(grad_in);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) g[c] = q[o + c * plane];
+        }
+      } else {
+        sample_smem<NC>(s_lr, ih, iw, i_min, j_min, g);
+        if (mode == 1) {
+          const int64_t lab = labels[p];
+          if (lab != ignore_index) {
+            float tgt = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) tgt = (c == lab) ? g[c] : tgt;
+            float lse;
+            softmax_inplace<NC>(g, &lse);
+            my_loss += fmaxf(lse - tgt, 0.f);
+            my_valid += 1.f;
+            const float cf = pixel_weight != nullptr ? cf0 * pixel_weight[p] : cf0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) g[c] = (g[c] - (c == lab ? 1.f : 0.f)) * cf;
+          } else {
+            live = false;
+          }
+        } else {
+          float lse;
+          softmax_inplace<NC>(g, &lse);
+          float dp[NC];
+          const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(grad_in) + p * p_ld;
+          if ((p_ld & 7) == 0) {  // 16-byte aligned pixel rows: three vector loads cover 24 classes
+            uint32_t raw[12];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (8 * k < NC) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(q) + k);
+                raw[4 * k] = u.x; raw[4 * k + 1] = u.y; raw[4 * k + 2] = u.z; raw[4 * k + 3] = u.w;
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const float2 f = unpack_bf16(raw[c >> 1]);
+              dp[c] = (c & 1) ? f.y : f.x;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) dp[c] = __bfloat162float(q[c]);
+          }
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) dot += dp[c] * g[c];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) g[c] = g[c] * (dp[c] - dot) * cf0;
+        }
+      }
+    }
+    if (live) {
+      const bool same = ih.i1 == ih.i0;  // clamped at the bottom edge
+      const float le0 = same ? ih.l0 + ih.l1 : ih.l0, le1 = same ? 0.f : ih.l1;
+      if (ih.i0 == i_w) {                // warp-uniform: the whole warp is on one row
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          acc0[c] += le0 * g[c];
+          acc1[c] += le1 * g[c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          acc1[c] += le0 * g[c];
+          acc2[c] += le1 * g[c];
+        }
+      }
+    }
+  }
+  {
+    const int row = i_w - i_min;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) atomicAdd(&s_v[row][tx][c], acc0[c]);
+    if (row + 1 < LI) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) atomicAdd(&s_v[row + 1][tx][c], acc1[c]);
+    }
+    if (row + 2 < LI) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) atomicAdd(&s_v[row + 2][tx][c], acc2[c]);
+    }
+  }
+  if (loss_acc != nullptr) {
+    const float wl = warp_sum(my_loss), wv = warp_sum(my_valid);
+    if (tx == 0) {
+      s_loss[0][wp] = wl;
+      s_loss[1][wp] = wv;
+    }
+  }
+  __syncthreads();
+  if (loss_acc != nullptr && threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      a += s_loss[0][i];
+      b += s_loss[1][i];
+    }
+    if (b > 0.0) {
+      atomicAdd(&loss_acc[0], a);
+      atomicAdd(&loss_acc[1], b);
+    }
+  }
+  // transposed interpolation along w + the CTA's contribution to d_lr
+  for (int t = threadIdx.x; t < LI * LJ * NC; t += 256) {
+    const int c = t % NC, jj = (t / NC) % LJ, ii = t / (NC * LJ);
+    const int i = i_min + ii, j = j_min + jj;
+    if (i >= h_lr || j >= w_lr) continue;
+    const int x0 = s_xlo[jj], x1 = s_xhi[jj];
+    float sum = 0.f;
+    for (int x = x0; x < x1; ++x) sum += s_wx[jj][x] * s_v[ii][x][c];
+    if (sum != 0.f) atomicAdd(d_lr + (((int64_t)n * h_lr + i) * w_lr + j) * lr_ld + c, sum);
   }
 }
 
@@ -492,6 +835,14 @@ int b200_upsample_fwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
   if (mode == 2 && (p_ld % 8 || p_ld > kMaxCls || p_ld < n_classes))
     return set_error(B200_EINVAL, "upsample_fwd: probability stride %d unsupported", p_ld);
   const int64_t total = (int64_t)N * H * W;
+  const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
+  const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
+  if (sw * (TW - 1) + 2.f <= (float)LJ && sh * (TH - 1) + 2.f <= (float)LI_ROW) {
+    const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * N;
+    upsample_fwd_tiled_kernel<19><<<tiles, TH * TW, 0, stream>>>(
+        lr, lr_ld, N, h_lr, w_lr, H, W, mode, out, out_flag, p_ld, labels, ignore_index, acc, loss_map);
+    return check_launch("upsample_fwd(tiled)");
+  }
   upsample_fwd_kernel<19><<<grid1d(total, 148 * 16), 256, 0, stream>>>(
       lr, lr_ld, N, h_lr, w_lr, H, W, mode, out, out_flag, p_ld, labels, ignore_index, acc, loss_map);
   return check_launch("upsample_fwd");
@@ -506,8 +857,16 @@ int b200_upsample_bwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int
   if (lr_ld % 4 || lr_ld < 20) return set_error(B200_EINVAL, "upsample_bwd: logits pixel stride %d must be a multiple of 4, >= 20", lr_ld);
   const float sh = H > 1 ? (float)(h_lr - 1) / (float)(H - 1) : 0.f;
   const float sw = W > 1 ? (float)(w_lr - 1) / (float)(W - 1) : 0.f;
+  if (sw * (TW - 1) + 2.f <= (float)LJ && sh * 7.f + 2.f <= (float)LI_ROW && sh * (SH_ROWS - 1) + 2.f <= (float)LI) {
+    const int strips = ((W + TW - 1) / TW) * ((H + SH_ROWS - 1) / SH_ROWS) * N;
+    upsample_bwd_strip_kernel<19><<<strips, 256, 0, stream>>>(lr, lr_ld, N, h_lr, w_lr, H, W, mode, grad_in,
+                                                             grad_is_bf16, p_ld, labels, ignore_index,
+                                                             pixel_weight, coef_num, coef_den, coef_scale, d_lr,
+                                                             loss_acc);
+    return check_launch("upsample_bwd(strip)");
+  }
   if (sw * (TW - 1) + 2.f > (float)MAXJ || sh * (TH - 1) + 2.f > (float)MAXI)
-    return set_error(B200_EINVAL, "upsample_bwd: scale %dx%d -> %dx%d is below the supported 4x up-sampling", h_lr, w_lr, H, W);
+    return set_error(B200_EINVAL, "upsample_bwd: scale %dx%d -> %dx%d is below the supported up-sampling factor (>= 5.2 along w, >= 3.5 along h)", h_lr, w_lr, H, W);
   const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * N;
   upsample_bwd_kernel<19><<<tiles, TH * TW, 0, stream>>>(lr, lr_ld, N, h_lr, w_lr, H, W, mode, grad_in,
                                                         grad_is_bf16, p_ld, labels, ignore_index,
