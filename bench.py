@@ -398,7 +398,8 @@ def run_b200(args):
             ach = c["flops"] / (c["ms"] / 1e3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
                                 "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                                "frac": ach / peaks["tf_sustained"], "traffic": None,
+                                "frac": ach / peaks["tf_sustained"], "traffic": conv_traffic(args.workload),
+                                "traffic_source": "profiles/r1_conv_traffic.json (ncu dram__bytes_read+write per launch, da_dense step)",
                                 "peak_source": peaks["source"] + " bf16_tflops_sustained",
                                 "launches_per_step": c["calls"], "avg_launch_ms": c["ms"] / c["calls"],
                                 "share_of_kernel_time": c["ms"] / tot_ms}
@@ -431,6 +432,15 @@ def _finish(world):
     sys.stderr.flush()
     if world > 1:
         os._exit(0)
+
+
+def conv_traffic(workload):
+    """DRAM bytes per conv launch from the committed ncu capture (only measured for the default workload)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_conv_traffic.json")
+    if workload != "da_dense" or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get("traffic_bytes_per_launch")
 
 
 def main():
