@@ -118,6 +118,46 @@ def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images
     return loss.detach(), loss_adv_g.detach(), loss_d_src.detach(), loss_d_tgt.detach()
 
 
+def train_da_step_nni(model, model_D, optimizer, optimizer_D, images, labels, images_t, lambda_adv=0.001):
+    """The adversarial iteration of ``train_nni.py`` (train_nni.py:105-163): the discriminator and
+    the adversarial term work on softmax(out32), gradients of the source and target passes
+    accumulate, and each optimizer steps once at the end.
+
+    Returns (loss_seg, lambda_adv * loss_adv_G, loss_D_source, loss_D_target) as device scalars."""
+    H, W = images.shape[2:]
+    model.train()
+    model_D.train()
+    for p in model_D.parameters():          # train_nni.py:108-109
+        p.requires_grad = False
+    optimizer.zero_grad()
+    optimizer_D.zero_grad()
+
+    loss, lr_src = supervised_loss(model, images, labels)          # train_nni.py:118-126
+    loss.backward()
+
+    lr_tgt = model.forward_lowres(images_t)                         # train_nni.py:132-139
+    d_out = model_D(losses.upsample_softmax(lr_tgt[2], H, W))
+    loss_d1 = losses.bce_with_logits_const(d_out, 0.0) * lambda_adv
+    loss_d1.backward()
+
+    for p in model_D.parameters():          # train_nni.py:141-142
+        p.requires_grad = True
+    out32_src = lr_src[2].detach()
+    out32_tgt = lr_tgt[2].detach()
+    d_out = model_D(losses.upsample_softmax(out32_src, H, W))      # train_nni.py:147-151
+    loss_d_src = losses.bce_with_logits_const(d_out, 0.0)
+    loss_d_src.backward()
+    d_out = model_D(losses.upsample_softmax(out32_tgt, H, W))      # train_nni.py:153-157
+    loss_d_tgt = losses.bce_with_logits_const(d_out, 1.0)
+    loss_d_tgt.backward()
+
+    allreduce_grads(_opt_params(optimizer))
+    allreduce_grads(_opt_params(optimizer_D))
+    optimizer.step()                        # train_nni.py:159-161
+    optimizer_D.step()
+    return loss.detach(), loss_d1.detach(), loss_d_src.detach(), loss_d_tgt.detach()
+
+
 @torch.no_grad()
 def eval_batch(model, images, labels, n_classes=19, hist=None, pred_dtype=torch.uint8):
     """Forward + fused up-sample/argmax + confusion-matrix accumulation for a whole batch, all on

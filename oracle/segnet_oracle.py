@@ -262,6 +262,36 @@ def da_step(seg_sd, d_sd, kind, images, labels, images_t, opt_seg, opt_d, lambda
     return float(loss), float(loss_adv_g), float(loss_d_src), float(loss_d_tgt)
 
 
+def da_step_nni(seg_sd, d_sd, kind, images, labels, images_t, opt_seg, opt_d, lambda_adv=0.001):
+    """One iteration of train_nni.py's inner loop (train_nni.py:105-163), fp32, no AMP: the
+    adversarial term and the discriminator see softmax(out32) instead of softmax(out), gradients of
+    both passes accumulate and each optimizer steps ONCE at the end.
+    Returns (loss_seg, loss_adv_for_G * lambda, loss_D_source, loss_D_target) as floats."""
+    d_params = [v for v in d_sd.values() if v.is_floating_point() and v.requires_grad]
+    for p in d_params:  # train_nni.py:108-109
+        p.requires_grad_(False)
+    opt_seg.zero_grad()
+    opt_d.zero_grad()
+    loss, (_, _, out32) = supervised_loss(seg_sd, images, labels, True)  # train_nni.py:118-124
+    loss.backward()
+    _, _, out32_t = bisenet_forward(seg_sd, images_t, True)  # train_nni.py:131-136
+    d_out = discriminator_forward(kind, d_sd, F.softmax(out32_t, dim=1))
+    loss_d1 = bce_with_logits_const(d_out, 0.0) * lambda_adv
+    loss_d1.backward()
+    for p in d_params:  # train_nni.py:141-142
+        p.requires_grad_(True)
+    out32, out32_t = out32.detach(), out32_t.detach()
+    d_out = discriminator_forward(kind, d_sd, F.softmax(out32, dim=1))
+    loss_d_src = bce_with_logits_const(d_out, 0.0)  # train_nni.py:147-151
+    loss_d_src.backward()
+    d_out = discriminator_forward(kind, d_sd, F.softmax(out32_t, dim=1))
+    loss_d_tgt = bce_with_logits_const(d_out, 1.0)  # train_nni.py:153-157
+    loss_d_tgt.backward()
+    opt_seg.step()  # train_nni.py:159-161
+    opt_d.step()
+    return float(loss), float(loss_d1), float(loss_d_src), float(loss_d_tgt)
+
+
 # --------------------------------------------------------------------------- synthetic weights
 def _kaiming(shape, gen, a=0.0, mode="fan_in"):
     fan_in = shape[1] * shape[2] * shape[3]

@@ -126,3 +126,29 @@ def test_ctypes_wrappers_match_header_arity():
                 assert len(node.args) - 1 == _lib._arity[name], (fname, name, len(node.args) - 1, _lib._arity[name])
                 seen.add(name)
     assert len(seen) >= 30
+
+
+def test_checkpoint_helpers_round_trip(tmp_path):
+    """train.py:110,118,282-283: seg-net files carry bare keys, discriminator files `module.`-prefixed
+    ones (the shipped GTA5_10_D1.pth); both must load into bare and wrapped modules."""
+    from dasemanticsegmentationaml_b200 import checkpoint as C
+    from dasemanticsegmentationaml_b200.model import DepthWiseSepBNFCDiscriminator
+    torch.manual_seed(3)
+    a, b = DepthWiseSepBNFCDiscriminator(19), DepthWiseSepBNFCDiscriminator(19)
+    path = C.save_state(a, str(tmp_path / "ckpt" / "GTA5_10_D1.pth"), keep_wrapper_prefix=True)
+    saved = torch.load(path)
+    with open(os.path.join(GOLD, "state_dict_layout.json")) as f:
+        shipped = json.load(f)["shipped_D1"]
+    assert [(k, list(v.shape)) for k, v in saved.items()] == [(k, s) for k, s, _ in shipped]
+    assert C.load_state(b, path) == []
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v, w), k
+    # bare keys, wrapped target, partial overlay (BiSeNet.load_weight semantics)
+    wrapped = torch.nn.DataParallel(DepthWiseSepBNFCDiscriminator(19))
+    partial = {k: v for k, v in a.state_dict().items() if k.startswith("conv1_d")}
+    assert partial
+    partial["not.a.key"] = torch.zeros(1)
+    assert C.load_state(wrapped, partial, strict=False) == ["not.a.key"]
+    for k, v in partial.items():
+        if k != "not.a.key":
+            assert torch.equal(wrapped.module.state_dict()[k], v), k

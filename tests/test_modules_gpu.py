@@ -276,6 +276,39 @@ def test_da_step_matches_oracle_losses(cuda_lib, kind):
         assert abs(a - b) < 0.1 * max(1.0, abs(b))
 
 
+def test_nni_da_step_matches_oracle(cuda_lib):
+    """train_nni.py's iteration: adversarial term on out32, accumulated gradients, one step per optimizer."""
+    from dasemanticsegmentationaml_b200 import train as T
+    from dasemanticsegmentationaml_b200.model import BiSeNet, FCDiscriminator
+    sd = O.make_bisenet_state(seed=23)
+    dsd = O.make_discriminator_state("dense", seed=5)
+    m = load_oracle_state(BiSeNet("STDCNet813", 19), sd).to(DEV)
+    d = load_oracle_state(FCDiscriminator(19), dsd).to(DEV)
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    opt_d = torch.optim.Adam(d.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 128, 256, generator=g).to(DEV)
+    xt = torch.randn(2, 3, 128, 256, generator=g).to(DEV)
+    labels = torch.randint(0, 19, (2, 128, 256), generator=g).to(DEV)
+    key = "conv_out32.conv_out.weight"
+    w0 = m.state_dict()[key].clone()
+    got = [float(v) for v in T.train_da_step_nni(m, d, opt, opt_d, x, labels, xt, lambda_adv=0.01)]
+    osd, odsd = to_device(sd, DEV, True), to_device(dsd, DEV, True)
+    o_opt = torch.optim.SGD([v for v in osd.values() if v.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    o_opt_d = torch.optim.Adam([v for v in odsd.values() if v.requires_grad], lr=1e-3, betas=(0.9, 0.99))
+    o0 = osd[key].detach().clone()
+    want = O.da_step_nni(osd, odsd, "dense", x, labels, xt, o_opt, o_opt_d, lambda_adv=0.01)
+    print("nni step losses", got, want)
+    assert all(np.isfinite(got))
+    assert abs(got[0] - want[0]) / want[0] < 3e-2
+    for a, b in zip(got[1:], want[1:]):
+        assert abs(a - b) < 0.1 * max(1.0, abs(b))
+    # the out32 head sees both the CE gradient and the adversarial one: its SGD update must agree
+    c = cosine(m.state_dict()[key] - w0, osd[key].detach() - o0)
+    print("nni step: update cosine of", key, c)
+    assert c > 0.98
+
+
 @pytest.mark.parametrize("fused", [False, True])
 def test_weight_updates_reach_the_packed_filters(cuda_lib, fused):
     """torch's fused optimizers do not bump tensor version counters; the bf16 filter packings must

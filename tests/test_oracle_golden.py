@@ -104,3 +104,25 @@ def test_state_dict_layout_of_oracle_weights():
         ref = [(k, tuple(s)) for k, s, _ in layout["disc_" + kind]]
         got = [(k, tuple(v.shape)) for k, v in O.make_discriminator_state(kind).items()]
         assert got == ref
+
+
+@pytest.mark.parametrize("variant", ["da", "nni"])
+def test_adversarial_step_loops(variant):
+    """oracle.da_step / da_step_nni against the loop bodies of train.py:192-262 / train_nni.py:105-163
+    replayed with the reference's own modules (tests/golden/make_golden_steps.py)."""
+    torch.set_num_threads(8)
+    gold = np.load(os.path.join(GOLD, "reference_steps.npz"))
+    x, xt = torch.from_numpy(gold["x"]), torch.from_numpy(gold["xt"])
+    labels = torch.from_numpy(gold["labels"].astype(np.int64)).squeeze(1)  # train.py:214 squeezes too
+    sd = O.clone_state(O.make_bisenet_state(seed=31), requires_grad=True)
+    dsd = O.clone_state(O.make_discriminator_state("dense", seed=6), requires_grad=True)
+    opt = torch.optim.SGD([v for v in sd.values() if v.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
+    opt_d = torch.optim.Adam([v for v in dsd.values() if v.requires_grad], lr=1e-3, betas=(0.9, 0.99))
+    step = O.da_step if variant == "da" else O.da_step_nni
+    got = step(sd, dsd, "dense", x, labels, xt, opt, opt_d, lambda_adv=0.01)
+    close(np.array(got), gold[variant + "_losses"], rtol=2e-4)
+    for key in gold.files:
+        if key.startswith(variant + ":"):
+            close(sample(sd[key.split(":", 1)[1]], 7), gold[key], rtol=2e-3, atol=2e-6)
+        if key.startswith(variant + "_d:"):
+            close(sample(dsd[key.split(":", 1)[1]], 7), gold[key], rtol=2e-3, atol=2e-6)
