@@ -459,3 +459,28 @@ def cast_f32_bf16(x, y):
 def scale_f32(x, num, den, mul, y):
     call("b200_scale_f32", ptr(x), c_int64(x.numel()), ptr(num), ptr(den), c_float(mul), ptr(y), stream())
     return y
+
+
+# ------------------------------------------------------------------ input pipeline
+def image_resize_normalize(src, xb, xk, yb, yk, lut, dst, max_rows):
+    """uint8 [N, H0, W0, 3] -> fp32 [N, 3, H, W]: Pillow's two-pass bilinear resample + the
+    ToTensor/Normalize table (dataset/cityscapes.py:65,67).  Tables come from ``dataset.ResizeTables``."""
+    n, h0, w0, c = src.shape
+    assert c == 3 and src.dtype == torch.uint8 and src.is_contiguous()
+    _, _, h, w = dst.shape
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.shape[1] == 3
+    call("b200_image_resize_normalize", ptr(src), c_int(n), c_int(h0), c_int(w0), ptr(xb), ptr(xk),
+         c_int(xk.shape[1]), ptr(yb), ptr(yk), c_int(yk.shape[1]), c_int(h), c_int(w), ptr(lut), ptr(dst),
+         c_int(max_rows), stream())
+    return dst
+
+
+def label_resize_remap(src, ix, iy, lut, dst):
+    """uint8 [N, H0, W0] -> uint8 / int64 [N, H, W]: Pillow's NEAREST resize + a 256-entry id remap."""
+    n, h0, w0 = src.shape
+    assert src.dtype == torch.uint8 and src.is_contiguous() and dst.is_contiguous()
+    h, w = dst.shape[-2:]
+    assert dst.dtype in (torch.uint8, torch.int64)
+    call("b200_label_resize_remap", ptr(src), c_int(n), c_int(h0), c_int(w0), ptr(ix), ptr(iy), c_int(h),
+         c_int(w), ptr(lut), ptr(dst), c_int(1 if dst.dtype == torch.int64 else 0), stream())
+    return dst

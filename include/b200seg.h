@@ -220,6 +220,27 @@ int b200_fast_hist(const void* label, int label_bytes, const void* pred, int pre
 int b200_count_equal(const void* label, int label_bytes, const void* pred, int pred_bytes,
                      int64_t count, int64_t* out, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ input pipeline */
+/* pil_loader(path).resize(size, Image.BILINEAR) -> ToTensor() -> Normalize(mean, std)
+ * (dataset/cityscapes.py:65,67 and dataset/GTAV.py:85,87; Pillow Resample.c two-pass 8-bit resample).
+ * src: decoded uint8 RGB [N, H0, W0, 3].  xb / yb: int32 [W or H][2] = (first source index, tap count)
+ * per output column / row; xk / yk: int32 fixed-point (22 fractional bits) coefficients [W][kx] /
+ * [H][ky] (the host restates Pillow's precompute_coeffs in float64).  The horizontal pass rounds to
+ * uint8 before the vertical pass exactly as Pillow does.  lut: float [3][256] = ((v/255) - mean_c) /
+ * std_c in fp32.  dst: fp32 NCHW [N, 3, H, W].  max_rows: the largest number of source rows one band
+ * of 8 output rows touches (sizes the shared-memory staging).  Bit-exact with the reference. */
+int b200_image_resize_normalize(const uint8_t* src, int N, int H0, int W0, const int32_t* xb,
+                                const int32_t* xk, int kx, const int32_t* yb, const int32_t* yk, int ky,
+                                int H, int W, const float* lut, float* dst, int max_rows,
+                                cudaStream_t stream);
+/* Image.open(path).resize(size, Image.NEAREST) -> PILToTensor() [-> GtaV.convert_labels]
+ * (cityscapes.py:66,68; GTAV.py:86,88-89,97-100; Pillow Geometry.c ImagingScaleAffine).
+ * src: uint8 [N, H0, W0]; ix / iy: int32 source column / row per output column / row; lut: uint8[256]
+ * label remap (identity for Cityscapes); dst: uint8 or int64 [N, H, W]. */
+int b200_label_resize_remap(const uint8_t* src, int N, int H0, int W0, const int32_t* ix, const int32_t* iy,
+                            int H, int W, const uint8_t* lut, void* dst, int dst_is_i64,
+                            cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,3 +152,20 @@ def test_checkpoint_helpers_round_trip(tmp_path):
     for k, v in partial.items():
         if k != "not.a.key":
             assert torch.equal(wrapped.module.state_dict()[k], v), k
+
+
+def test_input_tables_match_oracle():
+    """Host side of the input pipeline: the vectorised table builders against the oracle's scalar
+    restatement of Pillow, at the dataset sizes and a few odd ones."""
+    from dasemanticsegmentationaml_b200 import dataset as D
+    from oracle import input_oracle as I
+    for (i, o) in [(96, 48), (97, 50), (50, 100), (1914, 512), (1052, 1024), (2048, 1280), (1024, 720), (33, 33)]:
+        b, k = D.bilinear_tables(i, o)
+        xmin, cnt, kk = I.bilinear_coeffs(i, o)
+        assert np.array_equal(b[:, 0], xmin) and np.array_equal(b[:, 1], cnt) and np.array_equal(k, kk)
+        assert np.array_equal(D.nearest_table(i, o), I.nearest_index(i, o))
+    ref = I.to_tensor_normalize(np.arange(256, dtype=np.uint8)[None, :, None].repeat(3, 2))[:, 0]
+    assert np.array_equal(D.normalize_table().numpy(), ref)
+    lut = D.label_table(D.GTA5_ID_TO_TRAINID).numpy()
+    ids = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(lut, I.convert_labels(ids, {k: v for k, v in D.GTA5_ID_TO_TRAINID.items() if k >= 0}))
