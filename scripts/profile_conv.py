@@ -12,7 +12,10 @@ CASES = [  # n, cin, cout, h, w, r, stride, pad
     (8, 128, 256, 128, 256, 4, 2, 1),   # discriminator conv3
     (8, 128, 64, 64, 128, 3, 1, 1),     # bottleneck tail
     (8, 32, 64, 512, 1024, 4, 2, 1),    # discriminator conv1 (19 -> padded 32 channels)
+    (8, 64, 128, 128, 256, 1, 1, 0),    # block-1 1x1: store/epilogue bound (100 MB in+out)
 ]
+if os.environ.get("CASE"):
+    CASES = [CASES[int(os.environ["CASE"])]]
 reps = int(os.environ.get("REPS", "1"))
 for (n, cin, cout, h, w, r, stride, pad) in CASES:
     x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
@@ -25,7 +28,8 @@ for (n, cin, cout, h, w, r, stride, pad) in CASES:
         K.conv_igemm(x, filt, out, geom, stats=stats)
     dz = torch.randn(n, geom.Hout, geom.Wout, cout, device=dev).to(torch.bfloat16)
     dw = torch.zeros_like(wgt)
-    for _ in range(reps):
-        K.conv_wgrad(dz, x, dw, r, r, stride, pad)
+    if not os.environ.get("NO_WGRAD"):
+        for _ in range(reps):
+            K.conv_wgrad(dz, x, dw, r, r, stride, pad)
 torch.cuda.synchronize()
 print("done")
