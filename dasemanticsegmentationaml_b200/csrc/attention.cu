@@ -54,6 +54,12 @@ pool_sum_kernel(const __nv_bfloat16* __restrict__ x, int ld, int HW, int C, floa
 // ------------------------------------------------------------ tiny dense layers
 constexpr int kMaxBatch = 64;
 
+// These layers move a few KB and are pure latency chains, so each kernel is arranged to keep many
+// independent loads in flight (the first versions walked batch x channel serially and took 10-60 us
+// per launch under ncu): a lane carries the accumulators of kFcNB batch rows at once, loops are
+// unrolled over independent channels, per-row statistics come from shared memory.
+constexpr int kFcNB = 8;
+
 // pre[n][co] = in_scale * sum_ci in[n][ci] * W[co][ci];  optional BatchNorm over the batch
 // (train: batch statistics + running update, eval: running statistics); act 0 none, 1 relu,
 // 3 sigmoid.  One warp per output channel.
@@ -69,11 +75,22 @@ fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin
   const int co = blockIdx.x * 4 + warp;
   if (co >= Co) return;
   const float* wr = W + (int64_t)co * Cin;
-  for (int n = 0; n < N; ++n) {
-    float acc = 0.f;
-    for (int ci = lane; ci < Cin; ci += 32) acc += in[(int64_t)n * Cin + ci] * wr[ci];
-    acc = warp_sum(acc) * in_scale;
-    if (lane == 0) s_y[warp][n] = acc;
+  for (int n0 = 0; n0 < N; n0 += kFcNB) {
+    float acc[kFcNB];
+#pragma unroll
+    for (int j = 0; j < kFcNB; ++j) acc[j] = 0.f;
+#pragma unroll 4
+    for (int ci = lane; ci < Cin; ci += 32) {
+      const float w = __ldg(wr + ci);
+#pragma unroll
+      for (int j = 0; j < kFcNB; ++j)
+        if (n0 + j < N) acc[j] += __ldg(in + (int64_t)(n0 + j) * Cin + ci) * w;
+    }
+#pragma unroll
+    for (int j = 0; j < kFcNB; ++j) {
+      const float t = warp_sum(acc[j]) * in_scale;
+      if (lane == 0 && n0 + j < N) s_y[warp][n0 + j] = t;
+    }
   }
   __syncwarp();
   float mean = 0.f, rstd = 1.f, g = 1.f, b = 0.f;
@@ -122,59 +139,88 @@ fc_small_bwd_a_kernel(const float* __restrict__ dout, const float* __restrict__ 
                       const float* __restrict__ gamma, const float* __restrict__ mean,
                       const float* __restrict__ rstd, int act, float* __restrict__ dpre,
                       float* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float s_g[4][kMaxBatch];
+  __shared__ float s_g[4][kMaxBatch], s_x[4][kMaxBatch];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co = blockIdx.x * 4 + warp;
   if (co >= Co) return;
+  const float mu = has_bn ? mean[co] : 0.f, rs = has_bn ? rstd[co] : 1.f, gm = has_bn ? gamma[co] : 1.f;
+  float sg = 0.f, sgx = 0.f;
   for (int n = lane; n < N; n += 32) {
     const float o = out[(int64_t)n * Co + co];
     float gg = dout[(int64_t)n * Co + co];
     if (act == 1) gg = o > 0.f ? gg : 0.f;
     else if (act == 3) gg *= o * (1.f - o);
+    const float xh = has_bn ? (pre[(int64_t)n * Co + co] - mu) * rs : 0.f;
     s_g[warp][n] = gg;
+    s_x[warp][n] = xh;
+    sg += gg;
+    sgx += gg * xh;
   }
-  __syncwarp();
   if (has_bn) {
-    const float mu = mean[co], rs = rstd[co], gm = gamma[co];
-    float sg = 0.f, sgx = 0.f;
-    for (int n = 0; n < N; ++n) {
-      const float gg = s_g[warp][n];
-      sg += gg;
-      sgx += gg * (pre[(int64_t)n * Co + co] - mu) * rs;
-    }
-    __syncwarp();
+    sg = warp_sum(sg);
+    sgx = warp_sum(sgx);
     for (int n = lane; n < N; n += 32) {
-      const float xh = (pre[(int64_t)n * Co + co] - mu) * rs;
       const float gg = s_g[warp][n];
-      s_g[warp][n] = training ? gm * rs * (gg - sg / N - xh * sgx / N) : gm * rs * gg;
+      s_g[warp][n] = training ? gm * rs * (gg - sg / N - s_x[warp][n] * sgx / N) : gm * rs * gg;
     }
     if (lane == 0) {
       if (dgamma != nullptr) dgamma[co] += sgx;
       if (dbeta != nullptr) dbeta[co] += sg;
     }
-    __syncwarp();
   }
+  __syncwarp();
   for (int n = lane; n < N; n += 32) dpre[(int64_t)n * Co + co] = s_g[warp][n];
   if (dW != nullptr) {
+    float* dwr = dW + (int64_t)co * Cin;
+#pragma unroll 4
     for (int ci = lane; ci < Cin; ci += 32) {
+      const float old = dwr[ci];
       float acc = 0.f;
-      for (int n = 0; n < N; ++n) acc += s_g[warp][n] * in[(int64_t)n * Cin + ci];
-      dW[(int64_t)co * Cin + ci] += acc * in_scale;
+      for (int n0 = 0; n0 < N; n0 += kFcNB) {
+#pragma unroll
+        for (int j = 0; j < kFcNB; ++j)
+          if (n0 + j < N) acc += s_g[warp][n0 + j] * __ldg(in + (int64_t)(n0 + j) * Cin + ci);
+      }
+      dwr[ci] = old + acc * in_scale;
     }
   }
 }
 
-// Backward, part B: din[n][ci] (+)= in_scale * sum_co dpre[n][co] * W[co][ci]
+// Backward, part B: din[n][ci] (+)= in_scale * sum_co dpre[n][co] * W[co][ci].
+// Block = 64 input channels x 4 slices of the output channels; a thread carries kFcNB batch rows.
 __global__ void __launch_bounds__(256)
 fc_small_bwd_b_kernel(const float* __restrict__ dpre, const float* __restrict__ W, float in_scale,
                       int N, int Cin, int Co, float* __restrict__ din, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * Cin) return;
-  const int n = idx / Cin, ci = idx - n * Cin;
-  float acc = 0.f;
-  for (int co = 0; co < Co; ++co) acc += dpre[(int64_t)n * Co + co] * W[(int64_t)co * Cin + ci];
-  acc *= in_scale;
-  din[idx] = accumulate ? din[idx] + acc : acc;
+  __shared__ float s_red[4][kFcNB][64];
+  const int cl = threadIdx.x & 63, cg = threadIdx.x >> 6;
+  const int ci = blockIdx.x * 64 + cl;
+  for (int n0 = 0; n0 < N; n0 += kFcNB) {
+    float acc[kFcNB];
+#pragma unroll
+    for (int j = 0; j < kFcNB; ++j) acc[j] = 0.f;
+    if (ci < Cin) {
+#pragma unroll 4
+      for (int co = cg; co < Co; co += 4) {
+        const float w = __ldg(W + (int64_t)co * Cin + ci);
+#pragma unroll
+        for (int j = 0; j < kFcNB; ++j)
+          if (n0 + j < N) acc[j] += __ldg(dpre + (int64_t)(n0 + j) * Co + co) * w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kFcNB; ++j) s_red[cg][j][cl] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFcNB * 64; i += 256) {
+      const int j = i >> 6, c = i & 63;
+      const int n = n0 + j, cc = blockIdx.x * 64 + c;
+      if (n < N && cc < Cin) {
+        const float v = (s_red[0][j][c] + s_red[1][j][c] + s_red[2][j][c] + s_red[3][j][c]) * in_scale;
+        float* d = din + (int64_t)n * Cin + cc;
+        *d = accumulate ? *d + v : v;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------- broadcast scale/add
@@ -330,7 +376,7 @@ int b200_fc_small_bwd(const float* dout, const float* out, const float* pre, con
   int rc = check_launch("fc_small_bwd_a");
   if (rc) return rc;
   if (din != nullptr) {
-    fc_small_bwd_b_kernel<<<(N * Cin + 255) / 256, 256, 0, stream>>>(dpre_scratch, W, in_scale, N, Cin, Co, din, accumulate_din);
+    fc_small_bwd_b_kernel<<<(Cin + 63) / 64, 256, 0, stream>>>(dpre_scratch, W, in_scale, N, Cin, Co, din, accumulate_din);
     rc = check_launch("fc_small_bwd_b");
   }
   return rc;

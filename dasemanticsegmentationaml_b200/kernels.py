@@ -326,17 +326,13 @@ def dwconv_s2_wgrad(dz, x, k, dw, dbias):
         c_int(k), ptr(dw), ptr(dbias), stream())
 
 
-def stem_fwd(img, w, z, stats):
+def stem_im2col(img, col):
+    """fp32 NCHW image -> bf16 [N, Ho, Wo, 32] unfolded 3x3 stride-2 patches (k = ci*9 + r*3 + s)."""
     n, _, h, wd = img.shape
     assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
-    call("b200_stem_fwd", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(w), ptr(z),
-                              c_int(z.stride(2)), ptr(stats), stream())
-
-
-def stem_wgrad(img, dz, dw):
-    n, _, h, wd = img.shape
-    call("b200_stem_wgrad", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(dz), c_int(dz.stride(2)),
-                                ptr(dw), stream())
+    assert col.shape[3] == 32 and col.stride(3) == 1
+    call("b200_stem_im2col", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(col), c_int(col.stride(2)), stream())
+    return col
 
 
 # ------------------------------------------------------------------ attention

@@ -17,10 +17,11 @@ F32 = torch.float32
 FORCE_REPACK = False
 
 
-def packed_filter(weight, transpose):
+def packed_filter(weight, transpose, shape=None):
     """bf16 GEMM packing of a conv filter, cached ON the parameter object (so it dies with it and a
     recycled device address can never alias a stale packing) and refreshed when the parameter's
-    version counter or storage changes (optimizer steps, load_state_dict, .to())."""
+    version counter or storage changes (optimizer steps, load_state_dict, .to()).  ``shape``
+    reinterprets the filter memory (the stem's [32, 3, 3, 3] as a [32, 27, 1, 1] 1x1 filter)."""
     cache = getattr(weight, "_b200_pack", None)
     if cache is None:
         cache = {}
@@ -28,19 +29,21 @@ def packed_filter(weight, transpose):
             weight._b200_pack = cache
         except AttributeError:
             pass
+    shape = tuple(shape) if shape is not None else tuple(weight.shape)
+    key = (bool(transpose), shape)
     ver, ptr_now = weight._version, weight.data_ptr()
-    hit = cache.get(bool(transpose))
+    hit = cache.get(key)
     if hit is not None and hit[0] == ver and hit[1] == ptr_now and not FORCE_REPACK:
         return hit[2]
+    w = weight.detach().view(shape)
     if hit is not None and hit[2].device == weight.device:
         buf = hit[2]  # repack in place: stable pointer for graphs, no allocator churn
-        cout, cin, r, s = weight.shape
-        w = weight.detach()
+        cout, cin, r, s = shape
         K.call("b200_pack_filter", K.ptr(w), K.ptr(buf), K.c_int(cout), K.c_int(cin), K.c_int(r * s),
                K.c_int(buf.shape[0]), K.c_int(buf.shape[2]), K.c_int(1 if transpose else 0), K.stream())
     else:
-        buf = K.pack_filter(weight, transpose)
-    cache[bool(transpose)] = (ver, ptr_now, buf)
+        buf = K.pack_filter(w, transpose)
+    cache[key] = (ver, ptr_now, buf)
     return buf
 
 
@@ -63,24 +66,24 @@ def refresh_packs(module, force=False):
         if not cache:
             continue
         ver, ptr_now = w._version, w.data_ptr()
-        for tr, (v, pw, buf) in cache.items():
+        for key, (v, pw, buf) in cache.items():
             if v != ver or pw != ptr_now or FORCE_REPACK or force:
-                stale.append((w, tr, buf))
+                stale.append((w, key, buf))
     if not stale:
         return 0
-    key = tuple((w.data_ptr(), tr, buf.data_ptr()) for w, tr, buf in stale)
+    key = tuple((w.data_ptr(), k, buf.data_ptr()) for w, k, buf in stale)
     tab = getattr(module, "_b200_pack_table", None)
     if tab is None or tab[0] != key:
         rows = []
-        for w, tr, buf in stale:
-            cout, cin, r, s = w.shape
+        for w, (tr, shape), buf in stale:
+            cout, cin, r, s = shape
             rows.append([w.data_ptr(), buf.data_ptr(), cout, cin, r * s, buf.shape[0], buf.shape[2], 1 if tr else 0])
         dev = torch.tensor(rows, dtype=torch.int64).to(stale[0][0].device)
         tab = (key, dev)
         object.__setattr__(module, "_b200_pack_table", tab)
     K.call("b200_pack_filters_batched", K.ptr(tab[1]), K.c_int(len(stale)), K.stream())
-    for w, tr, buf in stale:
-        w._b200_pack[tr] = (w._version, w.data_ptr(), buf)
+    for w, k, buf in stale:
+        w._b200_pack[k] = (w._version, w.data_ptr(), buf)
     return len(stale)
 
 
@@ -170,7 +173,7 @@ def bn_act_bwd(ctx, dy1, dy2=None):
 
 # --------------------------------------------------------------------------- dense conv (+BN+act)
 class ConvCtx:
-    __slots__ = ("x", "weight", "stride", "pad", "bn", "a", "act", "slope", "stem_img")
+    __slots__ = ("x", "weight", "stride", "pad", "bn", "a", "act", "slope", "stem_col")
 
 
 def conv_raw_fwd(x, weight, stride, pad, stats=None, bias=None, act=K.ACT_NONE, slope=0.0, out=None,
@@ -210,14 +213,17 @@ def conv_bn_act_fwd(x, weight, bn, stride, pad, training, act=K.ACT_RELU, slope=
     cout = weight.shape[0]
     stats = zeros_f32((2, cout), weight.device) if training else None
     ctx = ConvCtx()
-    ctx.stem_img = None
+    ctx.stem_col = None
     if x.dim() == 4 and x.dtype == F32 and x.shape[1] == 3 and weight.shape[1] == 3:
-        # stem: 3x3 stride 2 directly from the NCHW image
+        # stem: unfold the NCHW image once (bf16, 32 values per output pixel), then a K = 32 1x1 GEMM
         assert weight.shape[2] == 3 and stride == 2 and pad == 1 and cout == 32
         n, _, h, w = x.shape
-        z = empty_act(n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cout, x.device)
-        K.stem_fwd(x, weight.detach(), z, stats)
-        ctx.stem_img = x
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        col = K.stem_im2col(x, empty_act(n, ho, wo, 32, x.device))
+        z = empty_act(n, ho, wo, cout, x.device)
+        K.conv_igemm(col, packed_filter(weight, False, (cout, 27, 1, 1)), z, K.fwd_geometry(ho, wo, 1, 1, 1, 0),
+                     stats=stats, k_real=27, n_real=cout)
+        ctx.stem_col = col
     else:
         assert cout % 16 == 0, "BatchNorm'd convs have a multiple of 16 output channels"
         z = conv_raw_fwd(x, weight, stride, pad, stats=stats)
@@ -230,9 +236,9 @@ def conv_bn_act_fwd(x, weight, bn, stride, pad, training, act=K.ACT_RELU, slope=
 def conv_bn_act_bwd(ctx, dy1, dy2=None, need_dx=True):
     """-> (dx or None, dW, dgamma, dbeta)"""
     dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy1, dy2)
-    if ctx.stem_img is not None:
+    if ctx.stem_col is not None:
         dw = zeros_f32(ctx.weight.shape, dz.device)
-        K.stem_wgrad(ctx.stem_img, dz, dw)
+        K.conv_wgrad(dz, ctx.stem_col[..., :27], dw.view(dw.shape[0], 27, 1, 1), 1, 1, 1, 0)
         return None, dw, dgamma, dbeta
     dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad)
     dx = None

@@ -82,12 +82,12 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
                     const void* x, int x_ld, int x_coff, int Cin, int Hin, int Win, int n_taps,
                     const int* taps, int RS, int in_stride, float* dw, int tune, cudaStream_t stream);
 
-/* Stem ConvX(3, 32, 3, 2) (stdcnet.py:171) straight from the fp32 NCHW image: z = conv (bf16 NHWC,
- * raw, pre-BatchNorm) + BatchNorm statistics; and its filter gradient. */
-int b200_stem_fwd(const float* img, int N, int H, int W, const float* w, void* z, int z_ld,
-                  float* stats, cudaStream_t stream);
-int b200_stem_wgrad(const float* img, int N, int H, int W, const void* dz, int dz_ld, float* dw,
-                    cudaStream_t stream);
+/* Stem ConvX(3, 32, 3, 2) (stdcnet.py:171, 6-15): K = 27 is too thin for a tap-by-tap implicit GEMM,
+ * so the fp32 NCHW image is unfolded ONCE into bf16 rows col[n, ho, wo, k], k = ci*9 + r*3 + s
+ * (k = 27..31 zero, 64-byte pixels), which fuses the layout and precision conversion; forward and
+ * filter gradient are then 1x1 launches of b200_conv_igemm / b200_conv_wgrad on `col` against the
+ * filter viewed as [32, 27, 1, 1] (same memory as [32, 3, 3, 3]). */
+int b200_stem_im2col(const float* img, int N, int H, int W, void* col, int col_ld, cudaStream_t stream);
 
 /* ------------------------------------------------ BatchNorm / activation passes */
 /* nn.BatchNorm2d (+ ReLU / LeakyReLU) of ConvX (stdcnet.py:10-14), ConvBNReLU (model_stages.py:21-29),
