@@ -62,7 +62,7 @@ constexpr int kFcNB = 8;
 
 // pre[n][co] = in_scale * sum_ci in[n][ci] * W[co][ci];  optional BatchNorm over the batch
 // (train: batch statistics + running update, eval: running statistics); act 0 none, 1 relu,
-// 3 sigmoid.  One warp per output channel.
+// 3 sigmoid.  One CTA per output channel (4 warps split the reduction over the input channels).
 __global__ void __launch_bounds__(128)
 fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin, int Co,
                     const float* __restrict__ W, int has_bn, const float* __restrict__ gamma,
@@ -70,17 +70,17 @@ fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin
                     float* __restrict__ running_var, float momentum, float eps, int training,
                     int act, float* __restrict__ pre, float* __restrict__ out,
                     float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  __shared__ float s_y[4][kMaxBatch];
+  __shared__ float s_part[4][kMaxBatch];
+  __shared__ float s_y[1][kMaxBatch];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co = blockIdx.x * 4 + warp;
-  if (co >= Co) return;
+  const int co = blockIdx.x;       // one CTA per output channel; its 4 warps split the input channels
   const float* wr = W + (int64_t)co * Cin;
   for (int n0 = 0; n0 < N; n0 += kFcNB) {
     float acc[kFcNB];
 #pragma unroll
     for (int j = 0; j < kFcNB; ++j) acc[j] = 0.f;
 #pragma unroll 4
-    for (int ci = lane; ci < Cin; ci += 32) {
+    for (int ci = threadIdx.x; ci < Cin; ci += 128) {
       const float w = __ldg(wr + ci);
 #pragma unroll
       for (int j = 0; j < kFcNB; ++j)
@@ -88,10 +88,14 @@ fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin
     }
 #pragma unroll
     for (int j = 0; j < kFcNB; ++j) {
-      const float t = warp_sum(acc[j]) * in_scale;
-      if (lane == 0 && n0 + j < N) s_y[warp][n0 + j] = t;
+      const float t = warp_sum(acc[j]);
+      if (lane == 0 && n0 + j < N) s_part[warp][n0 + j] = t;
     }
   }
+  __syncthreads();
+  if (warp != 0) return;
+  for (int n = lane; n < N; n += 32)
+    s_y[0][n] = (s_part[0][n] + s_part[1][n] + s_part[2][n] + s_part[3][n]) * in_scale;
   __syncwarp();
   float mean = 0.f, rstd = 1.f, g = 1.f, b = 0.f;
   if (has_bn) {
@@ -99,10 +103,10 @@ fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin
     b = beta[co];
     if (training) {
       float s1 = 0.f, s2 = 0.f;
-      for (int n = 0; n < N; ++n) s1 += s_y[warp][n];
+      for (int n = 0; n < N; ++n) s1 += s_y[0][n];
       mean = s1 / N;
       for (int n = 0; n < N; ++n) {
-        const float d = s_y[warp][n] - mean;
+        const float d = s_y[0][n] - mean;
         s2 += d * d;
       }
       const float var = s2 / N;
@@ -121,7 +125,7 @@ fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin
     }
   }
   for (int n = lane; n < N; n += 32) {
-    const float y = s_y[warp][n];
+    const float y = s_y[0][n];
     float t = has_bn ? (y - mean) * rstd * g + b : y;
     if (act == 1) t = fmaxf(t, 0.f);
     else if (act == 3) t = 1.f / (1.f + __expf(-t));
@@ -130,8 +134,9 @@ fc_small_fwd_kernel(const float* __restrict__ in, float in_scale, int N, int Cin
   }
 }
 
-// Backward, part A (one warp per output channel): activation + BatchNorm backward over the batch,
-// dgamma / dbeta, dpre[n][co], and dW[co][ci] += in_scale * sum_n dpre[n][co] * in[n][ci].
+// Backward, part A (one CTA per output channel): activation + BatchNorm backward over the batch,
+// dgamma / dbeta, dpre[n][co], and dW[co][ci] += in_scale * sum_n dpre[n][co] * in[n][ci].  Every warp
+// derives the (tiny) per-row gradients itself; the four warps then split the input channels of dW.
 __global__ void __launch_bounds__(128)
 fc_small_bwd_a_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                       const float* __restrict__ pre, const float* __restrict__ in, float in_scale,
@@ -141,8 +146,7 @@ fc_small_bwd_a_kernel(const float* __restrict__ dout, const float* __restrict__ 
                       float* __restrict__ dW, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float s_g[4][kMaxBatch], s_x[4][kMaxBatch];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co = blockIdx.x * 4 + warp;
-  if (co >= Co) return;
+  const int co = blockIdx.x;
   const float mu = has_bn ? mean[co] : 0.f, rs = has_bn ? rstd[co] : 1.f, gm = has_bn ? gamma[co] : 1.f;
   float sg = 0.f, sgx = 0.f;
   for (int n = lane; n < N; n += 32) {
@@ -163,17 +167,18 @@ fc_small_bwd_a_kernel(const float* __restrict__ dout, const float* __restrict__ 
       const float gg = s_g[warp][n];
       s_g[warp][n] = training ? gm * rs * (gg - sg / N - s_x[warp][n] * sgx / N) : gm * rs * gg;
     }
-    if (lane == 0) {
+    if (warp == 0 && lane == 0) {
       if (dgamma != nullptr) dgamma[co] += sgx;
       if (dbeta != nullptr) dbeta[co] += sg;
     }
   }
   __syncwarp();
-  for (int n = lane; n < N; n += 32) dpre[(int64_t)n * Co + co] = s_g[warp][n];
+  if (warp == 0)
+    for (int n = lane; n < N; n += 32) dpre[(int64_t)n * Co + co] = s_g[0][n];
   if (dW != nullptr) {
     float* dwr = dW + (int64_t)co * Cin;
 #pragma unroll 4
-    for (int ci = lane; ci < Cin; ci += 32) {
+    for (int ci = threadIdx.x; ci < Cin; ci += 128) {
       const float old = dwr[ci];
       float acc = 0.f;
       for (int n0 = 0; n0 < N; n0 += kFcNB) {
@@ -232,15 +237,15 @@ scale_add_bcast_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int Hs, in
                        float v_scale, const __nv_bfloat16* __restrict__ t, int t_ld,
                        __nv_bfloat16* __restrict__ out, int out_ld, int N, int Ho, int Wo, int C) {
   const int groups = C >> 3;
-  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  const uint32_t total = (uint32_t)N * Ho * Wo * groups;   // host-checked < 2^31: 32-bit index math
   const float sh = (float)Hs / (float)Ho, sw = (float)Ws / (float)Wo;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g = (int)(i % groups);
-    const int64_t p = i / groups;
+    const uint32_t p = i / groups;
     const int wo = (int)(p % Wo);
-    const int ho = (int)((p / Wo) % Ho);
-    const int n = (int)(p / ((int64_t)Wo * Ho));
+    const uint32_t t2 = p / Wo;
+    const int ho = (int)(t2 % Ho);
+    const int n = (int)(t2 / Ho);
     const int hs = (Hs == Ho) ? ho : nearest_src(ho, sh, Hs);
     const int ws = (Ws == Wo) ? wo : nearest_src(wo, sw, Ws);
     const int64_t q = ((int64_t)n * Hs + hs) * Ws + ws;
@@ -259,7 +264,7 @@ scale_add_bcast_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int Hs, in
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += y[j];
     }
-    st8a(out + p * out_ld + g * 8, o);
+    st8a(out + (int64_t)p * out_ld + g * 8, o);
   }
 }
 
@@ -358,7 +363,7 @@ int b200_fc_small_fwd(const float* in, float in_scale, int N, int Cin, int Co, c
                       float* running_var, float momentum, float eps, int training, int act,
                       float* pre, float* out, float* mean_out, float* rstd_out, cudaStream_t stream) {
   if (N > kMaxBatch) return set_error(B200_EINVAL, "fc_small: batch %d > %d", N, kMaxBatch);
-  fc_small_fwd_kernel<<<(Co + 3) / 4, 128, 0, stream>>>(in, in_scale, N, Cin, Co, W, has_bn, gamma, beta,
+  fc_small_fwd_kernel<<<Co, 128, 0, stream>>>(in, in_scale, N, Cin, Co, W, has_bn, gamma, beta,
                                                         running_mean, running_var, momentum, eps,
                                                         training, act, pre, out, mean_out, rstd_out);
   return check_launch("fc_small_fwd");
@@ -370,7 +375,7 @@ int b200_fc_small_bwd(const float* dout, const float* out, const float* pre, con
                       int act, float* dpre_scratch, float* dW, float* dgamma, float* dbeta,
                       float* din, int accumulate_din, cudaStream_t stream) {
   if (N > kMaxBatch) return set_error(B200_EINVAL, "fc_small: batch %d > %d", N, kMaxBatch);
-  fc_small_bwd_a_kernel<<<(Co + 3) / 4, 128, 0, stream>>>(dout, out, pre, in, in_scale, N, Cin, Co, has_bn,
+  fc_small_bwd_a_kernel<<<Co, 128, 0, stream>>>(dout, out, pre, in, in_scale, N, Cin, Co, has_bn,
                                                           training, gamma, mean, rstd, act,
                                                           dpre_scratch, dW, dgamma, dbeta);
   int rc = check_launch("fc_small_bwd_a");
@@ -387,6 +392,7 @@ int b200_scale_add_bcast(const void* a, int a_ld, int Hs, int Ws, const float* s
                          int out_ld, int N, int Ho, int Wo, int C, cudaStream_t stream) {
   if (C % 8) return set_error(B200_EINVAL, "scale_add_bcast: C=%d must be a multiple of 8", C);
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  if (total >= (1ll << 31)) return set_error(B200_EINVAL, "scale_add_bcast: tensor too large");
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;

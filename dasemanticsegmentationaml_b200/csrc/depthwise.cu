@@ -21,15 +21,33 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
                                             pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
+__device__ __forceinline__ void up8(const uint4& u, float (&v)[8]) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+// 16-byte load that yields zeros when `ok` is false (padding / ragged edges) without a branch
+// around the load, so that all the loads of a thread can be in flight together.
+__device__ __forceinline__ uint4 ldz(const __nv_bfloat16* p, bool ok) {
+  return ok ? __ldg(reinterpret_cast<const uint4*>(p)) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void fma8(float (&acc)[8], const float (&v)[8], const float* wrow) {
+  const float4 wa = *reinterpret_cast<const float4*>(wrow);
+  const float4 wb = *reinterpret_cast<const float4*>(wrow + 4);
+  acc[0] += v[0] * wa.x; acc[1] += v[1] * wa.y; acc[2] += v[2] * wa.z; acc[3] += v[3] * wa.w;
+  acc[4] += v[4] * wb.x; acc[5] += v[5] * wb.y; acc[6] += v[6] * wb.z; acc[7] += v[7] * wb.w;
+}
+
 // All three kernels keep the filter transposed in shared memory ([tap][C] fp32, float4 reads) so
-// that a thread's registers hold only its accumulators (the first version kept 16 taps x 8
-// channels in registers: 254 registers, one block per SM, latency-bound at 0.3 TB/s).
+// that a thread's registers hold only its accumulators, and they are written for memory-level
+// parallelism: every 16-byte load a thread needs for one work item is issued before the first
+// dependent FMA (the first versions had the loads inside the bounds-check branches and ran at
+// 0.17-0.28 of the HBM roofline inside the step's graph).
 
 // Forward.  w: fp32 [C][K*K] (PyTorch [C,1,K,K]).  Writes z = dwconv(x) (+bias, +act) and, when
 // `pool` is given, pool = avg_pool2d(x, 3, 2, 1) (only with K == 3).  stats (optional): [2][C]
 // sum / sum-of-squares of the bf16-rounded z.
 template <int K>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 2)
 dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H, int W, int C,
                      const float* __restrict__ w, const float* __restrict__ bias,
                      __nv_bfloat16* __restrict__ z, int z_ld, __nv_bfloat16* __restrict__ pool,
@@ -40,9 +58,10 @@ dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H
   const int groups = C >> 3;
   const int py = blockDim.x / groups;
   const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+#pragma unroll 4
   for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
     const int c = i / (K * K), t = i - c * (K * K);
-    s_w[t * C + c] = w[i];
+    s_w[t * C + c] = __ldg(w + i);
   }
   if (stats != nullptr)
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
@@ -58,31 +77,32 @@ dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H
       const int t2 = p / Wo;
       const int ho = t2 % Ho;
       const int n = t2 / Ho;
+      const __nv_bfloat16* img = x + (size_t)n * H * W * x_ld + g * 8;
+      uint4 raw[K * K];
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const int h = ho * 2 + r - 1;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+          const int ww = wo * 2 + s - 1;
+          const bool ok = h >= 0 && h < H && ww >= 0 && ww < W;
+          raw[r * K + s] = ldz(img + ((size_t)(ok ? h : 0) * W + (ok ? ww : 0)) * x_ld, ok);
+        }
+      }
       float acc[8], pl[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[j] = bs[j];
         pl[j] = 0.f;
       }
-      const __nv_bfloat16* img = x + (size_t)n * H * W * x_ld + g * 8;
 #pragma unroll
-      for (int r = 0; r < K; ++r) {
-        const int h = ho * 2 + r - 1;
-        if (h < 0 || h >= H) continue;
+      for (int t = 0; t < K * K; ++t) {
+        float v[8];
+        up8(raw[t], v);
+        fma8(acc, v, s_w + t * C + g * 8);
+        if (pool != nullptr) {
 #pragma unroll
-        for (int s = 0; s < K; ++s) {
-          const int ww = wo * 2 + s - 1;
-          if (ww < 0 || ww >= W) continue;
-          float v[8];
-          ld8(img + ((size_t)h * W + ww) * x_ld, v);
-          const float4 wa = *reinterpret_cast<const float4*>(s_w + (r * K + s) * C + g * 8);
-          const float4 wb = *reinterpret_cast<const float4*>(s_w + (r * K + s) * C + g * 8 + 4);
-          acc[0] += v[0] * wa.x; acc[1] += v[1] * wa.y; acc[2] += v[2] * wa.z; acc[3] += v[3] * wa.w;
-          acc[4] += v[4] * wb.x; acc[5] += v[5] * wb.y; acc[6] += v[6] * wb.z; acc[7] += v[7] * wb.w;
-          if (pool != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pl[j] += v[j];
-          }
+          for (int j = 0; j < 8; ++j) pl[j] += v[j];
         }
       }
       if (act == 2) {
@@ -106,7 +126,19 @@ dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H
     }
   }
   if (stats != nullptr) {
-    if (ty < py) {
+    // lanes that hold the same channel group (groups < 32) are summed by shuffles first, so the
+    // shared-memory atomics see one lane per group and warp
+    const bool fold = groups < 32 && (32 % groups) == 0 && (blockDim.x % 32) == 0;
+    if (fold) {
+      for (int off = groups; off < 32; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+        }
+      }
+    }
+    if (ty < py && (!fold || (threadIdx.x & 31) < groups)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&s_acc[g * 8 + j], s1[j]);
@@ -120,65 +152,95 @@ dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H
 
 // Data gradient: dx[n,h,w,c] = sum_{r,s} dz[n,(h+1-r)/2,(w+1-s)/2,c] * w[c,r,s]
 //                              (+ sum over the 3x3/s2 pooling windows covering (h,w) of dpool / 9)
+// One work item = the 2x2 block of dx pixels (2i+ph, 2j+pw): which filter tap links an output
+// pixel to dz[i+di, j+dj] depends only on the parities (r = ph + 1 - 2 di, s = pw + 1 - 2 dj), so the
+// control flow is uniform, the (2 or 3)^2 dz pixels the block needs are loaded up front and every
+// tap test below is resolved at compile time.
 template <int K>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 2)
 dwconv_s2_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld,
                        const __nv_bfloat16* __restrict__ dpool, int dpool_ld, int N, int H, int W,
                        int C, int Ho, int Wo, const float* __restrict__ w,
                        __nv_bfloat16* __restrict__ dx, int dx_ld) {
   extern __shared__ float s_w[];  // [K*K][C]
+  constexpr int DLO = (K == 4) ? -1 : 0;   // dz offsets di, dj in [DLO, 1]
+  constexpr int ND = 2 - DLO;
   const int groups = C >> 3;
   const int py = blockDim.x / groups;
   const int g = threadIdx.x % groups, ty = threadIdx.x / groups;
+#pragma unroll 4
   for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
     const int c = i / (K * K), t = i - c * (K * K);
-    s_w[t * C + c] = w[i];
+    s_w[t * C + c] = __ldg(w + i);
   }
   __syncthreads();
   if (ty >= py) return;
-  const int npix = N * H * W;
-  for (int p = blockIdx.x * py + ty; p < npix; p += gridDim.x * py) {
-    const int ww = p % W;
-    const int t2 = p / W;
-    const int h = t2 % H;
-    const int n = t2 / H;
-    float acc[8] = {0};
+  const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
+  const int nblk = N * Hb * Wb;
+  for (int p = blockIdx.x * py + ty; p < nblk; p += gridDim.x * py) {
+    const int j = p % Wb;
+    const int t2 = p / Wb;
+    const int i = t2 % Hb;
+    const int n = t2 / Hb;
+    uint4 rz[ND][ND], rp[ND][ND];
 #pragma unroll
-    for (int r = 0; r < K; ++r) {
-      const int hr = h + 1 - r;
-      if (hr < 0 || (hr & 1)) continue;
-      const int ho = hr >> 1;
-      if (ho >= Ho) continue;
+    for (int a = 0; a < ND; ++a) {
 #pragma unroll
-      for (int s = 0; s < K; ++s) {
-        const int wr = ww + 1 - s;
-        if (wr < 0 || (wr & 1)) continue;
-        const int wo = wr >> 1;
-        if (wo >= Wo) continue;
-        const size_t q = ((size_t)n * Ho + ho) * Wo + wo;
-        float v[8];
-        ld8(dz + q * dz_ld + g * 8, v);
-        const float4 wa = *reinterpret_cast<const float4*>(s_w + (r * K + s) * C + g * 8);
-        const float4 wb = *reinterpret_cast<const float4*>(s_w + (r * K + s) * C + g * 8 + 4);
-        acc[0] += v[0] * wa.x; acc[1] += v[1] * wa.y; acc[2] += v[2] * wa.z; acc[3] += v[3] * wa.w;
-        acc[4] += v[4] * wb.x; acc[5] += v[5] * wb.y; acc[6] += v[6] * wb.z; acc[7] += v[7] * wb.w;
-        if (dpool != nullptr) {
-          float u[8];
-          ld8(dpool + q * dpool_ld + g * 8, u);
+      for (int b = 0; b < ND; ++b) {
+        const int ho = i + DLO + a, wo = j + DLO + b;
+        const bool ok = ho >= 0 && ho < Ho && wo >= 0 && wo < Wo;
+        const size_t q = ((size_t)n * Ho + (ok ? ho : 0)) * Wo + (ok ? wo : 0);
+        rz[a][b] = ldz(dz + q * dz_ld + g * 8, ok);
+        if (dpool != nullptr) rp[a][b] = ldz(dpool + q * dpool_ld + g * 8, ok);
+      }
+    }
+    float acc[2][2][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += u[j] * (1.f / 9.f);
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[ph][pw][c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+#pragma unroll
+      for (int b = 0; b < ND; ++b) {
+        float v[8], u[8];
+        up8(rz[a][b], v);
+        if (dpool != nullptr) up8(rp[a][b], u);
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const int r = ph + 1 - 2 * (DLO + a);
+          if (r < 0 || r >= K) continue;
+#pragma unroll
+          for (int pw = 0; pw < 2; ++pw) {
+            const int s = pw + 1 - 2 * (DLO + b);
+            if (s < 0 || s >= K) continue;
+            fma8(acc[ph][pw], v, s_w + (r * K + s) * C + g * 8);
+            if (dpool != nullptr) {   // the pooling window is the 3x3 tap set with weight 1/9 (K == 3 only)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[ph][pw][c] += u[c] * (1.f / 9.f);
+            }
+          }
         }
       }
     }
-    st8(dx + (size_t)p * dx_ld + g * 8, acc);
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        const int h = 2 * i + ph, ww = 2 * j + pw;
+        if (h < H && ww < W) st8(dx + (((size_t)n * H + h) * W + ww) * dx_ld + g * 8, acc[ph][pw]);
+      }
+    }
   }
 }
 
 // Filter / bias gradient: dw[c][r][s] += sum_pixels dz[.,c] * x[.*2 + tap, c]; dbias[c] += sum dz.
 // A thread owns (channel group, filter row r): K accumulators x 8 channels; the K threads of a
-// pixel share the dz load through L1.
+// pixel share the dz load through L1.  Two pixels per iteration, all 2 (K + 1) loads issued first.
 template <int K>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 dwconv_s2_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld,
                        const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H, int W, int C,
                        int Ho, int Wo, float* __restrict__ dw, float* __restrict__ dbias) {
@@ -189,6 +251,7 @@ dwconv_s2_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld,
   const int slot = threadIdx.x % slots, ty = threadIdx.x / slots;
   const int g = slot % groups, r = slot / groups;
   constexpr int KK1 = K * K + 1;
+  constexpr int PP = 2;
   for (int i = threadIdx.x; i < C * KK1; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   float acc[K][8];
@@ -199,27 +262,42 @@ dwconv_s2_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, int dz_ld,
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   const int npix = N * Ho * Wo;
   if (ty < py) {
-    for (int p = blockIdx.x * py + ty; p < npix; p += gridDim.x * py) {
-      const int wo = p % Wo;
-      const int t2 = p / Wo;
-      const int ho = t2 % Ho;
-      const int n = t2 / Ho;
-      float d[8];
-      ld8(dz + (size_t)p * dz_ld + g * 8, d);
-      if (r == 0) {
+    for (int p0 = (blockIdx.x * py + ty) * PP; p0 < npix; p0 += gridDim.x * py * PP) {
+      uint4 rd[PP], rx[PP][K];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ab[j] += d[j];
+      for (int u = 0; u < PP; ++u) {
+        const int p = p0 + u;
+        const bool live = p < npix;
+        const int pc = live ? p : 0;
+        const int wo = pc % Wo;
+        const int t2 = pc / Wo;
+        const int ho = t2 % Ho;
+        const int n = t2 / Ho;
+        rd[u] = ldz(dz + (size_t)pc * dz_ld + g * 8, live);
+        const int h = ho * 2 + r - 1;
+        const bool hok = live && h >= 0 && h < H;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+          const int ww = wo * 2 + s - 1;
+          const bool ok = hok && ww >= 0 && ww < W;
+          rx[u][s] = ldz(x + (((size_t)n * H + (ok ? h : 0)) * W + (ok ? ww : 0)) * x_ld + g * 8, ok);
+        }
       }
-      const int h = ho * 2 + r - 1;
-      if (h < 0 || h >= H) continue;
 #pragma unroll
-      for (int s = 0; s < K; ++s) {
-        const int ww = wo * 2 + s - 1;
-        if (ww < 0 || ww >= W) continue;
-        float v[8];
-        ld8(x + (((size_t)n * H + h) * W + ww) * x_ld + g * 8, v);
+      for (int u = 0; u < PP; ++u) {
+        float d[8];
+        up8(rd[u], d);
+        if (r == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[s][j] += d[j] * v[j];
+          for (int j = 0; j < 8; ++j) ab[j] += d[j];
+        }
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+          float v[8];
+          up8(rx[u][s], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[s][j] += d[j] * v[j];
+        }
       }
     }
 #pragma unroll
@@ -269,7 +347,7 @@ int b200_dwconv_s2_fwd(const void* x, int x_ld, int N, int H, int W, int C, int 
   if ((int64_t)N * H * W >= (1ll << 31)) return set_error(B200_EINVAL, "dwconv: tensor too large");
   const int threads = threads_for(C);
   const int py = threads / (C / 8);
-  const int grid = grid_for((int64_t)N * Ho * Wo, py * 4, 148 * 16);
+  const int grid = grid_for((int64_t)N * Ho * Wo, py * 2, 148 * 2);   // resident CTAs loop: few end-of-CTA reductions
   const size_t smem = (size_t)(K * K + 2) * C * sizeof(float);
   static int optin = 0;
   if (!optin) {
@@ -300,7 +378,7 @@ int b200_dwconv_s2_dgrad(const void* dz, int dz_ld, const void* dpool, int dpool
   const int Ho = (H + 2 - K) / 2 + 1, Wo = (W + 2 - K) / 2 + 1;
   const int threads = threads_for(C);
   const int py = threads / (C / 8);
-  const int grid = grid_for((int64_t)N * H * W, py * 4, 148 * 16);
+  const int grid = grid_for((int64_t)N * ((H + 1) / 2) * ((W + 1) / 2), py * 2, 148 * 16);
   const size_t smem = (size_t)K * K * C * sizeof(float);
   if (smem > 48 * 1024) {
     static int optin = 0;
@@ -331,7 +409,7 @@ int b200_dwconv_s2_wgrad(const void* dz, int dz_ld, const void* x, int x_ld, int
   if (threads == 0) threads = slots;   // C = 1024, K = 4: 512 threads
   if (threads > 1024) return set_error(B200_EINVAL, "dwconv wgrad: C=%d too wide", C);
   const int py = threads / slots;
-  const int grid = grid_for((int64_t)N * Ho * Wo, py * 16, 148 * 4);
+  const int grid = grid_for((int64_t)N * Ho * Wo, py * 16, 148 * 2);
   const size_t smem = (size_t)C * (K * K + 1) * sizeof(float);
   if (smem > 48 * 1024) {
     static int optin = 0;

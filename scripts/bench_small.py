@@ -1,0 +1,120 @@
+"""GPU time of the small (non-tensor-core) kernels at the layer shapes of the DA step.
+
+Each kernel is captured `REPS` times into a CUDA graph and the graph is replayed: what is measured
+is the kernel inside a graph (no host launch overhead, warm instruction cache), which is how the
+train step runs it.  Tensors of the big shapes exceed L2 only for the first layers; the note column
+gives the algorithmic HBM bytes and the fraction of the measured copy bandwidth.
+
+Usage: python scripts/bench_small.py [name-filter ...]
+"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dasemanticsegmentationaml_b200 import build, kernels as K, ops
+from dasemanticsegmentationaml_b200.model import BiSeNet, FCDiscriminator
+
+build.build()
+dev = torch.device("cuda", 0)
+BF, F32 = torch.bfloat16, torch.float32
+PEAK = 6548.2
+REPS = 10
+FILT = sys.argv[1:]
+
+
+def act(n, h, w, c):
+    return torch.randn(n, h, w, c, device=dev).to(BF)
+
+
+def run(name, fn, nbytes=0):
+    if FILT and not any(f in name for f in FILT):
+        return
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(REPS):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / (3 * REPS) * 1e3
+    note = ""
+    if nbytes:
+        note = "%7.1f MB  %6.0f GB/s (%.2f of HBM)" % (nbytes / 1e6, nbytes / us / 1e3, nbytes / us / 1e3 / PEAK)
+    print("%-46s %8.1f us  %s" % (name, us, note), flush=True)
+
+
+N = 8
+# ---- depthwise 3x3 s2 (+ avg-pool skip, BN statistics): CatBottleneck stride-2 blocks
+for c, h, w in ((128, 128, 256), (256, 64, 128), (512, 32, 64)):
+    x = act(N, h, w, c)
+    wt = torch.randn(c, 1, 3, 3, device=dev)
+    z, pool = act(N, h // 2, w // 2, c), act(N, h // 2, w // 2, c)
+    stats = torch.zeros(2, c, device=dev)
+    dz, dpool, dx = act(N, h // 2, w // 2, c), act(N, h // 2, w // 2, c), act(N, h, w, c)
+    dw, e = torch.zeros(c, 1, 3, 3, device=dev), x.numel() * 2
+    run("dwconv_s2_fwd  C%d %dx%d +pool +stats" % (c, h, w), lambda: K.dwconv_s2_fwd(x, 3, wt, None, z, pool, 0, 0.0, stats), e + e // 2)
+    run("dwconv_s2_dgrad C%d %dx%d +dpool" % (c, h, w), lambda: K.dwconv_s2_dgrad(dz, dpool, 3, wt, dx), e + e // 2)
+    run("dwconv_s2_wgrad C%d %dx%d" % (c, h, w), lambda: K.dwconv_s2_wgrad(dz, x, 3, dw, None), e + e // 4)
+# ---- discriminator head (Cout = 1, 4x4 s2) on [8, 32, 64, 512]
+x = act(N, 32, 64, 512)
+wt, b = torch.randn(1, 512, 4, 4, device=dev) * 0.01, torch.zeros(1, device=dev)
+out = torch.empty(N, 16, 32, 1, device=dev)
+dout = torch.randn(N, 16, 32, 1, device=dev)
+dx, dw, db = act(N, 32, 64, 512), torch.zeros(1, 512, 4, 4, device=dev), torch.zeros(1, device=dev)
+e = x.numel() * 2
+run("classifier_fwd   [8,32,64,512]", lambda: K.classifier_fwd(x, wt, b, out), e)
+run("classifier_dgrad [8,32,64,512]", lambda: K.classifier_dgrad(dout, wt, dx), e)
+run("classifier_wgrad [8,32,64,512]", lambda: K.classifier_wgrad(dout, x, dw, db), e)
+# ---- filter packing of whole modules
+seg, disc = BiSeNet("STDCNet813", 19).to(dev), FCDiscriminator(19).to(dev)
+xs = torch.randn(2, 3, 64, 128, device=dev)
+seg.train(), disc.train()
+o = seg.forward_lowres(xs)
+(o[0].float().sum() + o[1].float().sum() + o[2].float().sum()).backward()
+p = torch.softmax(torch.randn(2, 19, 64, 128, device=dev), 1).to(BF).contiguous(memory_format=torch.channels_last)
+p.requires_grad_(True)
+disc(p).float().sum().backward()
+nseg = sum(q.numel() for q in seg.parameters() if q.dim() == 4)
+ndis = sum(q.numel() for q in disc.parameters() if q.dim() == 4)
+run("pack_filters BiSeNet (%.1f M weights)" % (nseg / 1e6), lambda: ops.refresh_packs(seg, force=True), nseg * 8)
+run("pack_filters FCDiscriminator (%.1f M)" % (ndis / 1e6), lambda: ops.refresh_packs(disc, force=True), ndis * 8)
+# ---- attention pieces
+for name, c, h, w in (("feat32", 1024, 16, 32), ("arm32", 128, 16, 32), ("arm16", 128, 32, 64), ("ffm", 256, 64, 128)):
+    x = act(N, h, w, c)
+    out = torch.zeros(N, c, device=dev)
+    run("pool_sum %s C%d %dx%d" % (name, c, h, w), lambda: K.pool_sum(x, out), x.numel() * 2)
+for name, c, hs, ws, ho, wo, has_t in (("arm32 -> x2", 128, 16, 32, 32, 64, False), ("arm16 -> x2", 128, 32, 64, 64, 128, True),
+                                       ("ffm", 256, 64, 128, 64, 128, False)):
+    a, s, v = act(N, hs, ws, c), torch.rand(N, c, device=dev), torch.rand(N, c, device=dev)
+    t = act(N, hs, ws, c) if has_t else None
+    o = act(N, ho, wo, c)
+    run("scale_add_bcast %s C%d" % (name, c), lambda: K.scale_add_bcast(a, s, 0.0, v, 1.0, t, o), (a.numel() + o.numel()) * 2)
+    dsum, dot, vs = act(N, hs, ws, c), torch.zeros(N, c, device=dev), torch.zeros(N, c, device=dev)
+    run("upsum_dot_reduce %s C%d" % (name, c), lambda: K.upsum_dot_reduce(o, a, dsum, hs, ws, dot, vs), (a.numel() * 2 + o.numel()) * 2)
+# ---- tiny dense layers
+for name, cin, co, bn, actn in (("conv_avg 1024->128 BN relu", 1024, 128, True, 1), ("arm 128->128 BN sigmoid", 128, 128, True, 3),
+                                ("ffm 256->64 relu", 256, 64, False, 1), ("ffm 64->256 sigmoid", 64, 256, False, 3)):
+    inp, W = torch.randn(N, cin, device=dev), torch.randn(co, cin, device=dev) * 0.05
+    bnp = (torch.ones(co, device=dev), torch.zeros(co, device=dev), torch.zeros(co, device=dev), torch.ones(co, device=dev)) if bn else None
+    pre, outp = torch.empty(N, co, device=dev), torch.empty(N, co, device=dev)
+    mean, rstd = torch.empty(co, device=dev), torch.empty(co, device=dev)
+    run("fc_small_fwd %s" % name, lambda: K.fc_small_fwd(inp, 1.0, W, bnp, True, actn, pre, outp, mean, rstd))
+    dout, scratch = torch.randn(N, co, device=dev), torch.empty(N, co, device=dev)
+    dW, dg, dbt, din = torch.zeros_like(W), torch.zeros(co, device=dev), torch.zeros(co, device=dev), torch.empty(N, cin, device=dev)
+    run("fc_small_bwd %s" % name, lambda: K.fc_small_bwd(dout, outp, pre, inp, 1.0, W, bn, True, bnp[0] if bn else None, mean, rstd,
+                                                          actn, scratch, dW, dg if bn else None, dbt if bn else None, din))
+# ---- LeakyReLU backward + bias gradient of the dense discriminator
+for c, h, w in ((64, 256, 512), (128, 128, 256), (256, 64, 128), (512, 32, 64)):
+    dy, a, dz, dbias = act(N, h, w, c), act(N, h, w, c), act(N, h, w, c), torch.zeros(c, device=dev)
+    run("act_bwd_bias C%d %dx%d" % (c, h, w), lambda: K.act_bwd_bias(dy, None, a, dz, 2, 0.2, dbias), dy.numel() * 6)
+# ---- stem unfold
+img = torch.randn(N, 3, 512, 1024, device=dev)
+col = act(N, 256, 512, 32)
+run("stem_im2col 512x1024", lambda: K.stem_im2col(img, col), img.numel() * 4 + col.numel() * 2)
