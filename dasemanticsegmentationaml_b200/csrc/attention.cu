@@ -48,7 +48,7 @@ pool_sum_kernel(const __nv_bfloat16* __restrict__ x, int ld, int HW, int C, floa
 #pragma unroll
   for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[g * 8 + j], acc[j]);
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[(int64_t)n * C + i], s_acc[i]);
+  flush_add_v4(out + (int64_t)n * C, s_acc, C, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------ tiny dense layers
@@ -192,20 +192,21 @@ fc_small_bwd_a_kernel(const float* __restrict__ dout, const float* __restrict__ 
 }
 
 // Backward, part B: din[n][ci] (+)= in_scale * sum_co dpre[n][co] * W[co][ci].
-// Block = 64 input channels x 4 slices of the output channels; a thread carries kFcNB batch rows.
+// Block = 16 input channels x 16 slices of the output channels (short dependent chains even for
+// Co = 256); a thread carries kFcNB batch rows; the slices are combined through shared memory.
 __global__ void __launch_bounds__(256)
 fc_small_bwd_b_kernel(const float* __restrict__ dpre, const float* __restrict__ W, float in_scale,
                       int N, int Cin, int Co, float* __restrict__ din, int accumulate) {
-  __shared__ float s_red[4][kFcNB][64];
-  const int cl = threadIdx.x & 63, cg = threadIdx.x >> 6;
-  const int ci = blockIdx.x * 64 + cl;
+  __shared__ float s_red[16][kFcNB][17];
+  const int cl = threadIdx.x & 15, cg = threadIdx.x >> 4;
+  const int ci = blockIdx.x * 16 + cl;
   for (int n0 = 0; n0 < N; n0 += kFcNB) {
     float acc[kFcNB];
 #pragma unroll
     for (int j = 0; j < kFcNB; ++j) acc[j] = 0.f;
     if (ci < Cin) {
 #pragma unroll 4
-      for (int co = cg; co < Co; co += 4) {
+      for (int co = cg; co < Co; co += 16) {
         const float w = __ldg(W + (int64_t)co * Cin + ci);
 #pragma unroll
         for (int j = 0; j < kFcNB; ++j)
@@ -216,11 +217,14 @@ fc_small_bwd_b_kernel(const float* __restrict__ dpre, const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < kFcNB; ++j) s_red[cg][j][cl] = acc[j];
     __syncthreads();
-    for (int i = threadIdx.x; i < kFcNB * 64; i += 256) {
-      const int j = i >> 6, c = i & 63;
-      const int n = n0 + j, cc = blockIdx.x * 64 + c;
+    if (threadIdx.x < kFcNB * 16) {
+      const int j = threadIdx.x >> 4, c = threadIdx.x & 15;
+      const int n = n0 + j, cc = blockIdx.x * 16 + c;
       if (n < N && cc < Cin) {
-        const float v = (s_red[0][j][c] + s_red[1][j][c] + s_red[2][j][c] + s_red[3][j][c]) * in_scale;
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v += s_red[k][j][c];
+        v *= in_scale;
         float* d = din + (int64_t)n * Cin + cc;
         *d = accumulate ? *d + v : v;
       }
@@ -251,11 +255,21 @@ scale_add_bcast_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, int Hs, in
     const int64_t q = ((int64_t)n * Hs + hs) * Ws + ws;
     float x[8], o[8];
     ld8a(a + q * a_ld + g * 8, x);
+    float sv[8], vv[8];
+    if (s != nullptr) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (int64_t)n * C + g * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(s + (int64_t)n * C + g * 8) + 1);
+      sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+    }
+    if (v != nullptr) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(v + (int64_t)n * C + g * 8));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(v + (int64_t)n * C + g * 8) + 1);
+      vv[0] = v0.x; vv[1] = v0.y; vv[2] = v0.z; vv[3] = v0.w; vv[4] = v1.x; vv[5] = v1.y; vv[6] = v1.z; vv[7] = v1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      float r = x[j] * ((s != nullptr ? __ldg(s + (int64_t)n * C + c) : 0.f) + s_plus);
-      if (v != nullptr) r += __ldg(v + (int64_t)n * C + c) * v_scale;
+      float r = x[j] * ((s != nullptr ? sv[j] : 0.f) + s_plus);
+      if (v != nullptr) r += vv[j] * v_scale;
       o[j] = r;
     }
     if (t != nullptr) {
@@ -329,10 +343,8 @@ upsum_dot_reduce_kernel(const __nv_bfloat16* __restrict__ dout, int dout_ld, int
     atomicAdd(&s_acc[C + g * 8 + j], a2[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    if (dot != nullptr) atomicAdd(&dot[(int64_t)n * C + i], s_acc[i]);
-    if (vsum != nullptr) atomicAdd(&vsum[(int64_t)n * C + i], s_acc[C + i]);
-  }
+  if (dot != nullptr) flush_add_v4(dot + (int64_t)n * C, s_acc, C, threadIdx.x, blockDim.x);
+  if (vsum != nullptr) flush_add_v4(vsum + (int64_t)n * C, s_acc + C, C, threadIdx.x, blockDim.x);
 }
 
 static int thr_for(int C) {
@@ -381,7 +393,7 @@ int b200_fc_small_bwd(const float* dout, const float* out, const float* pre, con
   int rc = check_launch("fc_small_bwd_a");
   if (rc) return rc;
   if (din != nullptr) {
-    fc_small_bwd_b_kernel<<<(Cin + 63) / 64, 256, 0, stream>>>(dpre_scratch, W, in_scale, N, Cin, Co, din, accumulate_din);
+    fc_small_bwd_b_kernel<<<(Cin + 15) / 16, 256, 0, stream>>>(dpre_scratch, W, in_scale, N, Cin, Co, din, accumulate_din);
     rc = check_launch("fc_small_bwd_b");
   }
   return rc;

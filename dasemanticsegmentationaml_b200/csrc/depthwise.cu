@@ -146,7 +146,7 @@ dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], s_acc[i]);
+    flush_add_v4(stats, s_acc, 2 * C, threadIdx.x, blockDim.x);
   }
 }
 

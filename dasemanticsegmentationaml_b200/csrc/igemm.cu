@@ -235,10 +235,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       const int t = threadIdx.x - 64;
-      for (int col = t; col < p.BN; col += 128) {
-        atomicAdd(p.stats + n0 + col, s_stats[0][col]);
-        atomicAdd(p.stats + p.stats_ld + n0 + col, s_stats[1][col]);
-      }
+      flush_add_v4(p.stats + n0, s_stats[0], p.BN, t, 128);
+      flush_add_v4(p.stats + p.stats_ld + n0, s_stats[1], p.BN, t, 128);
     }
   }
 
@@ -423,9 +421,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int t = threadIdx.x - 64;
+          flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
+          flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
           for (int col = t; col < p.BN; col += 128) {
-            atomicAdd(p.stats + cur_n0 + col, s_stats[0][col]);
-            atomicAdd(p.stats + p.stats_ld + cur_n0 + col, s_stats[1][col]);
             s_stats[0][col] = 0.f;
             s_stats[1][col] = 0.f;
           }
@@ -493,10 +492,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     if (p.stats != nullptr && cur_n0 >= 0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int t = threadIdx.x - 64;
-      for (int col = t; col < p.BN; col += 128) {
-        atomicAdd(p.stats + cur_n0 + col, s_stats[0][col]);
-        atomicAdd(p.stats + p.stats_ld + cur_n0 + col, s_stats[1][col]);
-      }
+      flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
+      flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
     }
   }
 
@@ -963,6 +960,8 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   if (in_ld % 8 || in_coff % 8 || out_ld % 8 || out_coff % 8)
     return set_error(B200_EINVAL, "conv_igemm: channel strides/offsets must be multiples of 8");
   if (filt_rows % 16) return set_error(B200_EINVAL, "conv_igemm: filter rows %d not a multiple of 16", filt_rows);
+  if (stats != nullptr && ((reinterpret_cast<uintptr_t>(stats) & 15) || stats_ld % 4))
+    return set_error(B200_EINVAL, "conv_igemm: the statistics buffer must be 16-byte aligned with a row length that is a multiple of 4");
   int rc = ensure_smem_optin();
   if (rc) return rc;
 

@@ -46,6 +46,8 @@ __device__ __forceinline__ float act_grad(float pre, int act, float slope) {
 // and walks pixels in batches of UNR independent 16-byte loads per tensor (memory-level parallelism).
 constexpr int UNR = 4;   // single-tensor kernels
 constexpr int UNR3 = 2;  // kernels streaming three tensors
+constexpr int UNRF = 4;  // the fused BatchNorm backward (register budget of 2 CTAs x 256 threads per SM)
+constexpr int kRedRep = 8;  // replicas of the partial-sum buffer of the fused BatchNorm backward
 
 struct Slot {
   int g, ty, py;
@@ -95,7 +97,7 @@ channel_stats_kernel(const __nv_bfloat16* __restrict__ x, int ld, int C, int64_t
     atomicAdd(&s_acc[C + t.g * 8 + j], s2[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], s_acc[i]);
+  flush_add_v4(stats, s_acc, 2 * C, threadIdx.x, blockDim.x);
 }
 
 // mean / biased var from (sum, sumsq) -> scale = gamma*rstd, shift = beta - mean*scale; running
@@ -260,7 +262,7 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
     atomicAdd(&s_acc[C + t.g * 8 + j], a2[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[i], s_acc[i]);
+  flush_add_v4(red, s_acc, 2 * C, threadIdx.x, blockDim.x);
 }
 
 // dz = scale * (g - red0/M - xhat * red1/M)        (train-mode BatchNorm backward)
@@ -328,6 +330,7 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                         float* red, float inv_count, int act, float slope) {
   extern __shared__ float s_acc[];  // [2][C]
   const Slot t = slot_of(C);
+  const int groups = C >> 3;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   float sc[8], sh[8], a1[8] = {0}, a2[8] = {0};
@@ -336,14 +339,14 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
     sc[j] = scale[t.g * 8 + j];
     sh[j] = shift[t.g * 8 + j];
   }
-  const int64_t step = (int64_t)gridDim.x * t.py * UNR3;
+  const int64_t step = (int64_t)gridDim.x * t.py * UNRF;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   int64_t last_base = -1;
-  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR3; base < npix; base += step) {
+  for (int64_t base = (int64_t)blockIdx.x * t.py * UNRF; base < npix; base += step) {
     last_base = base;
-    uint4 rd[UNR3], rz[UNR3], re[UNR3];
+    uint4 rd[UNRF], rz[UNRF], re[UNRF];
 #pragma unroll
-    for (int u = 0; u < UNR3; ++u) {
+    for (int u = 0; u < UNRF; ++u) {
       const int64_t p = base + u * t.py + t.ty;
       const bool ok = p < npix;
       rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
@@ -351,7 +354,7 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
       re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
     }
 #pragma unroll
-    for (int u = 0; u < UNR3; ++u) {
+    for (int u = 0; u < UNRF; ++u) {
       float d[8], zz[8], e[8];
       unpack8(rd[u], d);
       unpack8(rz[u], zz);
@@ -364,28 +367,56 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
       }
     }
   }
+  // block reduction: lanes holding the same channel group fold by shuffles, then one shared-memory
+  // atomic per (warp, channel)
+  const bool fold = groups < 32 && (32 % groups) == 0 && (blockDim.x % 32) == 0;
+  if (fold) {
+    for (int off = groups; off < 32; off <<= 1) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    a2[j] = (a2[j] - mean[t.g * 8 + j] * a1[j]) * rstd[t.g * 8 + j];
-    atomicAdd(&s_acc[t.g * 8 + j], a1[j]);
-    atomicAdd(&s_acc[C + t.g * 8 + j], a2[j]);
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off);
+        a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], off);
+      }
+    }
+  }
+  if (!fold || (threadIdx.x & 31) < groups) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a2[j] = (a2[j] - mean[t.g * 8 + j] * a1[j]) * rstd[t.g * 8 + j];
+      atomicAdd(&s_acc[t.g * 8 + j], a1[j]);
+      atomicAdd(&s_acc[C + t.g * 8 + j], a2[j]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&red[i], s_acc[i]);
+  // Same-address global atomics serialise at ~14 ns each in L2, so the CTAs spread their partial
+  // sums over kRedRep replicas (red[1 + rep][2][C]); the totals are rebuilt after the grid barrier.
+  float* rep = red + (size_t)(1 + blockIdx.x % kRedRep) * 2 * C;
+  flush_add_v4(rep, s_acc, 2 * C, threadIdx.x, blockDim.x);
   __threadfence();
   cooperative_groups::this_grid().sync();
   float k0[8], k1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = t.g * 8 + j;
-    const float r0 = __ldcg(red + c) * inv_count, r1 = __ldcg(red + C + c) * inv_count;
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < kRedRep; ++r) {
+      r0 += __ldcg(red + (size_t)(1 + r) * 2 * C + c);
+      r1 += __ldcg(red + (size_t)(1 + r) * 2 * C + C + c);
+    }
+    if (blockIdx.x == 0 && t.ty == 0) {   // totals for the caller: dbeta = red[0][c], dgamma = red[1][c]
+      red[c] = r0;
+      red[C + c] = r1;
+    }
+    r0 *= inv_count;
+    r1 *= inv_count;
     k1[j] = -sc[j] * r1 * rstd[c];
     k0[j] = -sc[j] * r0 - k1[j] * mean[c];
   }
   for (int64_t base = last_base; base >= 0; base -= step) {
-    uint4 rd[UNR3], rz[UNR3], re[UNR3];
+    uint4 rd[UNRF], rz[UNRF], re[UNRF];
 #pragma unroll
-    for (int u = 0; u < UNR3; ++u) {
+    for (int u = 0; u < UNRF; ++u) {
       const int64_t p = base + u * t.py + t.ty;
       const bool ok = p < npix;
       rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
@@ -393,7 +424,7 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
       re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
     }
 #pragma unroll
-    for (int u = 0; u < UNR3; ++u) {
+    for (int u = 0; u < UNRF; ++u) {
       const int64_t p = base + u * t.py + t.ty;
       if (p < npix) {
         float d[8], zz[8], e[8], o[8];
@@ -459,7 +490,7 @@ act_bwd_bias_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
   }
   __syncthreads();
   if (dbias != nullptr)
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dbias[i], s_acc[i]);
+    flush_add_v4(dbias, s_acc, C, threadIdx.x, blockDim.x);
 }
 
 // fp32 -> bf16 copy (gradient of the fp32 low-resolution logits entering the bf16 GEMMs)
@@ -588,21 +619,19 @@ int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_
   int rc = check_c(C, "bn_act_bwd_fused");
   if (rc) return rc;
   const int threads = block_for(C);
+  const int py = threads / (C / 8);
   const size_t smem = 2 * C * sizeof(float);
-  static int max_blocks_per_sm[2049] = {0};  // indexed by C (block shape and smem depend on C only)
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (max_blocks_per_sm[C] == 0) {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bn_act_bwd_fused_kernel, threads, smem);
-    if (nb < 1) return set_error(B200_ECUDA, "bn_act_bwd_fused: kernel does not fit an SM");
-    max_blocks_per_sm[C] = nb;
-  }
-  int grid = reduce_grid(npix, threads / (C / 8), n_sm * max_blocks_per_sm[C]);
+  // two co-resident CTAs of <= 256 threads per SM (128 registers per thread): the whole grid must
+  // be resident for the grid barrier
+  const int64_t blocks = (npix + (int64_t)py * UNRF - 1) / ((int64_t)py * UNRF);
+  const int cap = n_sm * (threads <= 256 ? 2 : 1);
+  const int grid = (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
   const __nv_bfloat16* a0 = static_cast<const __nv_bfloat16*>(dy1);
   const __nv_bfloat16* a1 = static_cast<const __nv_bfloat16*>(dy2);
   const __nv_bfloat16* a2 = static_cast<const __nv_bfloat16*>(z);

@@ -176,6 +176,18 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
 }
 
 // ----------------------------------------------------------- small helpers
+// 16-byte vector reduction (REDG.E.ADD.F32x4): one L2 atomic request for four floats.  Global
+// atomics are a chip-wide ~10 G requests/s resource and same-address requests serialise, so the
+// per-CTA flushes of per-channel partial sums use this instead of four scalar atomicAdd.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+// Flush n (multiple of 4) floats of shared memory into 16-byte aligned global memory.
+__device__ __forceinline__ void flush_add_v4(float* dst, const float* s_src, int n, int tid, int nthreads) {
+  for (int i = tid * 4; i < n; i += nthreads * 4) red_add_v4(dst + i, s_src[i], s_src[i + 1], s_src[i + 2], s_src[i + 3]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

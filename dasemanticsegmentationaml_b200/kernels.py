@@ -286,8 +286,13 @@ def bn_act_bwd_apply(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope)
         stream(), nbytes=(6.0 if dy2 is None else 8.0) * npix * c, tag="px%d C%d%s" % (npix, c, "" if dy2 is None else " +dy2"))
 
 
+BN_RED_REPLICAS = 8  # kRedRep in csrc/norm.cu
+
+
 def bn_act_bwd_fused(dy1, dy2, z, dz, scale, shift, mean, rstd, red, act, slope):
+    """`red`: zeroed fp32 [1 + BN_RED_REPLICAS, 2, C]; red[0] returns (dbeta, dgamma)."""
     npix, c, z_ld = _pix(z)
+    assert red.numel() == (1 + BN_RED_REPLICAS) * 2 * c
     call("b200_bn_act_bwd_fused",
          ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
          ptr(z), c_int(z_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), ptr(scale),

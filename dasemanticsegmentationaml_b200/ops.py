@@ -165,10 +165,10 @@ def bn_act_bwd(ctx, dy1, dy2=None):
     if not ctx.training:
         raise NotImplementedError("backward through eval-mode BatchNorm is not part of the reference's training path")
     c = ctx.z.shape[3]
-    red = zeros_f32((2, c), ctx.z.device)
+    red = zeros_f32((1 + K.BN_RED_REPLICAS, 2, c), ctx.z.device)   # [0]: totals, [1:]: partial-sum replicas
     dz = torch.empty(ctx.z.shape, dtype=BF16, device=ctx.z.device)
     K.bn_act_bwd_fused(dy1, dy2, ctx.z, dz, ctx.scale, ctx.shift, ctx.mean, ctx.rstd, red, ctx.act, ctx.slope)
-    return dz, red[1], red[0]
+    return dz, red[0, 1], red[0, 0]
 
 
 # --------------------------------------------------------------------------- dense conv (+BN+act)

@@ -119,7 +119,9 @@ int b200_bn_act_bwd_apply(const void* dy1, int dy1_ld, const void* dy2, int dy2_
                           const float* shift, const float* mean, const float* rstd,
                           const float* red, float inv_count, int act, float slope,
                           cudaStream_t stream);
-/* reduce + apply in one cooperative launch (grid-wide barrier in between; `red` zeroed by the caller). */
+/* reduce + apply in one cooperative launch (grid-wide barrier in between).  `red` is float
+ * [1 + 8][2][C], zeroed by the caller: [0] receives the totals (dbeta = red[0][0][c], dgamma =
+ * red[0][1][c]), [1..8] are partial-sum replicas (same-address atomics serialise in L2). */
 int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_ld, const void* z,
                           int z_ld, void* dz, int dz_ld, int C, int64_t npix, const float* scale,
                           const float* shift, const float* mean, const float* rstd, float* red,

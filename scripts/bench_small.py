@@ -118,3 +118,19 @@ for c, h, w in ((64, 256, 512), (128, 128, 256), (256, 64, 128), (512, 32, 64)):
 img = torch.randn(N, 3, 512, 1024, device=dev)
 col = act(N, 256, 512, 32)
 run("stem_im2col 512x1024", lambda: K.stem_im2col(img, col), img.numel() * 4 + col.numel() * 2)
+# ---- BatchNorm passes (forward normalise+act, fused backward) at the step's layer shapes
+for npix, c in ((1048576, 32), (262144, 64), (262144, 128), (65536, 256), (65536, 128), (65536, 64), (65536, 32),
+                (16384, 512), (16384, 256), (16384, 128), (16384, 64), (4096, 512), (4096, 256), (4096, 128)):
+    z, a, dy, dy2, dz = (act(1, 1, npix, c) for _ in range(5))
+    stats = torch.stack([z.float().sum((0, 1, 2)), z.float().square().sum((0, 1, 2))]).contiguous()
+    gamma, beta, rm, rv = torch.ones(c, device=dev), torch.zeros(c, device=dev), torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    buf, red = torch.empty(4, c, device=dev), torch.zeros(1 + K.BN_RED_REPLICAS, 2, c, device=dev)
+    e = npix * c
+    run("bn_norm_act px%d C%d" % (npix, c), lambda: K.bn_norm_act(z, a, stats, float(npix), gamma, beta, rm, rv, True, 1, 0.0,
+                                                                    buf[0], buf[1], buf[2], buf[3]), 4 * e)
+    run("bn_act_bwd_fused px%d C%d" % (npix, c), lambda: K.bn_act_bwd_fused(dy, None, z, dz, buf[0], buf[1], buf[2], buf[3], red, 1, 0.0), 6 * e)
+    run("bn_act_bwd_fused px%d C%d +dy2" % (npix, c), lambda: K.bn_act_bwd_fused(dy, dy2, z, dz, buf[0], buf[1], buf[2], buf[3], red, 1, 0.0), 8 * e)
+    def two_kernel():
+        K.bn_act_bwd_reduce(dy, None, z, buf[0], buf[1], buf[2], buf[3], 1, 0.0, red[0])
+        K.bn_act_bwd_apply(dy, None, z, dz, buf[0], buf[1], buf[2], buf[3], red[0], 1, 0.0)
+    run("bn_act_bwd reduce+apply px%d C%d" % (npix, c), two_kernel, 6 * e)
