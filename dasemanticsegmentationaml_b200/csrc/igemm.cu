@@ -1195,7 +1195,7 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   const double out_elems = (double)n_taps * p.co_tiles * 128.0 * p.ci_tiles * p.BNW;
   int splits = 1;
   double best = 1e30;
-  for (int s = 1; s <= total_tiles && s <= 64; ++s) {
+  for (int s = 1; s <= total_tiles && s <= 296; ++s) {
     const int ctas = ytiles * s;
     const int waves = (ctas + 147) / 148;
     const int iters = (total_tiles + s - 1) / s;

@@ -25,6 +25,7 @@ from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, Dept
 ap = argparse.ArgumentParser()
 ap.add_argument("--supervised", action="store_true")
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--only", default="", help="regex: tune only the shape keys that match, keep the other table entries")
 ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(K.__file__)), "tuned_tiles.json"))
 args = ap.parse_args()
 
@@ -84,9 +85,15 @@ def timeit(fn, reps=10):
     return best
 
 
+import re  # noqa: E402
 tuned = {}
+if args.only and os.path.exists(args.out):
+    with open(args.out) as f:
+        tuned = json.load(f)
 total_before = total_after = 0.0
 for key, (kind, m) in sorted(records.items()):
+    if args.only and not re.search(args.only, key):
+        continue
     try:
         if kind == "conv":
             geom = m["geom"]
@@ -136,7 +143,7 @@ for key, (kind, m) in sorted(records.items()):
             base = timeit(lambda: run(0))
             cin64 = (m["cin"] + 63) // 64 * 64
             total_px = m["n"] * m["ho"] * m["wo"]
-            for bnw, st, sp, kp in itertools.product((64, 128, 192, 256), (2, 3, 4), (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48),
+            for bnw, st, sp, kp in itertools.product((64, 128, 192, 256), (2, 3, 4), (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 74, 148, 296),
                                                      (1, 2)):
                 if bnw > cin64 or (bnw == 192 and cin64 % 192):
                     continue
@@ -154,6 +161,8 @@ for key, (kind, m) in sorted(records.items()):
         best_us, best_tune, best_name = results[0]
         if best_us < 0.97 * base:
             tuned[key] = best_tune
+        else:
+            tuned.pop(key, None)
         total_before += base
         total_after += min(base, best_us)
         log("%-58s auto %8.1f us | best %8.1f us %-26s | 2nd %s %.1f" % (key, base, best_us, best_name,
