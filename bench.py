@@ -116,7 +116,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------- clocks
@@ -421,7 +421,7 @@ def run_b200(args):
         except Exception as ex:  # the baseline is informational; never lose the GPU line over it
             line["cpu_baseline"] = {"value": None, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "failed: %r" % (ex,)}
-    print(json.dumps(line))
+    emit(line)
     _finish(world)
 
 
@@ -443,8 +443,20 @@ def conv_traffic(workload):
         return json.load(f).get("traffic_bytes_per_launch")
 
 
+_REAL_STDOUT = sys.stdout
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else any library or
+    module prints while the bench runs (e.g. STDCNet813's 'use pretrain model' notice, kept for parity
+    with stdcnet.py:139) is routed to stderr."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse()
+    sys.stdout = sys.stderr
     if args.impl == "reference":
         run_reference(args)
     else:
