@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="da_dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--torch-optim", action="store_true", help="torch's fused SGD/Adam instead of optim.FusedSGD/FusedAdam")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -206,13 +207,20 @@ def run_b200(args):
     model = BiSeNet("STDCNet813", NCLS).to(dev)
     # same optimizers and hyper-parameters as train.py:170-172; fused=True only changes how torch
     # launches the update (one multi-tensor kernel per step)
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
+    from dasemanticsegmentationaml_b200 import optim as B200Optim
+    if args.torch_optim:
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
+    else:   # one launch per optimizer step; same arithmetic as torch.optim.SGD / Adam
+        opt = B200Optim.FusedSGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
     model_d = opt_d = None
     if args.workload.startswith("da_"):
         cls = {"da_dense": FCDiscriminator, "da_dwsep": DepthWiseSepFCDiscriminator,
                "da_dwsep_bn": DepthWiseSepBNFCDiscriminator}[args.workload]
         model_d = cls(NCLS).to(dev)
-        opt_d = torch.optim.Adam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
+        if args.torch_optim:
+            opt_d = torch.optim.Adam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
+        else:
+            opt_d = B200Optim.FusedAdam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99))
 
     g = torch.Generator().manual_seed(100 + rank)  # rank-dependent data
     host = {

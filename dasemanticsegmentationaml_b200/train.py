@@ -214,6 +214,8 @@ class GraphedStep(object):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.outputs = fn(**self.static)
+        from . import optim
+        optim.flush_pending()   # pointer tables of optim.FusedSGD / FusedAdam steps inside the graph
 
     def load(self, **inputs):
         """Copy new inputs into the graph's static buffers (device or pinned-host tensors)."""

@@ -243,6 +243,22 @@ int b200_label_resize_remap(const uint8_t* src, int N, int H0, int W0, const int
                             int H, int W, const uint8_t* lut, void* dst, int dst_is_i64,
                             cudaStream_t stream);
 
+/* ------------------------------------------------------------------ optimizers */
+/* One launch = one optimizer.step() over every parameter tensor (train.py:170-172, 219-221, 235-237,
+ * 252-254, 260-262): torch.optim.SGD (momentum, dampening, L2 weight decay, nesterov) and
+ * torch.optim.Adam (bias-corrected, L2 weight decay, no amsgrad).
+ * table_dev: int64 [n_tensors][8] = {param*, grad*, state1* (momentum buffer / exp_avg, 0 = none),
+ *   state2* (exp_avg_sq), numel, first chunk (prefix sum of ceil(numel / b200_optim_chunk())),
+ *   hyper-parameter group, flags (bit 0: momentum buffer already initialised)}; all fp32.
+ * hyper_dev: float [n_groups][8] = {lr, momentum, dampening, weight_decay, nesterov, beta1, beta2, eps}.
+ * counters_dev (Adam): int64[2] = {step count, 0}; the kernel advances the step itself, so a captured
+ * graph replays correctly. */
+int b200_sgd_step(const int64_t* table_dev, int n_tensors, int total_chunks, const float* hyper_dev,
+                  cudaStream_t stream);
+int b200_adam_step(const int64_t* table_dev, int n_tensors, int total_chunks, const float* hyper_dev,
+                   int64_t* counters_dev, cudaStream_t stream);
+int b200_optim_chunk(void);
+
 #ifdef __cplusplus
 }
 #endif

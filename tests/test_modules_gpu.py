@@ -332,8 +332,11 @@ def test_weight_updates_reach_the_packed_filters(cuda_lib, fused):
     assert rel_l2(y, ref) < 1e-2
 
 
-def test_graphed_da_step_matches_eager(cuda_lib):
-    """The CUDA-graph replay of the DA step must train exactly like the eager launches."""
+@pytest.mark.parametrize("optimizers", ["torch", "b200"])
+def test_graphed_da_step_matches_eager(cuda_lib, optimizers):
+    """The CUDA-graph replay of the DA step must train exactly like the eager launches (with torch's
+    fused optimizers and with optim.FusedSGD / FusedAdam, whose pointer tables are built in-capture)."""
+    from dasemanticsegmentationaml_b200 import optim as B200Optim
     from dasemanticsegmentationaml_b200 import train as T
     from dasemanticsegmentationaml_b200.model import BiSeNet, FCDiscriminator
     g = torch.Generator().manual_seed(12)
@@ -346,8 +349,12 @@ def test_graphed_da_step_matches_eager(cuda_lib):
         dsd = O.make_discriminator_state("dense", seed=4)
         m = load_oracle_state(BiSeNet("STDCNet813", 19), sd).to(DEV)
         d = load_oracle_state(FCDiscriminator(19), dsd).to(DEV)
-        opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
-        opt_d = torch.optim.Adam(d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
+        if optimizers == "torch":
+            opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
+            opt_d = torch.optim.Adam(d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
+        else:
+            opt = B200Optim.FusedSGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+            opt_d = B200Optim.FusedAdam(d.parameters(), lr=1e-3, betas=(0.9, 0.99))
 
         def fn(images, labels, images_t):
             return T.train_da_step(m, d, opt, opt_d, images, labels, images_t)
