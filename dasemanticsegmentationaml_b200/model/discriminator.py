@@ -99,6 +99,8 @@ class FCDiscriminator(_DiscriminatorBase):
             if need_dw:
                 grads[convs[i].weight] = dw
                 grads[convs[i].bias] = db
+            if i == 3:
+                ops.REDUCER.hook()   # conv4 + classifier = 3/4 of the parameters: exchange them early
         return d, grads
 
 

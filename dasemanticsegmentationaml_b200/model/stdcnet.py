@@ -254,6 +254,10 @@ class STDCNet813(B200Module):
             else:
                 d, g = layer._bwd(ctx["layers"][i], d, True)
             grads.update(g)
+            if i == self._stage_ends[2]:
+                # stages 4 and 5 hold ~85 % of the parameters and are done first: start averaging
+                # their gradients over the ranks while the high-resolution stages still run
+                ops.REDUCER.hook()
         return None, grads
 
     def _fwd_api(self, x):

@@ -107,10 +107,10 @@ class _ZeroArena(object):
         self.stack = []
 
     def begin(self, tag, device):
-        self.stack.append([tag, device, None, 0, 0])  # tag, device, chunk, offset, requested
+        self.stack.append([tag, device, None, 0, 0, 0])  # tag, device, chunk, offset, requested, all-reduced mark
 
     def end(self):
-        tag, _, _, _, requested = self.stack.pop()
+        tag, _, _, _, requested, _ = self.stack.pop()
         self.hint[tag] = max(self.hint.get(tag, 0), requested)
 
     def zeros(self, shape, device):
@@ -125,12 +125,86 @@ class _ZeroArena(object):
         if st[2] is None or st[3] + size > st[2].numel():
             st[2] = torch.zeros(max(size, self.hint.get(st[0], 0) - (st[4] - size), 1 << 16), dtype=F32, device=device)
             st[3] = 0
+            st[5] = 0   # (an un-reduced tail of the retired chunk is picked up by the flat fallback)
         out = st[2][st[3]:st[3] + n].view(shape)
         st[3] += size
         return out
 
 
 ARENA = _ZeroArena()
+
+
+class _GradReducer(object):
+    """Data-parallel gradient exchange overlapped with the backward, with no flatten / unflatten copies.
+
+    Every parameter gradient of a module backward is a slice of the arena chunk above, handed out in
+    the order the backward produces them.  So "the gradients finished so far" is one contiguous fp32
+    span: `hook()` (called by the model backwards after their parameter-heavy late stages, and once
+    at the end) all-reduces the span produced since the previous hook IN PLACE on a communication
+    stream while the main stream keeps running the rest of the backward.  The span also contains
+    consumed scratch (BatchNorm partial sums); averaging that is harmless.  `finish()` makes the
+    main stream wait for the exchange and returns the gradients that were not covered (first
+    iterations, before the arena knows its size; gradients made by other autograd nodes)."""
+
+    MIN_FLOATS = 1 << 20
+
+    def __init__(self):
+        self.active = False
+        self.streams = {}
+        self.spans = []
+        self.snapshots = None   # tests: list that receives (span view, copy of the span before the exchange)
+
+    @staticmethod
+    def world():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def begin(self, need_dw, device):
+        import torch.distributed as dist
+        self.active = bool(need_dw) and device.type == "cuda" and self.world() > 1 and dist.get_backend() == "nccl"
+
+    def hook(self, final=False):
+        if not self.active or not ARENA.stack:
+            return
+        st = ARENA.stack[-1]
+        chunk, lo, hi = st[2], st[5], st[3]
+        if chunk is None or hi - lo < (1 if final else self.MIN_FLOATS):
+            return
+        import torch.distributed as dist
+        dev = st[1]
+        key = dev.index or 0
+        if key not in self.streams:
+            self.streams[key] = torch.cuda.Stream(device=dev)
+        comm, main = self.streams[key], torch.cuda.current_stream(dev)
+        view = chunk[lo:hi]
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            if self.snapshots is not None:
+                self.snapshots.append((view, view.clone()))
+            dist.all_reduce(view, op=dist.ReduceOp.AVG)
+        self.spans.append((view.data_ptr(), view.data_ptr() + 4 * view.numel(), view))
+        st[5] = hi
+
+    def end(self):
+        self.hook(final=True)
+        self.active = False
+
+    def finish(self, grads):
+        """-> the gradients still to be exchanged; the main stream now waits for the spans."""
+        if not self.spans:
+            return grads
+        for key, comm in self.streams.items():
+            torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(comm)
+        left = []
+        for g in grads:
+            ptr = g.data_ptr()
+            if not (g.dtype == F32 and any(lo <= ptr and ptr + 4 * g.numel() <= hi for lo, hi, _ in self.spans)):
+                left.append(g)
+        self.spans = []
+        return left
+
+
+REDUCER = _GradReducer()
 
 
 def zeros_f32(shape, device):

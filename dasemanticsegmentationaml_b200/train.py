@@ -33,6 +33,10 @@ def allreduce_grads(params, world=None):
     if world == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]
+    if grads and grads[0].is_cuda:
+        # most gradients were already averaged in place, overlapped with the backward (ops.REDUCER)
+        from . import ops
+        grads = ops.REDUCER.finish(grads)
     if not grads:
         return
     flat = torch._utils._flatten_dense_tensors(grads)

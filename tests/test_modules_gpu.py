@@ -3,6 +3,8 @@
 Tolerances are the north-star's: per-layer activation rel-L2 <= 2e-2 (bf16), gradient cosine
 >= 0.999 against the quantisation-matched oracle (fp32 math on bf16-rounded inputs), eval argmax
 agreement >= 99.5 % on `out`.  The oracle runs in fp32 on the GPU (TF32 off) for speed."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -381,3 +383,16 @@ def test_graphed_da_step_matches_eager(cuda_lib, optimizers):
         for u, v in zip(a[1:], b[1:]):
             assert abs(u - v) < 0.2, (runs[0], runs[1])
     assert runs[1][3][0] != runs[1][0][0]  # the weights do move between replays
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL)")
+def test_overlapped_gradient_exchange_two_gpus():
+    """ops.REDUCER on real NCCL (scripts/check_reducer.py): exchanged spans equal the mean of the
+    ranks' pre-exchange snapshots, cover every gradient, and are identical on all ranks."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531",
+                        os.path.join(root, "scripts", "check_reducer.py")], capture_output=True, text=True, timeout=300)
+    assert "REDUCER CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
