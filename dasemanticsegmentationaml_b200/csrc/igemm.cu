@@ -37,6 +37,18 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
+// v[j] *= leaky'(mask[j]) for 16 consecutive channels of one pixel (two 16-byte loads).
+__device__ __forceinline__ void apply_mask16(float (&v)[16], const __nv_bfloat16* m, float slope) {
+  const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(m)), u1 = __ldg(reinterpret_cast<const uint4*>(m) + 1);
+  const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float2 a = unpack_bf16(w[k]);
+    v[2 * k] *= a.x > 0.f ? 1.f : slope;
+    v[2 * k + 1] *= a.y > 0.f ? 1.f : slope;
+  }
+}
+
 // Sum 16 per-lane values over the 32 lanes of a warp with a halving butterfly (16 shuffles).
 // On return lane L holds in `v[0]` the total of column  col_of_lane(L) (see below); both lanes of
 // an (even, odd) pair hold the same column.
@@ -199,6 +211,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.bias != nullptr) x += __ldg(p.bias + n0 + c + j);
           v[j] = apply_act(x, p.act, p.slope);
         }
+        if (p.mask != nullptr && valid)
+          apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + n0 + c, p.mask_slope);
         if (valid) {
           if (p.out_f32) {
             float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
@@ -223,11 +237,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             s2[j] = x * x;
           }
           const float t1 = column_sums16(s1, lane);
-          const float t2 = column_sums16(s2, lane);
+          const float t2 = p.stats_sum_only ? 0.f : column_sums16(s2, lane);
           if ((lane & 1) == 0) {
             const int col = c + column_of_lane(lane);
             atomicAdd(&s_stats[0][col], t1);
-            atomicAdd(&s_stats[1][col], t2);
+            if (!p.stats_sum_only) atomicAdd(&s_stats[1][col], t2);
           }
         }
       }
@@ -453,6 +467,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             if (p.bias != nullptr) x += __ldg(p.bias + tc.n0 + c + j);
             v[j] = apply_act(x, p.act, p.slope);
           }
+          if (p.mask != nullptr && valid)
+            apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + tc.n0 + c, p.mask_slope);
           if (valid) {
             if (p.out_f32) {
               float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
@@ -475,11 +491,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
               s2[j] = x * x;
             }
             const float t1 = column_sums16(s1, lane);
-            const float t2 = column_sums16(s2, lane);
+            const float t2 = p.stats_sum_only ? 0.f : column_sums16(s2, lane);
             if ((lane & 1) == 0) {
               const int col = c + column_of_lane(lane);
               atomicAdd(&s_stats[0][col], t1);
-              atomicAdd(&s_stats[1][col], t2);
+              if (!p.stats_sum_only) atomicAdd(&s_stats[1][col], t2);
             }
           }
         }
@@ -951,7 +967,8 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
                     int n_classes, const int* class_Ho, const int* class_Wo, const int* class_oa,
                     const int* class_ob, const int* class_ntaps, const int* taps, int taps_stride,
                     int in_stride, int out_stride, const float* bias, int act, float slope,
-                    float* stats, int stats_ld, int tune, cudaStream_t stream) {
+                    float* stats, int stats_ld, const void* mask, int mask_ld, float mask_slope,
+                    int stats_sum_only, int tune, cudaStream_t stream) {
   // tune = BN | (mt << 12) | (stages << 16); a zero field = choose automatically
   // (bit 20: persistent kernel)
   const int bn_override = tune & 0xFFF, mt_override = (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
@@ -960,6 +977,8 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   if (in_ld % 8 || in_coff % 8 || out_ld % 8 || out_coff % 8)
     return set_error(B200_EINVAL, "conv_igemm: channel strides/offsets must be multiples of 8");
   if (filt_rows % 16) return set_error(B200_EINVAL, "conv_igemm: filter rows %d not a multiple of 16", filt_rows);
+  if (mask != nullptr && (mask_ld % 8 || (reinterpret_cast<uintptr_t>(mask) & 15)))
+    return set_error(B200_EINVAL, "conv_igemm: the mask view must be 16-byte aligned with a pixel stride that is a multiple of 8");
   if (stats != nullptr && ((reinterpret_cast<uintptr_t>(stats) & 15) || stats_ld % 4))
     return set_error(B200_EINVAL, "conv_igemm: the statistics buffer must be 16-byte aligned with a row length that is a multiple of 4");
   int rc = ensure_smem_optin();
@@ -1061,6 +1080,10 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   p.out_f32 = out_f32;
   p.stats = stats;
   p.stats_ld = stats_ld;
+  p.mask = mask;
+  p.mask_ld = mask_ld;
+  p.mask_slope = mask_slope;
+  p.stats_sum_only = stats_sum_only;
 
   CUtensorMap tmA, tmB;
   rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);

@@ -41,6 +41,14 @@ struct ConvParams {
   int out_f32;       // 1: fp32 output, 0: bf16
   float* stats;      // nullptr, or [2][C] per-channel sum / sum of squares of the fp32 results
   int stats_ld;      // C
+  // Backward of a biased conv + LeakyReLU layer fused into the data-gradient launch that produces
+  // its output gradient: out = acc * (mask[pixel, c] > 0 ? 1 : mask_slope), where `mask` is the
+  // layer's stored activation (sign(a) == sign(pre-activation)); with stats_sum_only the statistics
+  // path then yields stats[0][c] = sum of the masked gradient = the bias gradient.
+  const void* mask;  // nullptr, or bf16 NHWC view shaped like the output
+  int mask_ld;
+  float mask_slope;
+  int stats_sum_only;
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]

@@ -143,9 +143,12 @@ def wgrad_key(n, ho, wo, cout, cin, r, s, stride):
     return "wgrad %d %d %d co%d ci%d %dx%ds%d" % (n, ho, wo, cout, cin, r, s, stride)
 
 
-def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_tile=None, k_real=None, n_real=None):
+def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_tile=None, k_real=None, n_real=None,
+               mask=None, mask_slope=0.0, stats_sum_only=False):
     """out[N,Hout,Wout,rows_pad] = implicit-GEMM conv of x with a packed filter (see pack_filter).
-    k_real / n_real: un-padded reduction / output channel counts (for the algorithmic FLOP count)."""
+    k_real / n_real: un-padded reduction / output channel counts (for the algorithmic FLOP count).
+    mask / mask_slope / stats_sum_only: LeakyReLU backward + bias gradient of the layer that produced
+    `mask`, folded into this (data-gradient) launch: out *= leaky'(mask), stats[0] += column sums."""
     n, hin, win, cin, in_ld = _nhwc_meta(x)
     n2, hout, wout, cout_view, out_ld = _nhwc_meta(out)
     rows_pad, n_slabs, cin_pad = filt.shape
@@ -157,9 +160,11 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
         assert out.dtype == torch.bfloat16
     if stats is not None:
         assert stats.dtype == torch.float32 and stats.dim() == 2 and stats.shape[0] == 2
+    if mask is not None:
+        assert mask.dtype == torch.bfloat16 and tuple(mask.shape[:3]) == (n, hout, wout) and mask.shape[3] >= rows_pad
     flops = 2.0 * geom.px_taps * n * (k_real or min(cin, cin_pad)) * (n_real or rows_pad)
     if bn_tile is None:
-        key = conv_key(n, hin, win, cin_pad, rows_pad, geom, out_f32, stats is not None)
+        key = conv_key(n, hin, win, cin_pad, rows_pad, geom, out_f32, stats is not None and not stats_sum_only)
         bn_tile = TUNED.get(key, 0)
         if RECORD is not None:
             RECORD.append(("conv", key, dict(n=n, hin=hin, win=win, cin=cin, in_ld=in_ld, rows=rows_pad, cin_pad=cin_pad,
@@ -171,7 +176,9 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
          ptr(out), c_int(out_ld), c_int(0), c_int(hout), c_int(wout), c_int(out_f32),
          geom.c_n, geom.c_ho, geom.c_wo, geom.c_oa, geom.c_ob, geom.c_nt, geom.c_taps, c_int(geom.tmax),
          c_int(geom.in_stride), c_int(geom.out_stride), ptr(bias), c_int(act), c_float(slope),
-         ptr(stats), c_int(0 if stats is None else stats.shape[1]), c_int(bn_tile), stream(), flops=flops,
+         ptr(stats), c_int(0 if stats is None else stats.shape[1]),
+         ptr(mask), c_int(0 if mask is None else mask.stride(2)), c_float(mask_slope), c_int(1 if stats_sum_only else 0),
+         c_int(bn_tile), stream(), flops=flops,
          tag="M%d N%d K%dx%d s%d/%d%s" % (n * geom.classes[0]["Ho"] * geom.classes[0]["Wo"] * len(geom.classes), rows_pad, cin_pad,
                                             len(geom.classes[0]["taps"]), geom.in_stride, geom.out_stride, " stats" if stats is not None else ""))
     return out

@@ -93,9 +93,13 @@ class FCDiscriminator(_DiscriminatorBase):
     def _bwd(self, ctx, dout, need_dx=True, need_dw=True):
         d, grads = _Classifier.bwd(self.classifier, ctx["a4"], dout, need_dw)
         convs = (self.conv1, self.conv2, self.conv3, self.conv4)
+        ready = None   # (dz, dbias) of layer i when the layer above already applied its LeakyReLU backward
         for i in (3, 2, 1, 0):
-            d, dw, db = ops.conv_bias_act_bwd(ctx["convs"][i], d, None, need_dx=(i > 0 or need_dx),
-                                              need_dw=need_dw)
+            # layers 3..1: LeakyReLU backward + bias gradient of the layer below ride in this layer's
+            # data-gradient epilogue (one pass over the big activation gradients instead of three)
+            d, dw, db = ops.conv_bias_act_bwd(ctx["convs"][i], d, None, need_dx=(i > 0 or need_dx), need_dw=need_dw,
+                                              dz_dbias=ready, producer=ctx["convs"][i - 1] if i > 0 else None)
+            ready = d if isinstance(d, tuple) else None
             if need_dw:
                 grads[convs[i].weight] = dw
                 grads[convs[i].bias] = db

@@ -264,13 +264,17 @@ def conv_raw_fwd(x, weight, stride, pad, stats=None, bias=None, act=K.ACT_NONE, 
     return out
 
 
-def conv_dgrad(dz, weight, stride, pad, hin, win):
-    """dx[N,hin,win,round16(Cin)] of a dense conv given dz (NHWC bf16 view over the conv's output)."""
+def conv_dgrad(dz, weight, stride, pad, hin, win, mask=None, mask_slope=0.0, dbias=None):
+    """dx[N,hin,win,round16(Cin)] of a dense conv given dz (NHWC bf16 view over the conv's output).
+    With `mask` (the stored activation of the layer that produced this conv's input) the launch also
+    applies that layer's LeakyReLU backward, i.e. it returns the producer's dz directly, and
+    accumulates the producer's bias gradient into dbias[0] (fp32 [2, round16(Cin)], zeroed)."""
     _, _, r, s = weight.shape
     geom = K.dgrad_geometry(hin, win, r, s, stride, pad)
     filt_t = packed_filter(weight, True)
     dx = torch.empty((dz.shape[0], hin, win, filt_t.shape[0]), dtype=BF16, device=dz.device)
-    K.conv_igemm(dz, filt_t, dx, geom, k_real=weight.shape[0], n_real=weight.shape[1])
+    K.conv_igemm(dz, filt_t, dx, geom, k_real=weight.shape[0], n_real=weight.shape[1], mask=mask,
+                 mask_slope=mask_slope, stats=dbias, stats_sum_only=dbias is not None)
     return dx
 
 
@@ -334,15 +338,29 @@ def conv_bias_act_fwd(x, weight, bias_padded, stride, pad, act, slope):
     return a, ctx
 
 
-def conv_bias_act_bwd(ctx, dy1, dy2=None, need_dx=True, need_dw=True):
-    """-> (dx, dW, dbias)"""
+def conv_bias_act_bwd(ctx, dy1, dy2=None, need_dx=True, need_dw=True, dz_dbias=None, producer=None):
+    """-> (dx, dW, dbias).
+
+    dz_dbias = (dz, dbias): this layer's activation backward was already folded into the launch
+    that produced its output gradient (see `producer`), dy1 is ignored.
+    producer = ConvCtx of the biased conv + LeakyReLU layer that produced this layer's input: its
+    activation backward and bias gradient are folded into this layer's data-gradient launch and
+    `dx` is returned as the pair (producer's dz, producer's dbias) for the next call."""
     c = ctx.a.shape[3]
-    dz = torch.empty(ctx.a.shape, dtype=BF16, device=ctx.a.device)
-    dbias = zeros_f32((c,), ctx.a.device) if need_dw else None
-    K.act_bwd_bias(dy1, dy2, ctx.a, dz, ctx.act, ctx.slope, dbias)
+    if dz_dbias is not None:
+        dz, dbias = dz_dbias
+    else:
+        dz = torch.empty(ctx.a.shape, dtype=BF16, device=ctx.a.device)
+        dbias = zeros_f32((c,), ctx.a.device) if need_dw else None
+        K.act_bwd_bias(dy1, dy2, ctx.a, dz, ctx.act, ctx.slope, dbias)
     dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad) if need_dw else None
     dx = None
-    if need_dx:
+    if need_dx and producer is not None and producer.act == K.ACT_LEAKY and producer.a.shape[3] % 16 == 0:
+        pb = zeros_f32((2, producer.a.shape[3]), dz.device) if need_dw else None
+        pdz = conv_dgrad(dz, ctx.weight, ctx.stride, ctx.pad, ctx.x.shape[1], ctx.x.shape[2], mask=producer.a,
+                         mask_slope=producer.slope, dbias=pb)
+        dx = (pdz, None if pb is None else pb[0])
+    elif need_dx:
         dx = conv_dgrad(dz, ctx.weight, ctx.stride, ctx.pad, ctx.x.shape[1], ctx.x.shape[2])
     if dbias is not None:
         dbias = dbias[:ctx.weight.shape[0]]

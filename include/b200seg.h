@@ -66,14 +66,19 @@ int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStrea
  * gradient autograd derives for the same layers.  Out-of-bounds input is read as zero (padding).
  * stats != NULL: adds per-channel sum / sum of squares of the stored values to stats[0][.] /
  * stats[1][.] (train-mode BatchNorm, stdcnet.py:10,14).  tune: 0 = automatic tile, else
- * BN | (sub-tiles << 12) | (pipeline stages << 16) from the tuned table. */
+ * BN | (sub-tiles << 12) | (pipeline stages << 16) from the tuned table.  * mask (optional, bf16 NHWC view shaped like the output): the result is multiplied by
+ * LeakyReLU'(mask) = (mask > 0 ? 1 : mask_slope) -- the backward of the discriminators' biased
+ * conv + LeakyReLU layers (discriminator.py:17-26) folded into the data-gradient launch that produces
+ * the layer's output gradient; with stats_sum_only = 1 the statistics path then returns only
+ * stats[0][c] = sum over pixels = that layer's bias gradient (stats[1] is left untouched). */
 int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int Hin, int Win,
                     const void* filt, int filt_rows, int cin_pad, int n_slabs, void* out, int out_ld,
                     int out_coff, int Hout, int Wout, int out_f32, int n_classes, const int* class_Ho,
                     const int* class_Wo, const int* class_oa, const int* class_ob,
                     const int* class_ntaps, const int* taps, int taps_stride, int in_stride,
                     int out_stride, const float* bias, int act, float slope, float* stats,
-                    int stats_ld, int tune, cudaStream_t stream);
+                    int stats_ld, const void* mask, int mask_ld, float mask_slope, int stats_sum_only,
+                    int tune, cudaStream_t stream);
 
 /* Weight gradient dW[Cout][Cin][RS] (fp32, PyTorch layout, accumulated) of the same convolutions:
  * dW[co][ci][rs] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]; taps = [n_taps][3] = (dh, dw, rs).
