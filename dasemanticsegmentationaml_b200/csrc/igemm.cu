@@ -37,10 +37,46 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
+// 16 consecutive channels of one output pixel: 32 B of bf16 or 64 B of fp32.
+__device__ __forceinline__ void store16(const ConvParams& p, size_t off, const float (&v)[16]) {
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + off;
+    if (p.wide) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(v[8 * h + j]);
+        st_global_v8(o + 8 * h, r);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+    uint32_t r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    if (p.wide) {
+      st_global_v8(o, r);
+    } else {
+      reinterpret_cast<uint4*>(o)[0] = make_uint4(r[0], r[1], r[2], r[3]);
+      reinterpret_cast<uint4*>(o)[1] = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+  }
+}
+
 // v[j] *= leaky'(mask[j]) for 16 consecutive channels of one pixel (two 16-byte loads).
-__device__ __forceinline__ void apply_mask16(float (&v)[16], const __nv_bfloat16* m, float slope) {
-  const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(m)), u1 = __ldg(reinterpret_cast<const uint4*>(m) + 1);
-  const uint32_t w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+__device__ __forceinline__ void apply_mask16(float (&v)[16], const __nv_bfloat16* m, float slope, int wide) {
+  uint32_t w[8];
+  if (wide) {
+    ld_global_nc_v8(m, w);
+  } else {
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(m)), u1 = __ldg(reinterpret_cast<const uint4*>(m) + 1);
+    w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w; w[4] = u1.x; w[5] = u1.y; w[6] = u1.z; w[7] = u1.w;
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float2 a = unpack_bf16(w[k]);
@@ -212,20 +248,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           v[j] = apply_act(x, p.act, p.slope);
         }
         if (p.mask != nullptr && valid)
-          apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + n0 + c, p.mask_slope);
-        if (valid) {
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c);
-            o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                              pack_bf16(v[6], v[7]));
-            o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                              pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-          }
-        }
+          apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + n0 + c, p.mask_slope, p.wide);
+        if (valid) store16(p, obase + c, v);
         if (p.stats != nullptr) {
           float s1[16], s2[16];
 #pragma unroll
@@ -468,20 +492,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             v[j] = apply_act(x, p.act, p.slope);
           }
           if (p.mask != nullptr && valid)
-            apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + tc.n0 + c, p.mask_slope);
-          if (valid) {
-            if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c);
-              o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                pack_bf16(v[6], v[7]));
-              o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                                pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-            }
-          }
+            apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + tc.n0 + c, p.mask_slope, p.wide);
+          if (valid) store16(p, obase + c, v);
           if (p.stats != nullptr) {
             float s1[16], s2[16];
 #pragma unroll
@@ -1084,6 +1096,12 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   p.mask_ld = mask_ld;
   p.mask_slope = mask_slope;
   p.stats_sum_only = stats_sum_only;
+  {
+    const int esz = out_f32 ? 4 : 2;
+    const bool out_ok = (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (out_ld * esz) % 32 == 0 && (out_coff * esz) % 32 == 0;
+    const bool mask_ok = mask == nullptr || ((reinterpret_cast<uintptr_t>(mask) & 31) == 0 && mask_ld % 16 == 0);
+    p.wide = out_ok && mask_ok ? 1 : 0;
+  }
 
   CUtensorMap tmA, tmB;
   rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);

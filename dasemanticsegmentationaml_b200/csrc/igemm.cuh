@@ -49,6 +49,7 @@ struct ConvParams {
   int mask_ld;
   float mask_slope;
   int stats_sum_only;
+  int wide;          // 1: output (and mask) rows are 32-byte aligned -> 256-bit stores / loads
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]

@@ -175,6 +175,19 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   return d;
 }
 
+// 256-bit global accesses (LDG/STG.E.ENL2.256, sm_100): one request per 32-byte sector instead of
+// two 16-byte halves.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
 // ----------------------------------------------------------- small helpers
 // 16-byte vector reduction (REDG.E.ADD.F32x4): one L2 atomic request for four floats.  Global
 // atomics are a chip-wide ~10 G requests/s resource and same-address requests serialise, so the
