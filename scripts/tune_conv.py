@@ -1,7 +1,7 @@
 """Auto-tuner for the implicit-GEMM tile knobs (run on a B200).
 
 Records every distinct conv / wgrad launch shape of the DA train step (all three discriminator
-variants; optionally the 720x1280 supervised step), sweeps the tile configurations of each shape
+variants; with --supervised also the 720x1280 supervised step and the 1024x2048 eval forward), sweeps the tile configurations of each shape
 with synthetic tensors (CUDA events, best of 2 x 10 launches) and writes
 
     dasemanticsegmentationaml_b200/tuned_tiles.json     {shape key: packed tune word}
@@ -62,6 +62,10 @@ if args.supervised:
     ls = torch.randint(0, 19, (nb, 720, 1280), generator=g).to(dev)
     T.train_step(model, opt, xs, ls)
     del xs, ls
+    xe = torch.randn(nb, 3, 1024, 2048, generator=g).to(dev)      # BASELINE config 5: eval at full resolution
+    le = torch.randint(0, 19, (nb, 1024, 2048), generator=g).to(dev)
+    T.eval_batch(model, xe, le)
+    del xe, le
 torch.cuda.synchronize()
 records = {}
 for kind, key, meta in K.RECORD:
