@@ -642,11 +642,21 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
       tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, r);
       tmem_ld_wait();
       if (co < p.Cout) {
+        if (p.scratch != nullptr) {
+          if (ci0 + c < p.ci_pad) {
+            float* dst = p.scratch + ((size_t)rs * p.Cout + co) * p.ci_pad + ci0 + c;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int ci = ci0 + c + j;
-          if (ci < p.Cin)
-            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.RS + rs, __uint_as_float(r[j]));
+            for (int k = 0; k < 4; ++k)
+              red_add_v4(dst + 4 * k, __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
+                         __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ci = ci0 + c + j;
+            if (ci < p.Cin)
+              atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.RS + rs, __uint_as_float(r[j]));
+          }
         }
       }
     }
@@ -657,6 +667,23 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, p.BNW > 128 ? 256 : p.BNW);
+  }
+}
+
+// dw[co][ci][rs] = scratch[rs][co][ci] for every layer of a module backward in ONE launch.
+// table[i] = {scratch offset, dw offset (floats, from the two base pointers), Cout, Cin, RS, ci_pad}.
+__global__ void __launch_bounds__(256)
+wgrad_unscratch_kernel(const float* __restrict__ sbase, float* __restrict__ dbase,
+                       const long long* __restrict__ table) {
+  const long long* t = table + (size_t)blockIdx.y * 6;
+  const float* sc = sbase + t[0];
+  float* dw = dbase + t[1];
+  const int Cout = (int)t[2], Cin = (int)t[3], RS = (int)t[4], ci_pad = (int)t[5];
+  const int total = Cout * Cin * RS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int rs = i % RS, q = i / RS;
+    const int ci = q % Cin, co = q / Cin;
+    dw[i] = __ldg(sc + ((size_t)rs * Cout + co) * ci_pad + ci);
   }
 }
 
@@ -1149,7 +1176,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
 int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int Ho, int Wo,
                     const void* x, int x_ld, int x_coff, int Cin, int Hin, int Win,
                     int n_taps, const int* taps /* [n_taps][3] = dh, dw, rs */, int RS,
-                    int in_stride, float* dw, int tune, cudaStream_t stream) {
+                    int in_stride, float* dw, float* scratch, int ci_pad, int tune, cudaStream_t stream) {
   // tune = BNW | (stages << 12) | (splits << 16) | (kpix/64 << 28); a zero field = automatic
   const int bnw_override = tune & 0xFFF, st_override = (tune >> 12) & 0xF;
   const int sp_override = (tune >> 16) & 0xFFF, kp_override = (tune >> 28) & 0x3;
@@ -1161,6 +1188,10 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   WgradParams p;
   memset(&p, 0, sizeof(p));
   // thin-input variant: every tap's accumulator resident in TMEM (tune field kpix == 3 disables it)
+  if (scratch != nullptr && (ci_pad % 16 || ci_pad < Cin || (reinterpret_cast<uintptr_t>(scratch) & 15)))
+    return set_error(B200_EINVAL, "conv_wgrad: scratch needs 16-byte alignment and ci_pad = round_up(Cin, 16)");
+  if (scratch != nullptr && Cin <= 32)
+    return set_error(B200_EINVAL, "conv_wgrad: the tap-major scratch is for Cin > 32 (thin layers use the all-taps kernel)");
   if (Cin <= 32 && n_taps * 32 <= 512 && n_taps >= 16 && kp_override != 3 && (int64_t)N * Ho * Wo >= 262144) {
     // (measured: pays off for the 4x4 filters over >= 256K pixels; 3x3 layers keep the tuned generic path)
     pick_patch(Wo, &p.th, &p.tw, 64);
@@ -1261,6 +1292,8 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   }
   if (p.stages * stage_bytes > 222 * 1024) return set_error(B200_EINVAL, "conv_wgrad: tile does not fit shared memory");
   p.dw = dw;
+  p.scratch = scratch;
+  p.ci_pad = ci_pad;
 
   CUtensorMap tmDZ, tmX;
   rc = make_act_map(&tmDZ, dz, dz_coff, Cout, dz_ld, N, Ho, Wo, 64, p.tw, p.th, 1, 128);
@@ -1271,6 +1304,14 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   wgrad_igemm_kernel<<<grid, kThreads, smem, stream>>>(tmDZ, tmX, p);
   return check_launch("conv_wgrad");
+}
+
+int b200_wgrad_unscratch(const float* scratch_base, float* dw_base, const int64_t* table_dev, int n_layers,
+                          cudaStream_t stream) {
+  if (n_layers <= 0) return B200_OK;
+  wgrad_unscratch_kernel<<<dim3(64, n_layers), 256, 0, stream>>>(scratch_base, dw_base,
+                                                                 reinterpret_cast<const long long*>(table_dev));
+  return check_launch("wgrad_unscratch");
 }
 
 }  // extern "C"

@@ -187,8 +187,10 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
 _wgrad_taps = {}
 
 
-def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None):
-    """dw[Cout,Cin,R,S] (fp32) += sum_pixels dz (x) x ; dz [N,Ho,Wo,>=Cout], x [N,Hin,Win,>=Cin]."""
+def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None, scratch=None):
+    """dw[Cout,Cin,R,S] (fp32) += sum_pixels dz (x) x ; dz [N,Ho,Wo,>=Cout], x [N,Hin,Win,>=Cin].
+    scratch: zeroed fp32 [R*S, Cout, round_up(Cin, 16)] -- accumulate there instead (dw untouched until
+    wgrad_unscratch)."""
     n, ho, wo, _, dz_ld = _nhwc_meta(dz)
     n2, hin, win, _, x_ld = _nhwc_meta(x)
     cout, cin = dw.shape[0], dw.shape[1]
@@ -209,9 +211,14 @@ def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None):
     call("b200_conv_wgrad",
         ptr(dz), c_int(dz_ld), c_int(0), c_int(cout), c_int(n), c_int(ho), c_int(wo),
         ptr(x), c_int(x_ld), c_int(0), c_int(cin), c_int(hin), c_int(win),
-        c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), c_int(tune), stream(),
+        c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), ptr(scratch),
+        c_int(0 if scratch is None else scratch.shape[2]), c_int(tune), stream(),
         flops=2.0 * n * ho * wo * r * s * cout * cin, tag="px%d co%d ci%d taps%d s%d" % (n * ho * wo, cout, cin, r * s, stride))
     return dw
+
+
+def wgrad_unscratch(scratch_base, dw_base, table, n_layers):
+    call("b200_wgrad_unscratch", ptr(scratch_base), ptr(dw_base), ptr(table), c_int(n_layers), stream())
 
 
 # ------------------------------------------------------------------ metrics

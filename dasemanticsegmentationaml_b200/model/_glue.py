@@ -98,9 +98,14 @@ class _ModuleFunction(torch.autograd.Function):
         object.__setattr__(ctx.module, "_b200_dirty", True)  # an optimizer step is about to follow
         dev = next(d.device for d in douts if d is not None)
         ops.ARENA.begin((id(ctx.module), "b", tuple(d is not None for d in douts), any(needs_p)), dev)
+        ops.WSCRATCH.begin((id(ctx.module), "b", tuple(d is not None for d in douts), any(needs_p)), dev)
         ops.REDUCER.begin(any(needs_p), dev)
         try:
             dins, grads = ctx.module._bwd_api(ctx.saved, *douts, need_dx=any(needs_in), need_dw=any(needs_p))
+            ops.WSCRATCH.end()  # one launch: tap-major weight-gradient scratch -> PyTorch-layout gradients
+        except BaseException:
+            ops.WSCRATCH.end(ok=False)
+            raise
         finally:
             ops.REDUCER.end()   # exchanges what is left of this backward's gradient span (world > 1)
             ops.ARENA.end()

@@ -176,6 +176,7 @@ class _GradReducer(object):
         if key not in self.streams:
             self.streams[key] = torch.cuda.Stream(device=dev)
         comm, main = self.streams[key], torch.cuda.current_stream(dev)
+        WSCRATCH.flush()   # gradients accumulated in tap-major scratch become final first
         view = chunk[lo:hi]
         comm.wait_stream(main)
         with torch.cuda.stream(comm):
@@ -278,10 +279,88 @@ def conv_dgrad(dz, weight, stride, pad, hin, win, mask=None, mask_slope=0.0, dbi
     return dx
 
 
+class _WgradScratch(object):
+    """Tap-major scratch accumulators of the multi-tap weight gradients of ONE module backward.
+
+    The split-K partials of a 3x3 / 4x4 layer land in dW[co][ci][rs] 4*RS bytes apart: 16 scalar
+    atomics per thread and chunk (0.8 ms of a 15.3 ms step).  Inside a module backward they are
+    accumulated instead into scratch[rs][co][ci] (16-byte vector reductions) carved from a second
+    zero arena, and ONE launch at the end of the backward permutes every layer into its dW.  That
+    launch addresses the layers by their offsets inside the two arena chunks -- stable once the
+    arenas know their size (from the fourth eager step of a kind on) -- so its table is uploaded
+    during the eager warm-up and never inside a CUDA-graph capture (a capture taken earlier simply
+    keeps the scalar-atomic path)."""
+
+    def __init__(self):
+        self.arena = _ZeroArena()
+        self.depth = 0
+        self.pending = []
+        self.tables = {}
+        self.tag = None
+        self.seen = {}        # tag -> the row sets flushed during the previous backward of that kind
+        self.stable = {}      # tag -> the last two backwards of that kind flushed identical row sets
+        self.flushed = []
+
+    def begin(self, tag, device):
+        self.arena.begin(tag, device)
+        self.depth += 1
+        self.pending, self.flushed, self.tag = [], [], tag
+
+    def request(self, dw, cout, cin, rs):
+        """-> scratch tensor or None (not inside a module backward / arenas not settled / thin layer)."""
+        if self.depth == 0 or rs == 1 or cin <= 32 or not ARENA.stack:
+            return None
+        dchunk = ARENA.stack[-1][2]
+        if dchunk is None or self.arena.hint.get(self.tag) is None:
+            return None
+        if torch.cuda.is_current_stream_capturing() and not self.stable.get(self.tag):
+            return None          # layout not settled yet (needs 4 eager steps): no table upload inside a capture
+        ci_pad = (cin + 15) // 16 * 16
+        sc = self.arena.zeros((rs, cout, ci_pad), dw.device)
+        schunk = self.arena.stack[-1][2]
+        d_off = (dw.data_ptr() - dchunk.data_ptr()) // 4
+        s_off = (sc.data_ptr() - schunk.data_ptr()) // 4
+        if not (0 <= d_off and d_off + dw.numel() <= dchunk.numel() and 0 <= s_off and s_off + sc.numel() <= schunk.numel()):
+            return None
+        if self.pending and (self.pending[0][0] is not schunk or self.pending[0][1] is not dchunk):
+            self.flush()         # an arena grew mid-backward: close the batch of the old chunks
+        self.pending.append((schunk, dchunk, (s_off, d_off, cout, cin, rs, ci_pad)))
+        return sc
+
+    def flush(self):
+        """Permute the scratch accumulators gathered so far into their gradients (one launch).  Also
+        called by REDUCER.hook(): a gradient span must be final before it is exchanged."""
+        if not self.pending:
+            return
+        schunk, dchunk = self.pending[0][0], self.pending[0][1]
+        rows = tuple(p[2] for p in self.pending)
+        tab = self.tables.get(rows)
+        if tab is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise K._lib.B200Error("weight-gradient scratch layout changed inside a CUDA-graph capture: "
+                                       "run the step eagerly (three times) before capturing")
+            tab = self.tables[rows] = torch.tensor(rows, dtype=torch.int64).to(schunk.device)
+        K.wgrad_unscratch(schunk, dchunk, tab, len(rows))
+        self.flushed.append(rows)
+        self.pending = []
+
+    def end(self, ok=True):
+        if ok:
+            self.flush()
+            self.stable[self.tag] = bool(self.flushed) and self.flushed == self.seen.get(self.tag)
+            self.seen[self.tag] = self.flushed
+        self.pending = []
+        self.depth -= 1
+        self.arena.end()
+
+
+WSCRATCH = _WgradScratch()
+
+
 def conv_wgrad(dz, x, weight, stride, pad):
     cout, cin, r, s = weight.shape
     dw = zeros_f32((cout, cin, r, s), dz.device)
-    K.conv_wgrad(dz, x, dw, r, s, stride, pad)
+    K.conv_wgrad(dz, x, dw, r, s, stride, pad, scratch=WSCRATCH.request(dw, cout, cin, r * s))
     return dw
 
 

@@ -85,7 +85,16 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
  * tune: 0 = automatic, else ci-tile | (stages << 12) | (pixel splits << 16) | (K pixels / 64 << 28). */
 int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int Ho, int Wo,
                     const void* x, int x_ld, int x_coff, int Cin, int Hin, int Win, int n_taps,
-                    const int* taps, int RS, int in_stride, float* dw, int tune, cudaStream_t stream);
+                    const int* taps, int RS, int in_stride, float* dw, float* scratch, int ci_pad, int tune,
+                    cudaStream_t stream);
+/* scratch (optional, Cin > 32): zeroed fp32 [RS][Cout][ci_pad], ci_pad = round_up(Cin, 16).  The split-K
+ * partial sums are then accumulated there with 16-byte vector reductions (tap-major layout: a
+ * thread's 16 input channels are contiguous) and dw is NOT touched; b200_wgrad_unscratch afterwards
+ * writes dw[co][ci][rs] = scratch[rs][co][ci] for all layers of a module backward in one launch
+ * (table_dev: int64 [n_layers][6] = {scratch offset, dw offset in floats from the two base
+ * pointers, Cout, Cin, RS, ci_pad}). */
+int b200_wgrad_unscratch(const float* scratch_base, float* dw_base, const int64_t* table_dev, int n_layers,
+                         cudaStream_t stream);
 
 /* Stem ConvX(3, 32, 3, 2) (stdcnet.py:171, 6-15): K = 27 is too thin for a tap-by-tap implicit GEMM,
  * so the fp32 NCHW image is unfolded ONCE into bf16 rows col[n, ho, wo, k], k = ci*9 + r*3 + s

@@ -197,3 +197,31 @@ def test_fused_optimizers_match_torch(cuda_lib, kind):
         again.step()
         for a, b in zip(ref_p, our_p):
             assert torch.allclose(a, b, rtol=2e-5, atol=1e-6), (kind, "reloaded", a.shape)
+
+
+def test_weight_gradient_scratch_path_matches_plain_atomics(cuda_lib):
+    """From its second backward on a module accumulates its multi-tap weight gradients in tap-major
+    scratch (vector reductions) and permutes them with one launch; the result must equal the plain
+    scalar-atomic path of the first backward (same inputs) up to fp32 summation order."""
+    from dasemanticsegmentationaml_b200 import ops
+    from dasemanticsegmentationaml_b200.model.stdcnet import CatBottleneck
+    torch.manual_seed(5)
+    m = CatBottleneck(128, 256, 4, 2).to(DEV).train()
+    x = torch.randn(2, 128, 32, 64, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = None
+    runs = []
+    for it in range(4):
+        for p in m.parameters():
+            p.grad = None
+        y = m(x)
+        if dy is None:
+            dy = torch.randn_like(y)
+        y.backward(dy)
+        runs.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None and p.dim() == 4})
+    tag_rows = [rows for rows in ops.WSCRATCH.seen.values() if rows]
+    assert tag_rows, "the scratch path was never taken"
+    n_scratch = max(sum(len(r) for r in rows) for rows in tag_rows)
+    assert n_scratch >= 3          # the three 3x3 convs with Cin > 32
+    for n, g0 in runs[0].items():
+        for later in runs[1:]:
+            assert rel_l2(later[n], g0) < 1e-5, (n, rel_l2(later[n], g0))
