@@ -29,7 +29,7 @@ x = torch.randn(4, 3, 256, 512, generator=g).to(dev)
 lab = torch.randint(0, 19, (4, 256, 512), generator=g).to(dev)
 params = list(m.parameters()) + list(d.parameters())
 ok = True
-for it in range(3):
+for it in range(4):
     for p in params:
         p.grad = None
     ops.REDUCER.snapshots = []
