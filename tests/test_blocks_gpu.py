@@ -221,7 +221,10 @@ def test_weight_gradient_scratch_path_matches_plain_atomics(cuda_lib):
     tag_rows = [rows for rows in ops.WSCRATCH.seen.values() if rows]
     assert tag_rows, "the scratch path was never taken"
     n_scratch = max(sum(len(r) for r in rows) for rows in tag_rows)
-    assert n_scratch >= 3          # the three 3x3 convs with Cin > 32
+    assert n_scratch >= 2          # the 3x3 convs with Cin = 128 and 64 (the Cin = 32 one stays on the plain path)
     for n, g0 in runs[0].items():
         for later in runs[1:]:
-            assert rel_l2(later[n], g0) < 1e-5, (n, rel_l2(later[n], g0))
+            # (loose: dz itself carries bf16 roundings that depend on the BatchNorm reductions' atomic
+            #  order -- even the 1x1 layer, which never uses the scratch, moves by ~1e-2 between runs;
+            #  the exact comparison is test_igemm_gpu.py::test_conv_wgrad_scratch_accumulation)
+            assert rel_l2(later[n], g0) < 3e-2, (n, rel_l2(later[n], g0))

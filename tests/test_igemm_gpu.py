@@ -155,3 +155,41 @@ def test_conv_wgrad_thin_input_all_taps(cuda_lib, case):
     torch.cuda.synchronize()
     err = rel_l2(dw, wf.grad)
     assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("case", [(2, 64, 128, 32, 64, 3, 1, 1), (2, 128, 256, 64, 96, 4, 2, 1), (1, 72, 40, 33, 47, 3, 1, 1),
+                                  (2, 256, 64, 16, 32, 3, 2, 1)])
+def test_conv_wgrad_scratch_accumulation(cuda_lib, case):
+    """Tap-major scratch accumulation (16-byte vector reductions) + b200_wgrad_unscratch against the
+    scalar-atomic path on identical operands and against torch; two layers share one un-scratch
+    launch through the offset table, as a module backward does."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = case
+    x, wgt = make_case(*case)
+    wf = wgt.clone().requires_grad_(True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wf, stride=stride, padding=pad)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    dz = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+    y.backward(dz.float())
+    dz_nhwc = dz.permute(0, 2, 3, 1).contiguous()
+    plain = torch.zeros_like(wgt)
+    K.conv_wgrad(dz_nhwc, x, plain, r, r, stride, pad)
+    ci_pad = (cin + 15) // 16 * 16
+    per = r * r * cout * ci_pad
+    sbase = torch.zeros(2 * per + 64, device="cuda")           # two "layers" in one scratch chunk
+    dbase = torch.full((2 * wgt.numel() + 32,), float("nan"), device="cuda")
+    rows = []
+    for i in range(2):
+        s_off, d_off = i * (per + 64), i * (wgt.numel() + 32)
+        sc = sbase[s_off:s_off + per].view(r * r, cout, ci_pad)
+        dw = dbase[d_off:d_off + wgt.numel()].view_as(wgt)
+        K.conv_wgrad(dz_nhwc, x, dw, r, r, stride, pad, scratch=sc)
+        rows.append((s_off, d_off, cout, cin, r * r, ci_pad))
+    assert torch.isnan(dbase).all()                              # dw is untouched until the permute
+    K.wgrad_unscratch(sbase, dbase, torch.tensor(rows, dtype=torch.int64).cuda(), 2)
+    torch.cuda.synchronize()
+    for s_off, d_off, *_ in rows:
+        dw = dbase[d_off:d_off + wgt.numel()].view_as(wgt)
+        assert rel_l2(dw, plain) < 1e-5, rel_l2(dw, plain)
+        assert rel_l2(dw, wf.grad) < 1e-3
+    assert torch.isnan(dbase[wgt.numel():wgt.numel() + 32]).all()   # nothing written between the layers
