@@ -12,8 +12,8 @@ from . import kernels as K
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-# when True the packed-filter cache is bypassed (needed while capturing CUDA graphs: the captured
-# graph must contain the repacking kernels because the fp32 masters change between replays)
+# debugging aid: when True every filter is re-packed on every use (the normal policy is in
+# refresh_packs: always in training mode and after any backward, otherwise on version change)
 FORCE_REPACK = False
 
 
@@ -90,10 +90,6 @@ def refresh_packs(module, force=False):
 def invalidate_packs(module):
     """Force the next forward of `module` to re-pack every filter (after editing weights in place)."""
     object.__setattr__(module, "_b200_dirty", True)
-
-
-def clear_caches():
-    pass
 
 
 class _ZeroArena(object):
