@@ -169,3 +169,62 @@ def test_input_tables_match_oracle():
     lut = D.label_table(D.GTA5_ID_TO_TRAINID).numpy()
     ids = np.arange(256, dtype=np.uint8)
     assert np.array_equal(lut, I.convert_labels(ids, {k: v for k, v in D.GTA5_ID_TO_TRAINID.items() if k >= 0}))
+
+
+def test_dataset_classes_discover_and_decode_like_the_reference(tmp_path):
+    """Host half of the input pipeline (no GPU): directory layouts, sorting / pairing, the 'color'
+    label files being skipped (cityscapes.py:37-57), decoded uint8 items, collate_raw, aug_type."""
+    from PIL import Image
+    from dasemanticsegmentationaml_b200 import dataset as D
+    rng = np.random.default_rng(1)
+    cs = tmp_path / "cs"
+    want = {}
+    for city, names in (("bern", ["b_2", "b_1"]), ("aachen", ["a_1"])):
+        (cs / "images" / "train" / city).mkdir(parents=True)
+        (cs / "gtFine" / "train" / city).mkdir(parents=True)
+        for nm in names:
+            img = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+            lab = rng.integers(0, 19, (20, 30), dtype=np.uint8)
+            Image.fromarray(img).save(str(cs / "images" / "train" / city / (nm + "_leftImg8bit.png")))
+            Image.fromarray(lab).save(str(cs / "gtFine" / "train" / city / (nm + "_gtFine_labelTrainIds.png")))
+            Image.fromarray(img).save(str(cs / "gtFine" / "train" / city / (nm + "_gtFine_color.png")))
+            want[nm] = (img, lab)
+    (cs / "images" / "train" / "notes.txt").write_text("not a city")
+    ds = D.CityScapes("train", str(cs), 16, 32)
+    assert len(ds) == 3
+    order = [os.path.basename(p).split("_leftImg8bit")[0] for p, _ in ds.data]
+    assert order == ["a_1", "b_1", "b_2"]                      # sorted full paths, as the reference pairs them
+    for i, nm in enumerate(order):
+        assert nm in os.path.basename(ds.data[i][1])
+        img, lab = ds[i]
+        assert img.dtype == torch.uint8 and lab.dtype == torch.uint8
+        assert np.array_equal(img.numpy(), want[nm][0]) and np.array_equal(lab.numpy(), want[nm][1])
+    imgs, labs = D.collate_raw([ds[0], ds[1]])
+    assert imgs.shape == (2, 20, 30, 3) and labs.shape == (2, 20, 30)
+    other = (torch.zeros(10, 12, 3, dtype=torch.uint8), torch.zeros(10, 12, dtype=torch.uint8))
+    imgs, labs = D.collate_raw([ds[0], other])
+    assert isinstance(imgs, list) and len(labs) == 2            # mixed source sizes stay a list
+    assert (ds.preprocess.out_w, ds.preprocess.out_h) == (16, 32)   # the reference's (height, width) -> PIL (w, h)
+    gta = tmp_path / "gta"
+    (gta / "images").mkdir(parents=True)
+    (gta / "labels").mkdir()
+    Image.fromarray(want["a_1"][0]).save(str(gta / "images" / "00001.png"))
+    Image.fromarray(want["a_1"][1]).save(str(gta / "labels" / "00001.png"))
+    g = D.GtaV(str(gta), None, 16, 32)
+    assert len(g) == 1 and g.lb_map[7] == 0 and g.lb_map[33] == 18 and g.lb_map[0] == 255
+    assert torch.equal(g.convert_labels(torch.tensor([7, 0, 33, 200], dtype=torch.uint8)),
+                       torch.tensor([0, 255, 18, 200], dtype=torch.uint8))
+    with pytest.raises(NotImplementedError):
+        D.GtaV(str(gta), "H-RP", 16, 32)
+
+
+def test_fused_optimizers_refuse_cpu_parameters():
+    from dasemanticsegmentationaml_b200 import optim as B200Optim
+    from dasemanticsegmentationaml_b200._lib import B200Error
+    p = torch.nn.Parameter(torch.ones(4))
+    p.grad = torch.ones(4)
+    for opt in (B200Optim.FusedSGD([p], lr=0.1, momentum=0.9), B200Optim.FusedAdam([p], lr=0.1)):
+        with pytest.raises(B200Error):
+            opt.step()
+    with pytest.raises(ValueError):
+        B200Optim.FusedSGD([p], lr=0.1, nesterov=True)
