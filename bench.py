@@ -404,7 +404,7 @@ def run_b200(args):
         if conv and conv[0]["ms"] > 0:
             c = conv[0]
             ach = c["flops"] / (c["ms"] / 1e3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel (forward + data-gradient launches)",
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_igemm_persistent_kernel (forward + data-gradient launches)",
                                 "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                                 "frac": ach / peaks["tf_sustained"], "traffic": conv_traffic(args.workload),
                                 "traffic_source": "profiles/r1_conv_traffic.json (ncu dram__bytes_read+write per launch, da_dense step)",
