@@ -60,6 +60,23 @@ count_equal_kernel(const LabelT* __restrict__ a, const PredT* __restrict__ b, in
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
+// Same per image: out[blockIdx.y] += #(pred == label) over that image's `per_image` positions (the
+// evaluation loop keeps one counter per image so that the host reproduces the reference's
+// mean of per-image ratios, train.py:50,56, with ONE device->host copy per evaluation).
+template <typename LabelT, typename PredT>
+__global__ void __launch_bounds__(256)
+count_equal_batched_kernel(const LabelT* __restrict__ a, const PredT* __restrict__ b, int64_t per_image,
+                           unsigned long long* __restrict__ out) {
+  const LabelT* ai = a + (int64_t)blockIdx.y * per_image;
+  const PredT* bi = b + (int64_t)blockIdx.y * per_image;
+  unsigned long long local = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += stride)
+    local += ((long long)ai[i] == (long long)bi[i]) ? 1ull : 0ull;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out + blockIdx.y, local);
+}
+
 static int hist_grid(int64_t count) {
   int64_t blocks = (count + kHistThreads * 16 - 1) / (kHistThreads * 16);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -109,6 +126,25 @@ int b200_count_equal(const void* label, int label_bytes, const void* pred, int p
   else
     return set_error(B200_EINVAL, "count_equal: unsupported element sizes %d/%d", label_bytes, pred_bytes);
   return check_launch("count_equal");
+}
+
+int b200_count_equal_batched(const void* label, int label_bytes, const void* pred, int pred_bytes,
+                             int n_images, int64_t per_image, int64_t* out, cudaStream_t stream) {
+  if (n_images <= 0 || per_image <= 0) return B200_OK;
+  if (n_images > 65535) return set_error(B200_EINVAL, "count_equal_batched: at most 65535 images per call");
+  int gx = hist_grid(per_image);
+  if (gx > 148 * 2) gx = 148 * 2;
+  const dim3 grid(gx, n_images);
+  unsigned long long* o = reinterpret_cast<unsigned long long*>(out);
+  if (label_bytes == 8 && pred_bytes == 8)
+    count_equal_batched_kernel<int64_t, int64_t><<<grid, 256, 0, stream>>>(static_cast<const int64_t*>(label), static_cast<const int64_t*>(pred), per_image, o);
+  else if (label_bytes == 8 && pred_bytes == 1)
+    count_equal_batched_kernel<int64_t, uint8_t><<<grid, 256, 0, stream>>>(static_cast<const int64_t*>(label), static_cast<const uint8_t*>(pred), per_image, o);
+  else if (label_bytes == 1 && pred_bytes == 1)
+    count_equal_batched_kernel<uint8_t, uint8_t><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(label), static_cast<const uint8_t*>(pred), per_image, o);
+  else
+    return set_error(B200_EINVAL, "count_equal_batched: unsupported element sizes %d/%d", label_bytes, pred_bytes);
+  return check_launch("count_equal_batched");
 }
 
 }  // extern "C"

@@ -240,6 +240,17 @@ def count_equal(label, pred, out):
     return out
 
 
+def count_equal_batched(label, pred, out):
+    """out[i] (int64 [N], device) += #(pred[i] == label[i]) for [N, H, W] maps."""
+    n = label.shape[0]
+    assert pred.shape == label.shape and out.numel() == n and out.dtype == torch.int64
+    label, pred = label.contiguous(), pred.contiguous()
+    call("b200_count_equal_batched", ptr(label), c_int(label.element_size()), ptr(pred), c_int(pred.element_size()),
+         c_int(n), c_int64(label.numel() // max(n, 1)), ptr(out), stream(),
+         nbytes=float(label.numel() * (label.element_size() + pred.element_size())), tag="px%d" % label.numel())
+    return out
+
+
 # ------------------------------------------------------------------ BatchNorm / activation passes
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
 

@@ -99,7 +99,7 @@ class _ModuleFunction(torch.autograd.Function):
         dev = next(d.device for d in douts if d is not None)
         ops.ARENA.begin((id(ctx.module), "b", tuple(d is not None for d in douts), any(needs_p)), dev)
         ops.WSCRATCH.begin((id(ctx.module), "b", tuple(d is not None for d in douts), any(needs_p)), dev)
-        ops.REDUCER.begin(any(needs_p), dev)
+        ops.REDUCER.begin(any(needs_p), dev, ctx.params)
         try:
             dins, grads = ctx.module._bwd_api(ctx.saved, *douts, need_dx=any(needs_in), need_dw=any(needs_p))
             ops.WSCRATCH.end()  # one launch: tap-major weight-gradient scratch -> PyTorch-layout gradients

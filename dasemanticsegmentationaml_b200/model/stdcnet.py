@@ -123,8 +123,8 @@ class CatBottleneck(B200Module):
 
 class AddBottleneck(B200Module):
     """STDC module, residual-add variant (reference stdcnet.py:17-64).  The reference never
-    instantiates it (STDCNet813 defaults to type="cat", ContextPath passes no type); parameters and
-    state_dict layout are reproduced, the forward is composed from the same kernels."""
+    instantiates it (STDCNet813 defaults to type="cat", ContextPath passes no type); reachable through
+    ``STDCNet813(type="add")``.  Same kernels as CatBottleneck plus one fused add for the residual."""
 
     def __init__(self, in_planes, out_planes, block_num=3, stride=1):
         super(AddBottleneck, self).__init__()
@@ -148,9 +148,60 @@ class AddBottleneck(B200Module):
         self.out_planes = out_planes
 
     def _fwd(self, x, out=None):
-        raise NotImplementedError(
-            "AddBottleneck is never built by the reference's BiSeNet (type='cat'); only its "
-            "parameters/state_dict layout are provided in this round")
+        """cat(conv_list outputs) + skip(x)   (reference stdcnet.py:49-64)."""
+        n, h, w, _ = x.shape
+        half = self.conv_list[0].conv.out_channels
+        ctx = {}
+        if self.stride == 2:
+            a1, ctx["c0"] = self.conv_list[0]._fwd(x)
+            ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            y = ops.empty_act(n, ho, wo, self.out_planes, x.device)
+            cur, ctx["dw"] = ops.dw_bn_fwd(a1, self.avd_layer[0].weight, bn_tuple(self.avd_layer[1], self.training),
+                                           self.training, out=y[..., :half])
+            # skip = dw3x3 s2 -> BN -> 1x1 conv -> BN (no activation anywhere, stdcnet.py:30-35)
+            s1, ctx["skip_dw"] = ops.dw_bn_fwd(x, self.skip[0].weight, bn_tuple(self.skip[1], self.training), self.training)
+            res, ctx["skip_pw"] = ops.conv_bn_act_fwd(s1, self.skip[2].weight, bn_tuple(self.skip[3], self.training), 1, 0,
+                                                      self.training, act=K.ACT_NONE)
+        else:
+            if x.shape[3] != self.out_planes:
+                raise ValueError("AddBottleneck(stride=1) adds its input to its output: in_planes must equal out_planes")
+            y = ops.empty_act(n, h, w, self.out_planes, x.device)
+            cur, ctx["c0"] = self.conv_list[0]._fwd(x, out=y[..., :half])
+            res = x
+        off = half
+        ctx["tail"] = []
+        for conv in list(self.conv_list)[1:]:
+            c = conv.conv.out_channels
+            cur, cc = conv._fwd(cur, out=y[..., off:off + c])
+            ctx["tail"].append((cc, off, c))
+            off += c
+        return ops.add_acts(y, res, out), ctx
+
+    def _bwd(self, ctx, dy, need_dx=True):
+        grads = {}
+        half = self.conv_list[0].conv.out_channels
+        dnext = None
+        tail = list(self.conv_list)[1:]
+        for conv, (cc, off, c) in zip(reversed(tail), reversed(ctx["tail"])):
+            dnext, g = conv._bwd(cc, dy[..., off:off + c], dnext, True)
+            grads.update(g)
+        if self.stride == 2:
+            da1, dw, _, dg, db = ops.dw_bn_bwd(ctx["dw"], dy[..., :half], dy2=dnext)
+            grads.update({self.avd_layer[0].weight: dw, self.avd_layer[1].weight: dg, self.avd_layer[1].bias: db})
+            dx, g = self.conv_list[0]._bwd(ctx["c0"], da1, None, need_dx)
+            grads.update(g)
+            ds1, dwp, dgp, dbp = ops.conv_bn_act_bwd(ctx["skip_pw"], dy, None, True)
+            grads.update({self.skip[2].weight: dwp, self.skip[3].weight: dgp, self.skip[3].bias: dbp})
+            dxs, dws, _, dgs, dbs = ops.dw_bn_bwd(ctx["skip_dw"], ds1, need_dx=need_dx)
+            grads.update({self.skip[0].weight: dws, self.skip[1].weight: dgs, self.skip[1].bias: dbs})
+            if need_dx:
+                dx = ops.add_acts(dx, dxs)
+        else:
+            dx, g = self.conv_list[0]._bwd(ctx["c0"], dy[..., :half], dnext, need_dx)
+            grads.update(g)
+            if need_dx:
+                dx = ops.add_acts(dx, dy)
+        return dx, grads
 
 
 class STDCNet813(B200Module):

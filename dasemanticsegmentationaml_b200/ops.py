@@ -149,15 +149,38 @@ class _GradReducer(object):
         self.streams = {}
         self.spans = []
         self.snapshots = None   # tests: list that receives (span view, copy of the span before the exchange)
+        self.force = False      # tests: take the overlapped path on a 1-rank NCCL group too
+        self.dropped = 0        # backwards that found accumulated gradients and fell back to the flat exchange
 
     @staticmethod
     def world():
         import torch.distributed as dist
         return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
-    def begin(self, need_dw, device):
+    def begin(self, need_dw, device, params=()):
+        """Called at the top of a module backward.  `params`: the module's parameters.
+
+        The in-place exchange is only valid for the FIRST backward after zero_grad(): autograd then
+        adopts the arena slice as ``p.grad``.  When a parameter already holds a gradient
+        (train_da_step_nni accumulates two backwards per optimizer step, train_nni.py:118-139),
+        autograd will run ``p.grad += new`` on the main stream -- so this backward is not exchanged
+        span by span, the main stream first waits for any exchange still in flight on ``p.grad``, and
+        the spans that hold such gradients are forgotten: ``finish()`` then hands those gradients to
+        the flat all-reduce (averaging an already averaged part again is the identity on it)."""
         import torch.distributed as dist
-        self.active = bool(need_dw) and device.type == "cuda" and self.world() > 1 and dist.get_backend() == "nccl"
+        self.active = bool(need_dw) and device.type == "cuda" and (self.world() > 1 or self.force) and \
+            dist.is_initialized() and dist.get_backend() == "nccl"
+        if not self.active:
+            return
+        held = [p.grad for p in params if p.grad is not None]
+        if held:
+            self.active = False
+            if self.spans:
+                for key, comm in self.streams.items():
+                    torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(comm)
+                ptrs = [g.data_ptr() for g in held]
+                self.spans = [sp for sp in self.spans if not any(sp[0] <= q < sp[1] for q in ptrs)]
+                self.dropped += 1
 
     def hook(self, final=False):
         if not self.active or not ARENA.stack:
@@ -490,7 +513,7 @@ class DwCtx:
     __slots__ = ("x", "weight", "k", "bn", "z", "a", "act", "slope", "has_pool", "bias")
 
 
-def dw_bn_fwd(x, weight, bn, training, pool_out=None, act=K.ACT_NONE, slope=0.0, bias=None):
+def dw_bn_fwd(x, weight, bn, training, pool_out=None, act=K.ACT_NONE, slope=0.0, bias=None, out=None):
     """Depthwise k x k stride-2 conv (+ fused 3x3/s2 average pool of the same input) followed by
     BatchNorm (+act).  With bn=None: conv + bias + act only."""
     n, h, w, c = x.shape
@@ -503,7 +526,7 @@ def dw_bn_fwd(x, weight, bn, training, pool_out=None, act=K.ACT_NONE, slope=0.0,
         z = empty_act(n, ho, wo, c, x.device)
         stats = zeros_f32((2, c), x.device) if training else None
         K.dwconv_s2_fwd(x, k, wflat, bias, z, pool_out, K.ACT_NONE, 0.0, stats)
-        a, ctx.bn = bn_act_fwd(z, stats, bn, training, act, slope)
+        a, ctx.bn = bn_act_fwd(z, stats, bn, training, act, slope, out)
         ctx.z, ctx.a = z, a
         return a, ctx
     a = empty_act(n, ho, wo, c, x.device)
@@ -512,19 +535,20 @@ def dw_bn_fwd(x, weight, bn, training, pool_out=None, act=K.ACT_NONE, slope=0.0,
     return a, ctx
 
 
-def dw_bn_bwd(ctx, dy, dpool=None, need_dx=True):
-    """-> (dx, dW, dbias, dgamma, dbeta)"""
+def dw_bn_bwd(ctx, dy, dpool=None, need_dx=True, dy2=None):
+    """-> (dx, dW, dbias, dgamma, dbeta); dy2: a second gradient of the same output, summed in the
+    BatchNorm backward pass (BatchNorm'd layers only)."""
     dev = dy.device
     c = ctx.x.shape[3]
     dgamma = dbeta = dbias = None
     if ctx.bn is not None:
-        dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy)
+        dz, dgamma, dbeta = bn_act_bwd(ctx.bn, dy, dy2)
         if ctx.bias is not None:
             dbias = zeros_f32((c,), dev)
     else:
         dz = torch.empty(ctx.a.shape, dtype=BF16, device=dev)
         dbias = zeros_f32((c,), dev) if ctx.bias is not None else None
-        K.act_bwd_bias(dy, None, ctx.a, dz, ctx.act, ctx.slope, None)
+        K.act_bwd_bias(dy, dy2, ctx.a, dz, ctx.act, ctx.slope, None)
     dw = zeros_f32((c * ctx.k * ctx.k,), dev)
     K.dwconv_s2_wgrad(dz, ctx.x, ctx.k, dw, dbias)
     dx = None
@@ -535,9 +559,10 @@ def dw_bn_bwd(ctx, dy, dpool=None, need_dx=True):
 
 
 # --------------------------------------------------------------------------- small helpers
-def add_acts(a, b):
+def add_acts(a, b, out=None):
     """a + b for two NHWC bf16 views of the same shape (gradient joins of branching features)."""
-    out = torch.empty(a.shape, dtype=BF16, device=a.device)
+    if out is None:
+        out = torch.empty(a.shape, dtype=BF16, device=a.device)
     K.scale_add_bcast(a, None, 1.0, None, 0.0, b, out)
     return out
 

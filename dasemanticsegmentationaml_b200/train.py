@@ -176,21 +176,51 @@ def eval_batch(model, images, labels, n_classes=19, hist=None, pred_dtype=torch.
     return hist, pred
 
 
-def val(model, batches, n_classes=19):
-    """Evaluation loop (train.py:24-61): (mean pixel precision, mIoU).  ``batches`` yields
-    (images, labels) CUDA tensors; the confusion matrix is summed over ranks with NCCL."""
+def _val_batch(model, images, labels, n_classes, hist):
+    """One evaluation batch on the device -> (hist, per-image count of pred == label, int64 [N])."""
+    from . import kernels as K
+    hist, pred = eval_batch(model, images, labels, n_classes, hist)
+    lab = labels[:, 0] if labels.dim() == 4 else labels
+    if lab.dtype != torch.int64:
+        lab = lab.long()
+    correct = torch.zeros(images.shape[0], dtype=torch.int64, device=images.device)
+    K.count_equal_batched(lab, pred, correct)
+    return hist, correct
+
+
+def val(model, batches, n_classes=19, device=None):
+    """Evaluation loop (train.py:24-61): (mean pixel precision, mIoU).
+
+    ``batches`` yields (images, labels) CUDA tensors -- this rank's shard of the evaluation set.  The
+    confusion matrix and the per-image hit counts stay on the device for the whole loop (one
+    device->host copy at the end, no per-image ``.item()``); with several ranks the int64 matrix is
+    summed over them (NCCL all-reduce; BASELINE config 5) and the precision is the mean over ALL ranks'
+    images, so every rank returns the same pair.  An empty shard contributes a zero matrix.
+    ``precision`` reproduces the reference's arithmetic: ``float(count) / float(total)`` per image
+    (utils.py:151-159), then ``np.mean`` (train.py:56)."""
     hist = None
-    precisions = []
+    counts, totals = [], []
     for images, labels in batches:
-        hist, pred = eval_batch(model, images, labels, n_classes, hist)
-        lab = labels[:, 0] if labels.dim() == 4 else labels
-        for i in range(images.shape[0]):
-            precisions.append(compute_global_accuracy(pred[i], lab[i]))
+        hist, correct = _val_batch(model, images, labels, n_classes, hist)
+        counts.append(correct)
+        totals += [int(labels[0].numel())] * int(labels.shape[0])
+        device = hist.device
+    if hist is None:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        hist = torch.zeros(n_classes * n_classes, dtype=torch.int64, device=device)
+    ratios = [float(c) / float(t) for c, t in zip(torch.cat(counts).tolist(), totals)] if counts else []
+    psum = torch.tensor([float(np.sum(ratios)) if ratios else 0.0, float(len(ratios))], dtype=torch.float64, device=device)
     if _world() > 1:
         dist.all_reduce(hist)
+        dist.all_reduce(psum)
+        precision = float(psum[0] / psum[1]) if float(psum[1]) > 0 else float("nan")
+    else:
+        precision = float(np.mean(ratios)) if ratios else float("nan")
     h = hist.cpu().numpy().reshape(n_classes, n_classes).astype(np.float64)
     miou_list = per_class_iu(h)
-    return float(np.mean(precisions)), float(np.mean(miou_list))
+    val.last_hist = hist      # the exact int64 matrix (summed over ranks), for callers that want it
+    return precision, float(np.mean(miou_list))
 
 
 class GraphedStep(object):
@@ -205,8 +235,19 @@ class GraphedStep(object):
     capture-safe (``fused=True``; Adam additionally ``capturable=True``).
     """
 
-    def __init__(self, fn, example_inputs, warmup=3):
+    def __init__(self, fn, example_inputs, warmup=3, optimizers=()):
         self.fn = fn
+        # A replay never runs optimizer.step() on the host again.  optim.FusedSGD / FusedAdam read
+        # their hyper-parameters from device memory (poly_lr_scheduler refreshes it); a torch
+        # optimizer with a Python-float lr bakes the value into the captured kernels' arguments, so
+        # the reference's per-epoch decay (train.py:188-189) would silently stop: refuse that.
+        for opt in optimizers:
+            if hasattr(opt, "refresh_hyperparameters"):
+                continue
+            if any(not torch.is_tensor(g["lr"]) for g in opt.param_groups):
+                raise ValueError("GraphedStep: %s has a float learning rate, which a CUDA graph freezes; build it "
+                                 "with lr=torch.tensor(lr) (capturable) or use optim.FusedSGD / FusedAdam"
+                                 % type(opt).__name__)
         self.static = {k: v.clone() for k, v in example_inputs.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -220,6 +261,16 @@ class GraphedStep(object):
             self.outputs = fn(**self.static)
         from . import optim
         optim.flush_pending()   # pointer tables of optim.FusedSGD / FusedAdam steps inside the graph
+
+    @staticmethod
+    def set_lr(optimizer, lr, group=0):
+        """Change a learning rate so that the next replay uses it (device-resident in both cases)."""
+        g = optimizer.param_groups[group]
+        if torch.is_tensor(g["lr"]):
+            g["lr"].fill_(lr)
+        else:
+            g["lr"] = lr
+            optimizer.refresh_hyperparameters()
 
     def load(self, **inputs):
         """Copy new inputs into the graph's static buffers (device or pinned-host tensors)."""

@@ -17,6 +17,12 @@ def poly_lr_scheduler(optimizer, init_lr, iter, lr_decay_iter=1, max_iter=300, p
     """Polynomial learning-rate decay (reference utils.py:11-26)."""
     lr = init_lr * (1 - iter / max_iter) ** power
     optimizer.param_groups[0]['lr'] = lr
+    # optim.FusedSGD / FusedAdam keep their hyper-parameters in device memory (that is what makes a
+    # step replayable inside a CUDA graph): push the new rate now, so that a GraphedStep replay --
+    # which never runs optimizer.step() on the host again -- trains at the decayed rate
+    refresh = getattr(optimizer, "refresh_hyperparameters", None)
+    if refresh is not None:
+        refresh()
     return lr
 
 

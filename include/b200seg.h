@@ -235,6 +235,11 @@ int b200_fast_hist(const void* label, int label_bytes, const void* pred, int pre
 /* compute_global_accuracy numerator (utils.py:151-159): *out += #(pred == label). */
 int b200_count_equal(const void* label, int label_bytes, const void* pred, int pred_bytes,
                      int64_t count, int64_t* out, cudaStream_t stream);
+/* The same per image, for the evaluation loop (train.py:50,56: precision = mean of the per-image
+ * ratios): out[i] += #(pred == label) over image i's `per_image` positions; label/pred hold n_images
+ * images back to back.  Element sizes 8/8, 8/1 or 1/1. */
+int b200_count_equal_batched(const void* label, int label_bytes, const void* pred, int pred_bytes,
+                             int n_images, int64_t per_image, int64_t* out, cudaStream_t stream);
 
 /* ------------------------------------------------------------------ input pipeline */
 /* pil_loader(path).resize(size, Image.BILINEAR) -> ToTensor() -> Normalize(mean, std)

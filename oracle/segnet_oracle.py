@@ -23,6 +23,18 @@ import torch.nn.functional as F
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
+# Quantisation-matched mode (tests only): the CUDA path stores every conv output and every
+# activation as bf16; with QUANT = True the oracle rounds the same tensors (straight-through in the
+# backward), so that a comparison isolates arithmetic differences from the storage format
+# (SURVEY 8c "quantisation-matched oracle").  Off for the golden-vector tests.
+QUANT = False
+
+
+def _q(x):
+    if not QUANT:
+        return x
+    return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
+
 
 # --------------------------------------------------------------------------- building blocks
 def _bn(sd, prefix, x, training):
@@ -37,8 +49,8 @@ def _bn(sd, prefix, x, training):
 def conv_bn_relu(sd, prefix, x, stride, padding, training):
     """ConvX (model/stdcnet.py:6-15) and ConvBNReLU (model/model_stages.py:11-29):
     bias-free conv -> BatchNorm2d -> ReLU."""
-    y = F.conv2d(x, sd[prefix + ".conv.weight"], None, stride, padding)
-    return F.relu(_bn(sd, prefix + ".bn", y, training))
+    y = _q(F.conv2d(x, sd[prefix + ".conv.weight"], None, stride, padding))
+    return _q(F.relu(_bn(sd, prefix + ".bn", y, training)))
 
 
 def cat_bottleneck(sd, prefix, x, out_planes, stride, training, block_num=4):
@@ -48,26 +60,55 @@ def cat_bottleneck(sd, prefix, x, out_planes, stride, training, block_num=4):
     cur = out1
     if stride == 2:
         c = out_planes // 2
-        cur = F.conv2d(out1, sd[prefix + ".avd_layer.0.weight"], None, 2, 1, 1, c)  # stdcnet.py:73-77
-        cur = _bn(sd, prefix + ".avd_layer.1", cur, training)
+        cur = _q(F.conv2d(out1, sd[prefix + ".avd_layer.0.weight"], None, 2, 1, 1, c))  # stdcnet.py:73-77
+        cur = _q(_bn(sd, prefix + ".avd_layer.1", cur, training))
     for idx in range(1, block_num):
         cur = conv_bn_relu(sd, prefix + ".conv_list.%d" % idx, cur, 1, 1, training)
         feats.append(cur)
-    skip = F.avg_pool2d(out1, 3, 2, 1) if stride == 2 else out1  # stdcnet.py:78,108-110
+    skip = _q(F.avg_pool2d(out1, 3, 2, 1)) if stride == 2 else out1  # stdcnet.py:78,108-110
     return torch.cat([skip] + feats, dim=1)
 
 
-def stdcnet813(sd, prefix, x, training):
-    """STDCNet813.forward (model/stdcnet.py:185-194) with layers=[2,2,2], block_num=4, base=64."""
+def add_bottleneck(sd, prefix, x, out_planes, stride, training, block_num=4):
+    """AddBottleneck.forward (model/stdcnet.py:49-64) for block_num=4: the first list entry is the
+    (depthwise-strided) 1x1 output itself, and the skip is x (stride 1) or
+    dw3x3/s2 -> BN -> 1x1 -> BN of x (stride 2, stdcnet.py:30-35)."""
+    cur = conv_bn_relu(sd, prefix + ".conv_list.0", x, 1, 0, training)
+    if stride == 2:
+        c = out_planes // 2
+        cur = _q(F.conv2d(cur, sd[prefix + ".avd_layer.0.weight"], None, 2, 1, 1, c))    # stdcnet.py:24-28
+        cur = _q(_bn(sd, prefix + ".avd_layer.1", cur, training))
+    feats = [cur]
+    for idx in range(1, block_num):
+        cur = conv_bn_relu(sd, prefix + ".conv_list.%d" % idx, cur, 1, 1, training)
+        feats.append(cur)
+    if stride == 2:
+        cin = x.shape[1]
+        skip = _q(F.conv2d(x, sd[prefix + ".skip.0.weight"], None, 2, 1, 1, cin))
+        skip = _q(_bn(sd, prefix + ".skip.1", skip, training))
+        skip = _q(F.conv2d(skip, sd[prefix + ".skip.2.weight"]))
+        skip = _q(_bn(sd, prefix + ".skip.3", skip, training))
+    else:
+        skip = x
+    return _q(torch.cat(feats, dim=1) + skip)
+
+
+def stdcnet813(sd, prefix, x, training, block="cat", use_conv_last=False):
+    """STDCNet813.forward (model/stdcnet.py:185-194) with layers=[2,2,2], block_num=4, base=64;
+    `block` = the constructor's `type` ("cat" is what BiSeNet builds), `use_conv_last` adds the 1x1
+    ConvX on feat32 (stdcnet.py:126,191-192)."""
     f = prefix + ".features"
+    blk = cat_bottleneck if block == "cat" else add_bottleneck
     feat2 = conv_bn_relu(sd, f + ".0", x, 2, 1, training)
     feat4 = conv_bn_relu(sd, f + ".1", feat2, 2, 1, training)
-    feat8 = cat_bottleneck(sd, f + ".2", feat4, 256, 2, training)
-    feat8 = cat_bottleneck(sd, f + ".3", feat8, 256, 1, training)
-    feat16 = cat_bottleneck(sd, f + ".4", feat8, 512, 2, training)
-    feat16 = cat_bottleneck(sd, f + ".5", feat16, 512, 1, training)
-    feat32 = cat_bottleneck(sd, f + ".6", feat16, 1024, 2, training)
-    feat32 = cat_bottleneck(sd, f + ".7", feat32, 1024, 1, training)
+    feat8 = blk(sd, f + ".2", feat4, 256, 2, training)
+    feat8 = blk(sd, f + ".3", feat8, 256, 1, training)
+    feat16 = blk(sd, f + ".4", feat8, 512, 2, training)
+    feat16 = blk(sd, f + ".5", feat16, 512, 1, training)
+    feat32 = blk(sd, f + ".6", feat16, 1024, 2, training)
+    feat32 = blk(sd, f + ".7", feat32, 1024, 1, training)
+    if use_conv_last:
+        feat32 = conv_bn_relu(sd, prefix + ".conv_last", feat32, 1, 0, training)
     return feat2, feat4, feat8, feat16, feat32
 
 
@@ -81,15 +122,17 @@ def attention_refinement(sd, prefix, x, training):
 
 
 def context_path(sd, prefix, x, training):
-    """ContextPath.forward (model/model_stages.py:112-135)."""
-    feat2, feat4, feat8, feat16, feat32 = stdcnet813(sd, prefix + ".backbone", x, training)
+    """ContextPath.forward (model/model_stages.py:112-135).  The optional 1x1 ConvX on feat32
+    (use_conv_last, model_stages.py:98 -> stdcnet.py:191-192) is applied when the state holds its weights."""
+    last = (prefix + ".backbone.conv_last.conv.weight") in sd
+    feat2, feat4, feat8, feat16, feat32 = stdcnet813(sd, prefix + ".backbone", x, training, use_conv_last=last)
     avg = F.avg_pool2d(feat32, feat32.shape[2:])
     avg = conv_bn_relu(sd, prefix + ".conv_avg", avg, 1, 0, training)
     avg_up = F.interpolate(avg, feat32.shape[2:], mode="nearest")
-    feat32_sum = attention_refinement(sd, prefix + ".arm32", feat32, training) + avg_up
+    feat32_sum = _q(attention_refinement(sd, prefix + ".arm32", feat32, training) + avg_up)
     feat32_up = F.interpolate(feat32_sum, feat16.shape[2:], mode="nearest")
     feat32_up = conv_bn_relu(sd, prefix + ".conv_head32", feat32_up, 1, 1, training)
-    feat16_sum = attention_refinement(sd, prefix + ".arm16", feat16, training) + feat32_up
+    feat16_sum = _q(attention_refinement(sd, prefix + ".arm16", feat16, training) + feat32_up)
     feat16_up = F.interpolate(feat16_sum, feat8.shape[2:], mode="nearest")
     feat16_up = conv_bn_relu(sd, prefix + ".conv_head16", feat16_up, 1, 1, training)
     return feat2, feat4, feat8, feat16, feat16_up, feat32_up
@@ -101,7 +144,7 @@ def feature_fusion(sd, prefix, fsp, fcp, training):
     atten = F.avg_pool2d(feat, feat.shape[2:])
     atten = F.relu(F.conv2d(atten, sd[prefix + ".conv1.weight"]))
     atten = torch.sigmoid(F.conv2d(atten, sd[prefix + ".conv2.weight"]))
-    return feat * atten + feat
+    return _q(feat * atten + feat)
 
 
 def seg_head(sd, prefix, x, training):
@@ -128,7 +171,7 @@ def bisenet_forward(sd, x, training=False):
 def fc_discriminator(sd, x, prefix=""):
     """FCDiscriminator.forward (model/discriminator.py:17-28)."""
     for name in ("conv1", "conv2", "conv3", "conv4"):
-        x = F.leaky_relu(F.conv2d(x, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"], 2, 1), 0.2)
+        x = _q(F.leaky_relu(F.conv2d(x, sd[prefix + name + ".weight"], sd[prefix + name + ".bias"], 2, 1), 0.2))
     return F.conv2d(x, sd[prefix + "classifier.weight"], sd[prefix + "classifier.bias"], 2, 1)
 
 
@@ -140,12 +183,12 @@ def dwsep_discriminator(sd, x, batch_norm=False, training=True, prefix=""):
         wd = sd[prefix + "conv%d_d.weight" % i]
         x = F.conv2d(x, wd, sd[prefix + "conv%d_d.bias" % i], 2, 1, 1, wd.shape[0])
         if batch_norm:
-            x = _bn(sd, prefix + "bn%d_d" % i, x, training)
-        x = F.leaky_relu(x, 0.2)
+            x = _bn(sd, prefix + "bn%d_d" % i, _q(x), training)
+        x = _q(F.leaky_relu(x, 0.2))
         x = F.conv2d(x, sd[prefix + "conv%d_p.weight" % i], sd[prefix + "conv%d_p.bias" % i], 1, 1)
         if batch_norm:
-            x = _bn(sd, prefix + "bn%d_p" % i, x, training)
-        x = F.leaky_relu(x, 0.2)
+            x = _bn(sd, prefix + "bn%d_p" % i, _q(x), training)
+        x = _q(F.leaky_relu(x, 0.2))
     return F.conv2d(x, sd[prefix + "classifier.weight"], sd[prefix + "classifier.bias"], 2, 1)
 
 
@@ -353,6 +396,41 @@ def make_bisenet_state(seed=0, n_classes=19, randomize_bn=False):
     for name, cin, mid in (("conv_out", 256, 256), ("conv_out16", 128, 64), ("conv_out32", 128, 64)):
         convx(name + ".conv", cin, mid, 3, False)
         sd[name + ".conv_out.weight"] = _kaiming((n_classes, mid, 1, 1), gen, 1.0)
+    return sd
+
+
+def make_backbone_state(seed=0, block="cat", use_conv_last=False, randomize_bn=True, prefix="bb."):
+    """Random weights for a stand-alone STDCNet813 (no alias keys, no ImageNet head except
+    conv_last when asked): `block` = "cat" | "add" (stdcnet.py:117,119-122)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def convx(name, cin, cout, k):
+        sd[name + ".conv.weight"] = _kaiming((cout, cin, k, k), gen, 0.0, "fan_out")
+        _add_bn(sd, name + ".bn", cout, gen, randomize_bn)
+
+    def blk(name, cin, cout, stride):
+        convx(name + ".conv_list.0", cin, cout // 2, 1)
+        convx(name + ".conv_list.1", cout // 2, cout // 4, 3)
+        convx(name + ".conv_list.2", cout // 4, cout // 8, 3)
+        convx(name + ".conv_list.3", cout // 8, cout // 8, 3)
+        if stride == 2:
+            sd[name + ".avd_layer.0.weight"] = _kaiming((cout // 2, 1, 3, 3), gen, 0.0, "fan_out")
+            _add_bn(sd, name + ".avd_layer.1", cout // 2, gen, randomize_bn)
+            if block == "add":
+                sd[name + ".skip.0.weight"] = _kaiming((cin, 1, 3, 3), gen, 0.0, "fan_out")
+                _add_bn(sd, name + ".skip.1", cin, gen, randomize_bn)
+                sd[name + ".skip.2.weight"] = _kaiming((cout, cin, 1, 1), gen, 0.0, "fan_out")
+                _add_bn(sd, name + ".skip.3", cout, gen, randomize_bn)
+
+    f = prefix + "features"
+    convx(f + ".0", 3, 32, 3)
+    convx(f + ".1", 32, 64, 3)
+    for i, (cin, cout, stride) in enumerate(((64, 256, 2), (256, 256, 1), (256, 512, 2), (512, 512, 1),
+                                             (512, 1024, 2), (1024, 1024, 1))):
+        blk(f + ".%d" % (i + 2), cin, cout, stride)
+    if use_conv_last:
+        convx(prefix + "conv_last", 1024, 1024, 1)
     return sd
 
 

@@ -18,7 +18,13 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+import torch.nn.functional as F
+
 from dasemanticsegmentationaml_b200 import build, kernels as K, train as T
+from tests.tuned_cases import igemm_reference
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, DepthWiseSepFCDiscriminator,
                                                   DepthWiseSepBNFCDiscriminator)
 
@@ -111,12 +117,35 @@ for key, (kind, m) in sorted(records.items()):
             bias = torch.zeros(m["rows"], device=dev) if m["bias"] else None
             kc = 64 if m["cin_pad"] % 64 == 0 else 32
             results = []
+            # fp32 restatement of this launch from its tap tables: a candidate tile configuration is
+            # only timed after its output (and BN statistics) match it
+            ref = igemm_reference(xin, filt, geom)
+            if bias is not None:
+                ref = F.leaky_relu(ref + bias, 0.2)
+            tol = 1e-4 if m["f32"] else 4e-3
 
             def run(tune):
                 K.conv_igemm(xin, filt, out, geom, bias=bias, act=2 if bias is not None else 0, slope=0.2,
                              stats=stats, bn_tile=tune)
 
-            run(0)
+            def correct(tune):
+                obuf.fill_(7.0)
+                if stats is not None:
+                    stats.zero_()
+                run(tune)
+                torch.cuda.synchronize()
+                err = ((out.float() - ref).norm() / (ref.norm() + 1e-12)).item()
+                ok = err < tol
+                if ok and stats is not None:
+                    flat = (ref if m["f32"] else out.float()).reshape(-1, m["rows"])
+                    ok = ((stats[0] - flat.sum(0)).norm() / (flat.sum(0).norm() + 1e-12)).item() < 1e-3 and \
+                        ((stats[1] - (flat * flat).sum(0)).norm() / ((flat * flat).sum(0).norm() + 1e-12)).item() < 1e-3
+                if not ok:
+                    log("   REJECTED (wrong output, rel-L2 %.3g): %s tune=%d" % (err, key, tune))
+                return ok
+
+            if not correct(0):
+                raise RuntimeError("the heuristic configuration itself is wrong")
             base = timeit(lambda: run(0))
             for bn, mt, st, ps in itertools.product((256, 128, 64, 32, 16), (1, 2), (2, 3, 4, 6), (0, 1, 3)):
                 if m["rows"] % bn or bn * mt > 512:
@@ -130,7 +159,8 @@ for key, (kind, m) in sorted(records.items()):
                     continue
                 tune = bn | (mt << 12) | (st << 16) | (ps << 20)
                 try:
-                    run(tune)
+                    if not correct(tune):
+                        continue
                     results.append((timeit(lambda: run(tune)), tune, "BN%d MT%d S%d%s" % (bn, mt, st, {0: "", 1: " P", 3: " PB"}[ps])))
                 except Exception as ex:  # a configuration the launcher rejects
                     continue
@@ -139,11 +169,25 @@ for key, (kind, m) in sorted(records.items()):
             xx = torch.randn(m["n"], m["hin"], m["win"], m["x_ld"], device=dev).to(BF)[..., :m["x_c"]]
             dw = torch.zeros(m["cout"], m["cin"], m["r"], m["s"], device=dev)
             results = []
+            wref = torch.zeros(m["cout"], m["cin"], m["r"], m["s"], device=dev, requires_grad=True)
+            F.conv2d(xx[..., :m["cin"]].float().permute(0, 3, 1, 2), wref, stride=m["stride"], padding=m["pad"]).backward(
+                dz[..., :m["cout"]].float().permute(0, 3, 1, 2))
+            wref = wref.grad
 
             def run(tune):
                 K.conv_wgrad(dz, xx, dw, m["r"], m["s"], m["stride"], m["pad"], tune=tune)
 
-            run(0)
+            def correct(tune):
+                dw.zero_()
+                run(tune)
+                torch.cuda.synchronize()
+                err = ((dw - wref).norm() / (wref.norm() + 1e-12)).item()
+                if err >= 1e-3:
+                    log("   REJECTED (wrong dW, rel-L2 %.3g): %s tune=%d" % (err, key, tune))
+                return err < 1e-3
+
+            if not correct(0):
+                raise RuntimeError("the heuristic configuration itself is wrong")
             base = timeit(lambda: run(0))
             cin64 = (m["cin"] + 63) // 64 * 64
             total_px = m["n"] * m["ho"] * m["wo"]
@@ -157,7 +201,8 @@ for key, (kind, m) in sorted(records.items()):
                     continue
                 tune = bnw | (st << 12) | (sp << 16) | (kp << 28)
                 try:
-                    run(tune)
+                    if not correct(tune):
+                        continue
                     results.append((timeit(lambda: run(tune), 6), tune, "BNW%d S%d split%d kpix%d" % (bnw, st, sp, 64 * kp)))
                 except Exception:
                     continue

@@ -41,3 +41,22 @@ def to_device(sd, device, requires_grad=False):
             t.requires_grad_(True)
         out[k] = t
     return out
+
+
+def gate(name, value, threshold):
+    """Assert value > threshold, printing the measured number so that a GPU run's log records it."""
+    print("GATE %-60s %.6f (> %.4f)" % (name, value, threshold))
+    assert value > threshold, (name, value, threshold)
+
+
+class quantised_oracle(object):
+    """Context manager: oracle stores conv outputs / activations as bf16 like the CUDA path
+    (SURVEY 8c quantisation-matched oracle)."""
+
+    def __enter__(self):
+        from oracle import segnet_oracle as O
+        self._old, O.QUANT = O.QUANT, True
+
+    def __exit__(self, *a):
+        from oracle import segnet_oracle as O
+        O.QUANT = self._old

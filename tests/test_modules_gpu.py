@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import segnet_oracle as O
-from tests.helpers import bf16_round, cosine, load_oracle_state, rel_l2, to_device
+from tests.helpers import bf16_round, cosine, gate, load_oracle_state, quantised_oracle, rel_l2, to_device
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -41,18 +41,21 @@ def test_convx_teacher_forced(cuda_lib, cfg):
     osd = to_device(sd, DEV, True)
     osd["conv.weight"] = bf16_round(osd["conv.weight"]).detach().requires_grad_(True)
     xo = (bf16_round(x) if cin == 3 else xq).clone().requires_grad_(True)
-    yo = O.conv_bn_relu(osd, "", xo, stride, k // 2, True) if False else F.relu(F.batch_norm(
-        F.conv2d(xo, osd["conv.weight"], None, stride, k // 2), osd["bn.running_mean"], osd["bn.running_var"],
-        osd["bn.weight"], osd["bn.bias"], True, 0.1, 1e-5))
+    osd = {"l." + k_: v for k_, v in osd.items()}
+    with quantised_oracle():
+        yo = O.conv_bn_relu(osd, "l", xo, stride, k // 2, True)     # stdcnet.py:13-15
     assert y.shape == yo.shape
     assert rel_l2(y, yo) < 2e-2
     dy = torch.randn(yo.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
     dyq = bf16_round(dy)
     yo.backward(dyq)
     y.backward(dyq.to(y.dtype))
-    assert cosine(m.conv.weight.grad, osd["conv.weight"].grad) > 0.999
-    assert cosine(m.bn.weight.grad, osd["bn.weight"].grad) > 0.999
-    assert cosine(m.bn.bias.grad, osd["bn.bias"].grad) > 0.999
+    osd = {k_[2:]: v for k_, v in osd.items()}
+    gate("convx %s dW" % (cfg,), cosine(m.conv.weight.grad, osd["conv.weight"].grad), 0.999)
+    gate("convx %s dgamma" % (cfg,), cosine(m.bn.weight.grad, osd["bn.weight"].grad), 0.999)
+    gate("convx %s dbeta" % (cfg,), cosine(m.bn.bias.grad, osd["bn.bias"].grad), 0.999)
+    if cin != 3:    # the stem has no data gradient (the image does not require grad, train.py:84)
+        gate("convx %s dX" % (cfg,), cosine(xin.grad, xo.grad), 0.999)
     assert rel_l2(m.bn.running_mean, osd["bn.running_mean"]) < 2e-2
     assert rel_l2(m.bn.running_var, osd["bn.running_var"]) < 2e-2
     assert int(m.bn.num_batches_tracked) == 1
@@ -146,17 +149,20 @@ def test_discriminator_forward_backward(cuda_lib, kind):
     loss.backward()
     osd = to_device(sd, DEV, True)
     po = pq.clone().requires_grad_(True)
-    yo = O.discriminator_forward(kind, osd, po, training=True)
+    with quantised_oracle():
+        yo = O.discriminator_forward(kind, osd, po, training=True)
     loss_o = O.bce_with_logits_const(yo, 0.0)
     loss_o.backward()
     assert y.shape == yo.shape
     print(kind, "out rel-L2", rel_l2(y, yo), "loss", loss.item(), loss_o.item())
     assert rel_l2(y, yo) < 2e-2
     assert abs(loss.item() - loss_o.item()) < 2e-3 * max(1.0, abs(loss_o.item()))
-    # yard-stick: torch's own bf16 autocast on the oracle graph.  Gate = 0.995, or the yard-stick
-    # minus 0.03 where bf16 itself cannot do better (the 8-BatchNorm variant; parameters whose exact
-    # gradient is zero -- a bias or a scale in front of a scale-invariant BatchNorm -- are pure noise
-    # for both and are skipped when the yard-stick is below 0.5).
+    # Gate: the north-star's 0.999 against the quantisation-matched oracle for the dense and the plain
+    # depthwise-separable variants.  Documented exception: the 8-BatchNorm variant,
+    # gated at 0.995 or the yard-stick (torch's own bf16 autocast on the oracle graph) minus 0.03
+    # where bf16 itself cannot do better; parameters whose exact gradient is zero -- a bias or a scale
+    # in front of a scale-invariant BatchNorm -- are pure noise for both and are skipped when the
+    # yard-stick is below 0.5.
     osd2 = to_device(sd, DEV, True)
     po2 = pq.clone().requires_grad_(True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -169,8 +175,9 @@ def test_discriminator_forward_backward(cuda_lib, kind):
             if yard < 0.5:
                 continue
             c = cosine(names[k].grad, v.grad)
-            assert c > min(0.995, yard - 0.03), (k, c, yard)
-    assert cosine(pin.grad, po.grad) > min(0.995, cosine(po2.grad, po.grad) - 0.03)
+            gate("disc %s %s (yard-stick %.4f)" % (kind, k, yard), c, min(0.995, yard - 0.03) if kind == "dwsep_bn" else 0.999)
+    gate("disc %s dX" % kind, cosine(pin.grad, po.grad),
+         min(0.995, cosine(po2.grad, po.grad) - 0.03) if kind == "dwsep_bn" else 0.999)
 
 
 @pytest.mark.parametrize("shape", [(16, 32, 128, 256),    # 8x: strip / tiled fast kernels
@@ -373,18 +380,16 @@ def test_graphed_da_step_matches_eager(cuda_lib, optimizers):
         runs.append(losses)
     print("eager  ", runs[0])
     print("graphed", runs[1])
-    # the first replayed step must agree closely; afterwards the adversarial game amplifies the
-    # run-to-run noise of fp32 atomics (BatchNorm statistics, weight gradients), so later steps are
-    # only required to stay in the same regime
-    for u, v in zip(runs[0][0], runs[1][0]):   # (train-mode gradients carry ~50 % run-to-run atomic-order noise)
+    # Step 1 starts from identical weights and inputs: the replay must reproduce the eager losses up to
+    # the fp32 atomic-order noise of the steps so far (BatchNorm statistics, weight gradients).  Later
+    # steps of the adversarial game amplify that noise chaotically (two EAGER runs differ from each
+    # other by up to 0.3 in the BCE terms at step 5), so only the well-conditioned segmentation loss is
+    # compared there; exact graph-vs-eager equality needs the deterministic mode DESIGN.md lists as open.
+    for u, v in zip(runs[0][0], runs[1][0]):
         assert abs(u - v) < 5e-2 * max(1.0, abs(u)), (runs[0], runs[1])
-    # (two eager runs of this 5-step game differ from each other by as much: observed up to 0.3 in the
-    #  BCE terms at step 5, so the bound is a regime check, not a precision check)
     for a, b in zip(runs[0], runs[1]):
         assert all(np.isfinite(b))
         assert abs(a[0] - b[0]) < 6e-2 * abs(a[0]), (runs[0], runs[1])
-        for u, v in zip(a[1:], b[1:]):
-            assert abs(u - v) < 0.6, (runs[0], runs[1])
     assert runs[1][3][0] != runs[1][0][0]  # the weights do move between replays
 
 

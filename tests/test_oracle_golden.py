@@ -126,3 +126,31 @@ def test_adversarial_step_loops(variant):
             close(sample(sd[key.split(":", 1)[1]], 7), gold[key], rtol=2e-3, atol=2e-6)
         if key.startswith(variant + "_d:"):
             close(sample(dsd[key.split(":", 1)[1]], 7), gold[key], rtol=2e-3, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag,block,last", [("add", "add", False), ("cat_last", "cat", True)])
+def test_backbone_variants_against_reference(tag, block, last):
+    """AddBottleneck (stdcnet.py:17-64) and use_conv_last (stdcnet.py:126,191-192) restatements vs
+    golden vectors of the reference's own STDCNet813(type=..., use_conv_last=...)."""
+    torch.set_num_threads(8)
+    gold = np.load(os.path.join(GOLD, "reference_backbone.npz"))
+
+    def smp(t, step=53):
+        return sample(t, step)
+
+    x = torch.from_numpy(gold["x"])
+    sd = O.clone_state(O.make_backbone_state(seed=17, block=block, use_conv_last=last), requires_grad=True)
+    feats = O.stdcnet813(sd, "bb", x, True, block=block, use_conv_last=last)
+    gw = torch.Generator().manual_seed(22)
+    loss = sum((f * torch.randn(f.shape, generator=gw)).sum() for f in feats)
+    loss.backward()
+    for i, f in enumerate(feats):
+        close(smp(f), gold["%s_feat%d" % (tag, i)])
+    n_grad = 0
+    for key in gold.files:
+        if key.startswith(tag + "_grad:"):
+            close(sample(sd["bb." + key.split(":", 1)[1]].grad, 29), gold[key], rtol=2e-3, atol=1e-5)
+            n_grad += 1
+    assert n_grad >= 6
+    with torch.no_grad():
+        close(smp(O.stdcnet813(sd, "bb", x, False, block=block, use_conv_last=last)[4]), gold["%s_eval_feat4" % tag])
