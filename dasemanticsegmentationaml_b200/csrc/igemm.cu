@@ -533,6 +533,226 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   }
 }
 
+
+// ------------------------------------------------- CTA-pair (cta_group::2) forward / dgrad
+// Same implicit GEMM, executed by CTA PAIRS (a cluster of two CTAs = the two SMs of a TPC): one
+// tcgen05.mma.cta_group::2 covers M = 256 output pixels (CTA rank r owns the 128 pixels of patch
+// rows [h0 + r*th, h0 + (r+1)*th)) x BN channels.  Each CTA streams its own activation tile and only
+// HALF of the filter tile (BN/2 rows) through shared memory -- the tensor cores read the other half
+// from the peer SM -- so per FLOP a CTA pulls (128 + BN/2) rows of operands instead of (128 + BN):
+// the L2->SM fill that bounds the big layers drops by a third at BN = 256.
+// Persistent like conv_igemm_persistent_kernel: pair c keeps filter tile c % n_tiles, TWO TMEM
+// accumulators (tfull / tempty) overlap a tile's epilogue with the next tile's MMAs; the epilogue
+// reads TMEM in 32-column batches (one tcgen05.wait::ld per 32 columns).
+//   leader (even) CTA : arms full[s] with the bytes of BOTH CTAs, issues every MMA, multicasts the
+//                       commits (stage free / accumulator full) to both CTAs
+//   both CTAs         : TMA producer (own A rows, own half of B, signalling the leader's full[s]),
+//                       epilogue of their own 128 rows, arrival on the leader's tempty[buf]
+struct PairBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ ConvParams p, int m_total, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PairBarriers bars;
+  __shared__ float s_stats[2][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 128u * p.KC * 2u;
+  const uint32_t b_half = (uint32_t)(p.BN / 2) * p.KC * 2u;
+  const uint32_t stage_bytes = a_bytes + b_half;
+  const int cin_blocks = p.cin_pad / p.KC;
+  const int my_n = pair % n_tiles;
+  const int m_first = pair / n_tiles, m_step = n_pairs / n_tiles;
+  const uint32_t acc_cols = (uint32_t)p.BN;
+  const uint32_t want = 2u * acc_cols;
+  const uint32_t tmem_cols = want <= 32 ? 32u : (want <= 64 ? 64u : (want <= 128 ? 128u : (want <= 256 ? 256u : 512u)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bars.full[s]), 1);
+      mbar_init(smem_u32(&bars.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bars.tfull[b]), 1);
+      mbar_init(smem_u32(&bars.tempty[b]), 8);  // four epilogue warps of each CTA
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(&bars.tmem_base), tmem_cols);
+    tmem_relinquish_pair();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer (both CTAs)
+    if (lane == 0) {
+      int it = 0;
+      for (int m = m_first; m < m_total; m += m_step) {
+        const TileCoord tc = decode_tile(p, my_n, m);
+        const int h0 = tc.h0 + rank * p.th;
+        for (int t = 0; t < p.n_taps[tc.z]; ++t) {
+          const int hh = h0 * p.in_stride + p.tap_dh[tc.z][t];
+          const int ww = tc.w0 * p.in_stride + p.tap_dw[tc.z][t];
+          const int kb = p.tap_k[tc.z][t] * p.cin_pad;
+          for (int cb = 0; cb < cin_blocks; ++cb, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
+            const uint32_t full = smem_u32(&bars.full[s]);
+            if (leader) mbar_expect_tx(full, 2u * stage_bytes);
+            const uint32_t sa = smem_base + s * stage_bytes;
+            tma_load_4d_pair(sa, &tmA, full, cb * p.KC, ww, hh, tc.n_img);
+            tma_load_2d_pair(sa + a_bytes, &tmB, full, kb + cb * p.KC, tc.n0 + rank * (p.BN / 2));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------- MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, p.BN, 0, 0);
+      const uint32_t layout = (p.KC == 64) ? 2u : 4u;
+      const uint32_t sbo = 8u * p.KC * 2u;
+      const int ksteps = p.KC / 16;
+      int it = 0, lt = 0;
+      for (int m = m_first; m < m_total; m += m_step, ++lt) {
+        const TileCoord tc = decode_tile(p, my_n, m);
+        const int buf = lt & 1;
+        const uint32_t acc = tmem + buf * acc_cols;
+        mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // both epilogues drained it
+        tc_fence_after();
+        const int nk = p.n_taps[tc.z] * cin_blocks;
+        for (int kit = 0; kit < nk; ++kit, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(smem_u32(&bars.full[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, layout);
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
+            umma_f16_pair(acc, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(smem_u32(&bars.empty[s]), 3);   // frees the stage in both CTAs
+        }
+        umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
+      }
+    }
+  } else {
+    // --------------------------------------------------------- epilogue (own 128 rows)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int hl = row / p.tw, wl = row - hl * p.tw;
+    int lt = 0, cur_n0 = -1;
+    for (int m = m_first; m < m_total; m += m_step, ++lt) {
+      const TileCoord tc = decode_tile(p, my_n, m);
+      const int z = tc.z;
+      if (p.stats != nullptr && tc.n0 != cur_n0) {
+        if (cur_n0 >= 0) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int t = threadIdx.x - 64;
+          flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
+          flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int col = t; col < p.BN; col += 128) {
+            s_stats[0][col] = 0.f;
+            s_stats[1][col] = 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        cur_n0 = tc.n0;
+      }
+      const int buf = lt & 1;
+      const uint32_t acc = tmem + buf * acc_cols;
+      mbar_wait(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1);
+      tc_fence_after();
+      const int h = tc.h0 + rank * p.th + hl, w = tc.w0 + wl;
+      const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+      const size_t pix =
+          ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
+      const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hv = 0; hv < 2; ++hv) {
+          const int cc = c + 16 * hv;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(r[16 * hv + j]);
+            if (p.bias != nullptr) x += __ldg(p.bias + tc.n0 + cc + j);
+            v[j] = apply_act(x, p.act, p.slope);
+          }
+          if (p.mask != nullptr && valid)
+            apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + tc.n0 + cc, p.mask_slope, p.wide);
+          if (valid) store16(p, obase + cc, v);
+          if (p.stats != nullptr) {
+            float s1[16], s2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]))) : 0.f;
+              s1[j] = x;
+              s2[j] = x * x;
+            }
+            const float t1 = column_sums16(s1, lane);
+            const float t2 = p.stats_sum_only ? 0.f : column_sums16(s2, lane);
+            if ((lane & 1) == 0) {
+              const int col = cc + column_of_lane(lane);
+              atomicAdd(&s_stats[0][col], t1);
+              if (!p.stats_sum_only) atomicAdd(&s_stats[1][col], t2);
+            }
+          }
+        }
+      }
+      // this warp is done with the buffer: tell the leader's MMA warp (count 8 = both CTAs)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(smem_u32(&bars.tempty[buf]));
+    }
+    if (p.stats != nullptr && cur_n0 >= 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;
+      flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
+      flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
+    }
+  }
+
+  // neither CTA may leave (or free TMEM) while the peer can still read its shared memory, write its
+  // TMEM or signal its barriers
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem, tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------ wgrad
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmX,
@@ -970,9 +1190,38 @@ static int ensure_smem_optin() {
     e = cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_alltaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e != cudaSuccess) return set_error(B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   g_smem_optin_done = 1;
   return B200_OK;
+}
+
+// CTA pairs that can be resident at once (one CTA per SM at these shared-memory sizes: 74 TPCs on a
+// B200); asked of the driver once per shared-memory size class, 74 if the query fails.
+static int max_active_pairs(size_t smem) {
+  static int cached[2] = {0, 0};
+  const int cls = smem > 110 * 1024 ? 1 : 0;
+  if (cached[cls] > 0) return cached[cls];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * 148, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, conv_igemm_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    n = 74;
+  }
+  cached[cls] = n;
+  return n;
 }
 
 }  // namespace b200
@@ -1010,7 +1259,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
                     int stats_sum_only, int tune, cudaStream_t stream) {
   // tune = BN | (mt << 12) | (stages << 16); a zero field = choose automatically
   // (bit 20: persistent kernel)
-  const int bn_override = tune & 0xFFF, mt_override = (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
+  // (bit 22: CTA-pair kernel, cta_group::2 -- implies two 128-pixel sub-tiles, one per CTA)
+  const int pair_mode = (tune >> 22) & 1;
+  const int bn_override = tune & 0xFFF, mt_override = pair_mode ? 2 : (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
   if (n_classes < 1 || n_classes > kMaxClasses) return set_error(B200_EINVAL, "conv_igemm: bad class count %d", n_classes);
   if (cin_pad % 32) return set_error(B200_EINVAL, "conv_igemm: cin_pad %d not a multiple of 32", cin_pad);
   if (in_ld % 8 || in_coff % 8 || out_ld % 8 || out_coff % 8)
@@ -1131,6 +1382,31 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   }
 
   CUtensorMap tmA, tmB;
+  if (pair_mode) {
+    if (p.mt != 2 || p.BN < 32 || p.BN % 32)
+      return set_error(B200_EINVAL, "conv_igemm: the CTA-pair kernel needs BN in {32, 64, 128, 256} (got %d)", p.BN);
+    const int pstage = 128 * p.KC * 2 + (p.BN / 2) * p.KC * 2;
+    int st = st_override >= 2 ? st_override : (200 * 1024) / pstage;
+    if (st > kMaxStages) st = kMaxStages;
+    while (st > 2 && st * pstage > 216 * 1024) --st;
+    if (st < 2 || st * pstage > 216 * 1024) return set_error(B200_EINVAL, "conv_igemm: pair tile does not fit shared memory");
+    p.stages = st;
+    rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th, in_stride, p.KC * 2);
+    if (rc) return rc;
+    rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN / 2, p.KC * 2);
+    if (rc) return rc;
+    int m_total = 0;
+    for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
+    const int n_tiles = filt_rows / p.BN;
+    const int total_tiles = m_total * n_tiles;
+    const size_t psmem = (size_t)p.stages * pstage + 1024;
+    int pairs = max_active_pairs(psmem);
+    if (pairs > total_tiles) pairs = total_tiles;
+    pairs = (pairs / n_tiles) * n_tiles;      // every pair keeps one filter tile
+    if (pairs < n_tiles) pairs = n_tiles;
+    conv_igemm_pair_kernel<<<2 * pairs, kThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
+    return check_launch("conv_igemm(pair)");
+  }
   rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
   if (rc) return rc;
   rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);

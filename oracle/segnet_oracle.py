@@ -33,6 +33,9 @@ QUANT = False
 def _q(x):
     if not QUANT:
         return x
+    # straight-through: rounding the oracle's gradients as well was tried and LOWERS the agreement
+    # (the CUDA path sums some gradients in fp32 before its single rounding, so the rounding points
+    # do not coincide and the two noises add instead of cancelling)
     return x + (x.detach().to(torch.bfloat16).to(x.dtype) - x.detach())
 
 

@@ -193,3 +193,61 @@ def test_conv_wgrad_scratch_accumulation(cuda_lib, case):
         assert rel_l2(dw, plain) < 1e-5, rel_l2(dw, plain)
         assert rel_l2(dw, wf.grad) < 1e-3
     assert torch.isnan(dbase[wgt.numel():wgt.numel() + 32]).all()   # nothing written between the layers
+
+
+PAIR_CASES = [
+    # n, cin, cout, h, w, r, stride, pad, dgrad
+    (2, 64, 64, 16, 32, 3, 1, 1, False),
+    (2, 64, 128, 16, 32, 1, 1, 0, False),
+    (1, 128, 256, 24, 40, 3, 1, 1, False),       # ragged map: partial tiles, the second CTA's rows run off the map
+    (2, 32, 64, 32, 64, 4, 2, 1, False),         # KC = 32 (64-byte swizzle), stride-2 TMA boxes
+    (8, 256, 256, 64, 128, 3, 1, 1, False),      # BASELINE config-3 conv_out: 256 pair tiles -> persistent loop, both TMEM buffers
+    (4, 128, 256, 32, 64, 4, 2, 1, False),       # discriminator conv3 shape
+    (2, 64, 64, 16, 32, 3, 1, 1, True),
+    (2, 64, 128, 33, 65, 4, 2, 1, True),         # four output-parity classes with different tap lists
+    (8, 128, 64, 64, 128, 4, 2, 1, True),        # discriminator conv2 data gradient (N = 8)
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+@pytest.mark.parametrize("bn", [256, 128, 64, 32])
+def test_conv_pair_kernel(cuda_lib, case, bn):
+    """cta_group::2 kernel (tune bit 22): M = 256 across a CTA pair, each CTA loads half the filter
+    tile.  Against torch fp32 on the same bf16 operands, and bit-identical to the one-CTA kernel."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad, dgrad = case
+    x, wgt = make_case(n, cin, cout, h, w, r, stride, pad)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    if not dgrad:
+        rows = cout
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wgt, stride=stride, padding=pad).permute(0, 2, 3, 1)
+        filt = K.pack_filter(wgt)
+        geom = K.fwd_geometry(h, w, r, r, stride, pad)
+        inp = x
+    else:
+        rows = cin
+        xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        y = F.conv2d(xf, wgt, stride=stride, padding=pad)
+        dz = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
+        y.backward(dz.float())
+        ref = xf.grad.permute(0, 2, 3, 1)
+        filt = K.pack_filter(wgt, transpose=True)
+        geom = K.dgrad_geometry(h, w, r, r, stride, pad)
+        inp = dz.permute(0, 2, 3, 1).contiguous()
+    if filt.shape[0] % bn:
+        pytest.skip("BN does not divide the filter rows")
+    bias = torch.randn(filt.shape[0], device="cuda", generator=g)
+    ref = F.leaky_relu(ref + bias[:rows], 0.2)
+    outs, sts = [], []
+    for word in (bn | (1 << 22), bn | (1 << 22) | (3 << 16), 0):
+        out = torch.full((n, geom["Hout"], geom["Wout"], filt.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
+        stats = torch.zeros(2, filt.shape[0], device="cuda")
+        K.conv_igemm(inp, filt, out, geom, bias=bias, act=2, slope=0.2, stats=stats, bn_tile=word)
+        torch.cuda.synchronize()
+        err = rel_l2(out[..., :rows], ref)
+        assert err < 4e-3, (word, err)
+        flat = out.float().reshape(-1, filt.shape[0])
+        assert rel_l2(stats[0], flat.sum(0)) < 1e-3
+        assert rel_l2(stats[1], (flat * flat).sum(0)) < 1e-3
+        outs.append(out)
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2])
