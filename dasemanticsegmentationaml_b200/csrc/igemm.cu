@@ -179,46 +179,62 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
+    // (lean on purpose, like the MMA loop below: no divisions, barrier addresses by increment)
     if (lane == 0) {
-      int it = 0;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      const int hb = h0 * p.in_stride, wb = w0 * p.in_stride;
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < p.n_taps[z]; ++t) {
-        const int hh = h0 * p.in_stride + p.tap_dh[z][t];
-        const int ww = w0 * p.in_stride + p.tap_dw[z][t];
+        const int hh = hb + p.tap_dh[z][t];
+        const int ww = wb + p.tap_dw[z][t];
         const int kb = p.tap_k[z][t] * p.cin_pad;
-        for (int cb = 0; cb < cin_blocks; ++cb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
-          const uint32_t full = smem_u32(&bars.full[s]);
+        for (int cb = 0; cb < cin_blocks; ++cb) {
+          mbar_wait(empty0 + 8u * s, ph ^ 1u);
+          const uint32_t full = full0 + 8u * s;
           mbar_expect_tx(full, stage_bytes);
           const uint32_t sa = smem_base + s * stage_bytes;
           tma_load_4d(sa, &tmA, full, cb * p.KC, ww, hh, n_img);
           tma_load_2d(sa + a_bytes, &tmB, full, kb + cb * p.KC, n0);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
+    // The tensor pipe queues only about one instruction ahead of the issuing thread, so scalar work
+    // between two tcgen05.mma is idle tensor time: descriptors come from a precomputed template,
+    // stage / phase advance by increment, the next stage's barrier is polled while MMAs execute.
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-      const uint32_t layout = (p.KC == 64) ? 2u : 4u;  // 128B / 64B swizzle
       const uint32_t sbo = 8u * p.KC * 2u;              // 8 rows of KC bf16
+      const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
+      const uint32_t d_hi = (uint32_t)(dtmpl >> 32), d_lo = (uint32_t)dtmpl;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       const int ksteps = p.KC / 16;
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
+      bool ready = false;
       for (int it = 0; it < nk; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&bars.full[s]), ph);
+        if (!ready) mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
+        const uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
+        const uint32_t b_lo = a_lo + (a_bytes >> 4);
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
-          for (int j = 0; j < p.mt; ++j) {
-            const uint64_t da = make_smem_desc(sa + j * a_sub + k * 32, 16, sbo, layout);
-            umma_f16(tmem + j * p.BN, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+          const uint64_t db = ((uint64_t)d_hi << 32) | (b_lo + 2u * k);
+          for (int j = 0; j < p.mt; ++j)
+            umma_f16(tmem + j * p.BN, ((uint64_t)d_hi << 32) | (a_lo + j * (a_sub >> 4) + 2u * k), db, idesc, accum);
+          accum = 1u;
         }
-        umma_commit(smem_u32(&bars.empty[s]));  // frees the stage once these MMAs retire
+        umma_commit(empty0 + 8u * s);  // frees the stage once these MMAs retire
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
+        ready = (it + 1 < nk) && mbar_try_wait(full0 + 8u * s, ph);
       }
       umma_commit(smem_u32(&bars.accum));
     }
@@ -228,7 +244,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;
     const int hl = row / p.tw, wl = row - hl * p.tw;
 
-    mbar_wait(smem_u32(&bars.accum), 0);
+    mbar_wait_warp(smem_u32(&bars.accum), 0, lane);
     tc_fence_after();
     for (int sub = 0; sub < p.mt; ++sub) {
       const int h = h0 + sub * p.th + hl, w = w0 + wl;
@@ -383,7 +399,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      int it = 0;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      int s = 0;
+      uint32_t ph = 0;
       if (b_resident) {
         const uint32_t bf = smem_u32(&bars.bfull);
         mbar_expect_tx(bf, bres_bytes);
@@ -392,31 +410,38 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       }
       for (int m = m_first; m < m_total; m += m_step) {
         const TileCoord tc = decode_tile(p, my_n, m);
+        const int hb = tc.h0 * p.in_stride, wb = tc.w0 * p.in_stride;
         for (int t = 0; t < p.n_taps[tc.z]; ++t) {
-          const int hh = tc.h0 * p.in_stride + p.tap_dh[tc.z][t];
-          const int ww = tc.w0 * p.in_stride + p.tap_dw[tc.z][t];
+          const int hh = hb + p.tap_dh[tc.z][t];
+          const int ww = wb + p.tap_dw[tc.z][t];
           const int kb = p.tap_k[tc.z][t] * p.cin_pad;
-          for (int cb = 0; cb < cin_blocks; ++cb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
-            const uint32_t full = smem_u32(&bars.full[s]);
+          for (int cb = 0; cb < cin_blocks; ++cb) {
+            mbar_wait(empty0 + 8u * s, ph ^ 1u);
+            const uint32_t full = full0 + 8u * s;
             mbar_expect_tx(full, stage_bytes);
             const uint32_t sa = stage_base + s * stage_bytes;
             tma_load_4d(sa, &tmA, full, cb * p.KC, ww, hh, tc.n_img);
             if (!b_resident) tma_load_2d(sa + a_bytes, &tmB, full, kb + cb * p.KC, tc.n0);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // --------------------------------------------------------------- MMA issuer
+    // --------------------------------------------------------------- MMA issuer (lean: see conv_igemm_kernel)
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-      const uint32_t layout = (p.KC == 64) ? 2u : 4u;
       const uint32_t sbo = 8u * p.KC * 2u;
+      const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
+      const uint32_t d_hi = (uint32_t)(dtmpl >> 32), d_lo = (uint32_t)dtmpl;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       const int ksteps = p.KC / 16;
-      int it = 0, lt = 0;
+      int s = 0, lt = 0;
+      uint32_t ph = 0;
+      bool ready = false;
       if (b_resident) mbar_wait(smem_u32(&bars.bfull), 0);
       for (int m = m_first; m < m_total; m += m_step, ++lt) {
         const TileCoord tc = decode_tile(p, my_n, m);
@@ -424,24 +449,29 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // epilogue drained this buffer
         tc_fence_after();
-        const int nk = p.n_taps[tc.z] * cin_blocks;
-        for (int kit = 0; kit < nk; ++kit, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&bars.full[s]), ph);
-          tc_fence_after();
-          const uint32_t sa = stage_base + s * stage_bytes;
-          const uint32_t sb = b_resident
-                                  ? smem_base + (uint32_t)(p.tap_k[tc.z][kit / cin_blocks] * cin_blocks + kit % cin_blocks) * b_bytes
-                                  : sa + a_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
-            for (int j = 0; j < p.mt; ++j) {
-              const uint64_t da = make_smem_desc(sa + j * a_sub + k * 32, 16, sbo, layout);
-              umma_f16(acc + j * p.BN, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
+        const int ntap = p.n_taps[tc.z];
+        uint32_t accum = 0;
+        for (int t = 0; t < ntap; ++t) {
+          const uint32_t bres = smem_base + (uint32_t)(p.tap_k[tc.z][t] * cin_blocks) * b_bytes;
+          for (int cb = 0; cb < cin_blocks; ++cb) {
+            if (!ready) mbar_wait(full0 + 8u * s, ph);
+            tc_fence_after();
+            const uint32_t sa = stage_base + s * stage_bytes;
+            const uint32_t a_lo = d_lo | (sa >> 4);
+            const uint32_t b_lo = d_lo | ((b_resident ? bres + cb * b_bytes : sa + a_bytes) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t db = ((uint64_t)d_hi << 32) | (b_lo + 2u * k);
+              for (int j = 0; j < p.mt; ++j)
+                umma_f16(acc + j * p.BN, ((uint64_t)d_hi << 32) | (a_lo + j * (a_sub >> 4) + 2u * k), db, idesc, accum);
+              accum = 1u;
             }
+            umma_commit(empty0 + 8u * s);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            ready = mbar_try_wait(full0 + 8u * s, ph);
           }
-          umma_commit(smem_u32(&bars.empty[s]));
         }
         umma_commit(smem_u32(&bars.tfull[buf]));
       }
@@ -472,7 +502,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       }
       const int buf = lt & 1;
       const uint32_t acc = tmem + buf * acc_cols;
-      mbar_wait(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1);
+      mbar_wait_warp(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1, lane);
       tc_fence_after();
       for (int sub = 0; sub < p.mt; ++sub) {
         const int h = tc.h0 + sub * p.th + hl, w = tc.w0 + wl;
@@ -534,6 +564,99 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 }
 
 
+
+// ------------------------------------------------------------------ batched epilogue
+// 32 accumulator columns of one output pixel per thread: ONE tcgen05.ld + wait, then bias /
+// activation (branch-free: v > 0 ? v : v * ns with ns = 1 none, 0 ReLU, slope LeakyReLU) / LeakyReLU
+// backward mask / bf16 packing / 256-bit stores.  The BatchNorm column sums go through a per-warp
+// shared-memory transpose instead of shuffles: every lane writes its pixel's 16 values as four
+// 16-byte stores into a [32 rows][16 cols (+4 pad)] tile, then lane (col, half) adds 16 rows of one
+// column (conflict-free both ways) -- ~55 instructions per 16 columns against ~250 for the two
+// 16-value butterflies, which made the epilogue (not the MMAs) the longest phase of a tile.
+constexpr int kTrStride = 20;   // floats per row of the transpose tile
+
+template <bool F32, bool STATS>
+__device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t taddr, bool valid, size_t obase,
+                                                 size_t pix, int gcol, float ns, float* tb, float* s_sum,
+                                                 float* s_sq, int lane) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int hv = 0; hv < 2; ++hv) {
+    const int cc = 16 * hv;
+    float v[16];
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol + cc);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 b = __ldg(b4 + jj);
+        v[4 * jj] = __uint_as_float(r[cc + 4 * jj]) + b.x;
+        v[4 * jj + 1] = __uint_as_float(r[cc + 4 * jj + 1]) + b.y;
+        v[4 * jj + 2] = __uint_as_float(r[cc + 4 * jj + 2]) + b.z;
+        v[4 * jj + 3] = __uint_as_float(r[cc + 4 * jj + 3]) + b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[cc + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * ns;
+    if (p.mask != nullptr && valid)
+      apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + gcol + cc, p.mask_slope, p.wide);
+    float x[16];
+    if (F32) {
+      if (valid) store16(p, obase + cc, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = valid ? v[j] : 0.f;
+    } else {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      if (valid) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
+        if (p.wide) {
+          st_global_v8(o, pk);
+        } else {
+          reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      if (STATS) {
+        // statistics of the values as stored (bf16-rounded): mean / var describe the tensor the
+        // normalisation pass will read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          x[2 * j] = valid ? __uint_as_float(pk[j] << 16) : 0.f;
+          x[2 * j + 1] = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+        }
+      }
+    }
+    if (STATS) {
+      __syncwarp();   // the previous chunk's column reads are done
+      float4* w4 = reinterpret_cast<float4*>(tb + lane * kTrStride);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) w4[jj] = make_float4(x[4 * jj], x[4 * jj + 1], x[4 * jj + 2], x[4 * jj + 3]);
+      __syncwarp();
+      const int col = lane & 15, hf = lane >> 4;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        // the two half-warps walk their 16 rows 4 apart, which puts them on disjoint banks
+        const float t = tb[(hf * 16 + ((i + 4 * hf) & 15)) * kTrStride + col];
+        s1 += t;
+        s2 = fmaf(t, t, s2);
+      }
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+      if (lane < 16) {
+        atomicAdd(s_sum + cc + col, s1);
+        if (!p.stats_sum_only) atomicAdd(s_sq + cc + col, s2);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------- CTA-pair (cta_group::2) forward / dgrad
 // Same implicit GEMM, executed by CTA PAIRS (a cluster of two CTAs = the two SMs of a TPC): one
 // tcgen05.mma.cta_group::2 covers M = 256 output pixels (CTA rank r owns the 128 pixels of patch
@@ -556,12 +679,67 @@ struct PairBarriers {
   uint32_t tmem_base;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+constexpr int kPairThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+
+template <bool F32, bool STATS>
+__device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers& bars, float (*s_stats)[256], float* tb,
+                                              uint32_t tmem, int rank, int my_n, int m_first, int m_step, int m_total,
+                                              int warp, int lane) {
+  const int q = warp & 3;              // TMEM lane quarter this warp may read
+  const int half = (warp - 2) >> 2;    // which 32-column batches: b % 2 == half
+  const int row = q * 32 + lane;
+  const int hl = row / p.tw, wl = row - hl * p.tw;
+  const int t = threadIdx.x - 64;      // 0..255 among the epilogue threads
+  const float ns = p.act == 0 ? 1.f : (p.act == 1 ? 0.f : p.slope);
+  const uint32_t acc_cols = (uint32_t)p.BN;
+  int lt = 0, cur_n0 = -1;
+  for (int m = m_first; m < m_total; m += m_step, ++lt) {
+    const TileCoord tc = decode_tile(p, my_n, m);
+    const int z = tc.z;
+    if (STATS && tc.n0 != cur_n0) {
+      if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 256);
+        if (!p.stats_sum_only) flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 256);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int col = t; col < p.BN; col += 256) {
+          s_stats[0][col] = 0.f;
+          s_stats[1][col] = 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      cur_n0 = tc.n0;
+    }
+    const int buf = lt & 1;
+    const uint32_t acc = tmem + buf * acc_cols + ((uint32_t)(q * 32) << 16);
+    mbar_wait_warp(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1, lane);
+    tc_fence_after();
+    const int h = tc.h0 + rank * p.th + hl, w = tc.w0 + wl;
+    const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+    const size_t pix =
+        ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
+    const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
+    for (int c = 32 * half; c < p.BN; c += 64)
+      epilogue_batch32<F32, STATS>(p, acc + c, valid, obase + c, pix, tc.n0 + c, ns, tb, &s_stats[0][c], &s_stats[1][c], lane);
+    // this warp is done with the buffer: tell the leader's MMA warp (count 16 = both CTAs)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(smem_u32(&bars.tempty[buf]));
+  }
+  if (STATS && cur_n0 >= 0) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 256);
+    if (!p.stats_sum_only) flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 256);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ ConvParams p, int m_total, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PairBarriers bars;
   __shared__ float s_stats[2][256];
+  __shared__ __align__(16) float s_tr[8][32 * kTrStride];   // per-warp transpose tiles of the epilogue
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -571,7 +749,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = 128u * p.KC * 2u;
   const uint32_t b_half = (uint32_t)(p.BN / 2) * p.KC * 2u;
-  const uint32_t stage_bytes = a_bytes + b_half;
+  const uint32_t stage_bytes = (uint32_t)p.kg * (a_bytes + b_half);   // kg K-blocks of A, then kg of B
   const int cin_blocks = p.cin_pad / p.KC;
   const int my_n = pair % n_tiles;
   const int m_first = pair / n_tiles, m_step = n_pairs / n_tiles;
@@ -586,11 +764,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bars.tfull[b]), 1);
-      mbar_init(smem_u32(&bars.tempty[b]), 8);  // four epilogue warps of each CTA
+      mbar_init(smem_u32(&bars.tempty[b]), 16);  // eight epilogue warps of each CTA
     }
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += kPairThreads) (&s_stats[0][0])[i] = 0.f;
   if (warp == 1) {
     tmem_alloc_pair(smem_u32(&bars.tmem_base), tmem_cols);
     tmem_relinquish_pair();
@@ -607,138 +785,106 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer (both CTAs)
+    // One elected thread.  The loop is kept lean on purpose (no divisions, barrier addresses by
+    // increment): a single thread runs at ~0.2 IPC, and every cycle it spends between two stages is
+    // a cycle the loads start later.
     if (lane == 0) {
-      int it = 0;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      const uint32_t tx = 2u * stage_bytes;
+      const int bn_half = p.BN / 2;
+      int s = 0;
+      uint32_t ph = 0;
       for (int m = m_first; m < m_total; m += m_step) {
         const TileCoord tc = decode_tile(p, my_n, m);
-        const int h0 = tc.h0 + rank * p.th;
-        for (int t = 0; t < p.n_taps[tc.z]; ++t) {
-          const int hh = h0 * p.in_stride + p.tap_dh[tc.z][t];
-          const int ww = tc.w0 * p.in_stride + p.tap_dw[tc.z][t];
+        const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
+        const int brow = tc.n0 + rank * bn_half;
+        const int ntap = p.n_taps[tc.z];
+        for (int t = 0; t < ntap; ++t) {
+          const int hh = h0 + p.tap_dh[tc.z][t];
+          const int ww = w0 + p.tap_dw[tc.z][t];
           const int kb = p.tap_k[tc.z][t] * p.cin_pad;
-          for (int cb = 0; cb < cin_blocks; ++cb, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
-            const uint32_t full = smem_u32(&bars.full[s]);
-            if (leader) mbar_expect_tx(full, 2u * stage_bytes);
-            const uint32_t sa = smem_base + s * stage_bytes;
-            tma_load_4d_pair(sa, &tmA, full, cb * p.KC, ww, hh, tc.n_img);
-            tma_load_2d_pair(sa + a_bytes, &tmB, full, kb + cb * p.KC, tc.n0 + rank * (p.BN / 2));
+          for (int cb = 0; cb < cin_blocks; cb += p.kg) {
+            mbar_wait(empty0 + 8u * s, ph ^ 1u);
+            const uint32_t full = full0 + 8u * s;
+            if (leader) mbar_expect_tx(full, tx);
+            uint32_t sa = smem_base + s * stage_bytes;
+            for (int j = 0; j < p.kg; ++j, sa += a_bytes) tma_load_4d_pair(sa, &tmA, full, (cb + j) * p.KC, ww, hh, tc.n_img);
+            for (int j = 0; j < p.kg; ++j, sa += b_half) tma_load_2d_pair(sa, &tmB, full, kb + (cb + j) * p.KC, brow);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------- MMA issuer (leader CTA only)
+    // One thread feeds the tensor pipe of both SMs.  The pipe queues only about one instruction ahead
+    // (measured: issuing an M256 N256 K16 MMA blocks ~124 cycles = its execution time), so scalar
+    // work between two tcgen05.mma is idle tensor time unless it fits under one MMA: descriptors are
+    // built by adding to a precomputed template, stage / phase advance by increment, the K steps are
+    // unrolled, and the next stage's barrier is polled right after this stage's MMAs were queued.
     if (leader && lane == 0) {
       const uint32_t idesc = make_idesc_bf16(256, p.BN, 0, 0);
-      const uint32_t layout = (p.KC == 64) ? 2u : 4u;
       const uint32_t sbo = 8u * p.KC * 2u;
-      const int ksteps = p.KC / 16;
-      int it = 0, lt = 0;
+      const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
+      const uint32_t d_hi = (uint32_t)(dtmpl >> 32), d_lo = (uint32_t)dtmpl;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      const uint32_t b_off = (uint32_t)p.kg * a_bytes;
+      const int groups = cin_blocks / p.kg;
+      int s = 0, lt = 0;
+      uint32_t ph = 0;
+      bool ready = false;
       for (int m = m_first; m < m_total; m += m_step, ++lt) {
         const TileCoord tc = decode_tile(p, my_n, m);
         const int buf = lt & 1;
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // both epilogues drained it
         tc_fence_after();
-        const int nk = p.n_taps[tc.z] * cin_blocks;
-        for (int kit = 0; kit < nk; ++kit, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&bars.full[s]), ph);
+        const int nk = p.n_taps[tc.z] * groups;
+        uint32_t accum = 0;
+        for (int kit = 0; kit < nk; ++kit) {
+          if (!ready) mbar_wait(full0 + 8u * s, ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint32_t sb = sa + a_bytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, layout);
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, layout);
-            umma_f16_pair(acc, da, db, idesc, (kit | k) != 0 ? 1u : 0u);
+          uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
+          uint32_t b_lo = a_lo + (b_off >> 4);
+          for (int j = 0; j < p.kg; ++j) {
+            if (p.KC == 64) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_pair(acc, ((uint64_t)d_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
+                accum = 1u;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_f16_pair(acc, ((uint64_t)d_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
+                accum = 1u;
+              }
+            }
+            a_lo += a_bytes >> 4;
+            b_lo += b_half >> 4;
           }
-          umma_commit_pair(smem_u32(&bars.empty[s]), 3);   // frees the stage in both CTAs
+          umma_commit_pair(empty0 + 8u * s, 3);   // frees the stage in both CTAs once these MMAs retire
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+          ready = mbar_try_wait(full0 + 8u * s, ph);   // poll the next stage while the MMAs above execute
         }
         umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
       }
     }
   } else {
-    // --------------------------------------------------------- epilogue (own 128 rows)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int hl = row / p.tw, wl = row - hl * p.tw;
-    int lt = 0, cur_n0 = -1;
-    for (int m = m_first; m < m_total; m += m_step, ++lt) {
-      const TileCoord tc = decode_tile(p, my_n, m);
-      const int z = tc.z;
-      if (p.stats != nullptr && tc.n0 != cur_n0) {
-        if (cur_n0 >= 0) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int t = threadIdx.x - 64;
-          flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
-          flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int col = t; col < p.BN; col += 128) {
-            s_stats[0][col] = 0.f;
-            s_stats[1][col] = 0.f;
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        cur_n0 = tc.n0;
-      }
-      const int buf = lt & 1;
-      const uint32_t acc = tmem + buf * acc_cols;
-      mbar_wait(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1);
-      tc_fence_after();
-      const int h = tc.h0 + rank * p.th + hl, w = tc.w0 + wl;
-      const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
-      const size_t pix =
-          ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
-      const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
-      for (int c = 0; c < p.BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int hv = 0; hv < 2; ++hv) {
-          const int cc = c + 16 * hv;
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(r[16 * hv + j]);
-            if (p.bias != nullptr) x += __ldg(p.bias + tc.n0 + cc + j);
-            v[j] = apply_act(x, p.act, p.slope);
-          }
-          if (p.mask != nullptr && valid)
-            apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + tc.n0 + cc, p.mask_slope, p.wide);
-          if (valid) store16(p, obase + cc, v);
-          if (p.stats != nullptr) {
-            float s1[16], s2[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = valid ? (p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]))) : 0.f;
-              s1[j] = x;
-              s2[j] = x * x;
-            }
-            const float t1 = column_sums16(s1, lane);
-            const float t2 = p.stats_sum_only ? 0.f : column_sums16(s2, lane);
-            if ((lane & 1) == 0) {
-              const int col = cc + column_of_lane(lane);
-              atomicAdd(&s_stats[0][col], t1);
-              if (!p.stats_sum_only) atomicAdd(&s_stats[1][col], t2);
-            }
-          }
-        }
-      }
-      // this warp is done with the buffer: tell the leader's MMA warp (count 8 = both CTAs)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(smem_u32(&bars.tempty[buf]));
-    }
-    if (p.stats != nullptr && cur_n0 >= 0) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
-      flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
+    // --------------------------------------------------------- epilogue (own 128 rows, 8 warps)
+    float* tb = &s_tr[warp - 2][0];
+    if (p.out_f32) {
+      if (p.stats != nullptr) pair_epilogue<true, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
+      else pair_epilogue<true, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
+    } else {
+      if (p.stats != nullptr) pair_epilogue<false, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
+      else pair_epilogue<false, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
     }
   }
 
@@ -810,16 +956,17 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
+      // tile coordinates advance by increment (no divisions in the loop)
+      int n_img = tile_begin / tiles_per_img;
+      int t_in = tile_begin - n_img * tiles_per_img;
+      int th_i = t_in / p.tiles_w, tw_i = t_in - th_i * p.tiles_w;
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < nk; ++it) {
-        const int tile = tile_begin + it;
-        const int n_img = tile / tiles_per_img;
-        const int t_in = tile - n_img * tiles_per_img;
-        const int h0 = (t_in / p.tiles_w) * p.th;
-        const int w0 = (t_in % p.tiles_w) * p.tw;
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&bars.empty[s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bars.full[s]);
+        const int h0 = th_i * p.th, w0 = tw_i * p.tw;
+        mbar_wait(empty0 + 8u * s, ph ^ 1u);
+        const uint32_t full = full0 + 8u * s;
         mbar_expect_tx(full, stage_bytes);
         const uint32_t sa = smem_base + s * stage_bytes;
         tma_load_4d(sa, &tmDZ, full, co0, w0, h0, n_img);
@@ -827,34 +974,55 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
         for (int b = 0; b < n_bbox; ++b)
           tma_load_4d(sa + a_bytes + b * box_bytes, &tmX, full, ci0 + b * 64,
                       w0 * p.in_stride + dw, h0 * p.in_stride + dh, n_img);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
+        if (++tw_i == p.tiles_w) {
+          tw_i = 0;
+          if (++th_i == p.tiles_h) {
+            th_i = 0;
+            ++n_img;
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // (lean issue loop: see conv_igemm_kernel)
       const uint32_t idesc = make_idesc_bf16(128, p.BNW, 1, 1);
+      // MN-major, 128B swizzle: 64 channels contiguous, 8-pixel groups 1024 B apart (SBO),
+      // 64-channel groups one TMA box apart (LBO); a K step of 16 pixels = 2048 B.
+      const uint64_t dtmpl = make_smem_desc(0, box_bytes, 1024, 2);
+      const uint32_t d_hi = (uint32_t)(dtmpl >> 32), d_lo = (uint32_t)dtmpl;
+      const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       const int ksteps = kpix / 16;
+      int s = 0;
+      uint32_t ph = 0, accum = 0;
+      bool ready = false;
       for (int it = 0; it < nk; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&bars.full[s]), ph);
+        if (!ready) mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * stage_bytes;
-        const uint32_t sb = sa + a_bytes;
+        const uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
+        const uint32_t b_lo = a_lo + (a_bytes >> 4);
+#pragma unroll 4
         for (int k = 0; k < ksteps; ++k) {
-          // MN-major, 128B swizzle: 64 channels contiguous, 8-pixel groups 1024 B apart (SBO),
-          // 64-channel groups one TMA box apart (LBO); a K step of 16 pixels = 2048 B.
-          const uint64_t da = make_smem_desc(sa + k * 2048, box_bytes, 1024, 2);
-          const uint64_t db = make_smem_desc(sb + k * 2048, box_bytes, 1024, 2);
-          umma_f16(tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16(tmem, ((uint64_t)d_hi << 32) | (a_lo + 128u * k), ((uint64_t)d_hi << 32) | (b_lo + 128u * k), idesc, accum);
+          accum = 1u;
         }
-        umma_commit(smem_u32(&bars.empty[s]));
+        umma_commit(empty0 + 8u * s);
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1u;
+        }
+        ready = (it + 1 < nk) && mbar_try_wait(full0 + 8u * s, ph);
       }
       umma_commit(smem_u32(&bars.accum));
     }
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    mbar_wait(smem_u32(&bars.accum), 0);
+    mbar_wait_warp(smem_u32(&bars.accum), 0, lane);
     tc_fence_after();
     const int rs = p.tap_rs[tap];
     for (int c = 0; c < p.BNW; c += 16) {
@@ -1016,7 +1184,7 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    mbar_wait(smem_u32(&bars.accum), 0);
+    mbar_wait_warp(smem_u32(&bars.accum), 0, lane);
     tc_fence_after();
     for (int t = 0; t < p.n_taps; ++t) {
       const int rs = p.tap_rs[t];
@@ -1191,7 +1359,7 @@ static int ensure_smem_optin() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_alltaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    e = cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
   if (e != cudaSuccess) return set_error(B200_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   g_smem_optin_done = 1;
   return B200_OK;
@@ -1206,7 +1374,7 @@ static int max_active_pairs(size_t smem) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * 148, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(kPairThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1260,7 +1428,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   // tune = BN | (mt << 12) | (stages << 16); a zero field = choose automatically
   // (bit 20: persistent kernel)
   // (bit 22: CTA-pair kernel, cta_group::2 -- implies two 128-pixel sub-tiles, one per CTA)
-  const int pair_mode = (tune >> 22) & 1;
+  // tune == 0 (no table entry): the CTA-pair kernel whenever the filter rows allow a 32-column tile
+  int pair_mode = (tune >> 22) & 1;
+  if (tune == 0 && filt_rows % 32 == 0) pair_mode = 1;
   const int bn_override = tune & 0xFFF, mt_override = pair_mode ? 2 : (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
   if (n_classes < 1 || n_classes > kMaxClasses) return set_error(B200_EINVAL, "conv_igemm: bad class count %d", n_classes);
   if (cin_pad % 32) return set_error(B200_EINVAL, "conv_igemm: cin_pad %d not a multiple of 32", cin_pad);
@@ -1271,6 +1441,8 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     return set_error(B200_EINVAL, "conv_igemm: the mask view must be 16-byte aligned with a pixel stride that is a multiple of 8");
   if (stats != nullptr && ((reinterpret_cast<uintptr_t>(stats) & 15) || stats_ld % 4))
     return set_error(B200_EINVAL, "conv_igemm: the statistics buffer must be 16-byte aligned with a row length that is a multiple of 4");
+  if (bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15))
+    return set_error(B200_EINVAL, "conv_igemm: the bias vector must be 16-byte aligned");
   int rc = ensure_smem_optin();
   if (rc) return rc;
 
@@ -1300,8 +1472,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     const int bn = bn_cands[bi];
     if (filt_rows % bn) continue;
     if (bn_override > 0 && bn != bn_override) continue;
-    // keep at least ~one wave of CTAs unless nothing smaller divides Cout
-    if (m_tiles * (filt_rows / bn) < 148 && bn > 32) continue;
+    // keep at least ~one wave of CTAs (CTA pairs: 74 of them, each covering two pixel tiles) unless
+    // nothing smaller divides Cout
+    if (pair_mode ? ((m_tiles + 1) / 2 * (filt_rows / bn) < 74 && bn > 32) : (m_tiles * (filt_rows / bn) < 148 && bn > 32)) continue;
     best_bn = bn;
   }
   if (best_bn == 0) best_bn = (bn_override > 0 && filt_rows % bn_override == 0) ? bn_override : (filt_rows % 32 == 0 ? 32 : 16);
@@ -1309,12 +1482,6 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     best_mt = 2;
   if (mt_override > 0) best_mt = mt_override;
   if (best_bn == 0) return set_error(B200_EINVAL, "conv_igemm: no tile shape for %d output channels", filt_rows);
-  // tuning knobs (scripts/tune_conv.py): B200_BN / B200_MT / B200_STAGES override the choice
-  const char* e_bn = getenv("B200_BN");
-  const char* e_mt = getenv("B200_MT");
-  const char* e_st = getenv("B200_STAGES");
-  if (e_bn && atoi(e_bn) > 0 && filt_rows % atoi(e_bn) == 0) best_bn = atoi(e_bn);
-  if (e_mt && atoi(e_mt) > 0) best_mt = atoi(e_mt);
   if (best_mt * best_bn > 512) best_mt = 512 / best_bn;
   while (best_mt > 1 && p.th * best_mt * in_stride > 256) best_mt >>= 1;
   p.BN = best_bn;
@@ -1353,11 +1520,8 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     p.stages = st;
   }
   if (st_override >= 2) p.stages = st_override;
-  if (e_st && atoi(e_st) >= 2) {
-    p.stages = atoi(e_st);
-    while (p.stages > 2 && p.stages * stage_bytes > 220 * 1024) --p.stages;
-  }
-  if (p.stages < 2 || p.stages * stage_bytes > 222 * 1024) return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
+  if (!pair_mode && (p.stages < 2 || p.stages * stage_bytes > 222 * 1024))
+    return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
   p.out = out;
   p.out_ld = out_ld;
   p.out_coff = out_coff;
@@ -1385,11 +1549,25 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   if (pair_mode) {
     if (p.mt != 2 || p.BN < 32 || p.BN % 32)
       return set_error(B200_EINVAL, "conv_igemm: the CTA-pair kernel needs BN in {32, 64, 128, 256} (got %d)", p.BN);
-    const int pstage = 128 * p.KC * 2 + (p.BN / 2) * p.KC * 2;
-    int st = st_override >= 2 ? st_override : (200 * 1024) / pstage;
+    // K-blocks per pipeline stage (tune bits 24-26, 0 = automatic): one barrier round trip and one
+    // commit per stage cost the issuing threads a few hundred cycles, so a stage should hold >= ~512
+    // tensor cycles of work: 2 K-blocks at BN = 256, more for narrower tiles (as far as the channel
+    // count divides and three stages still fit).
+    const int cin_blocks = cin_pad / p.KC;
+    int kg = (tune >> 24) & 7;
+    if (kg == 0) {
+      kg = p.BN >= 256 ? 2 : 4;
+      if (p.KC == 32) kg *= 2;
+    }
+    if (kg > 8) kg = 8;
+    const int kPairDyn = 200 * 1024;   // 227 KB - 23 KB static (barriers, statistics, transpose tiles) - alignment slack
+    while (kg > 1 && (cin_blocks % kg || 3 * kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2) > kPairDyn)) --kg;
+    p.kg = kg;
+    const int pstage = kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2);
+    int st = st_override >= 2 ? st_override : kPairDyn / pstage;
     if (st > kMaxStages) st = kMaxStages;
-    while (st > 2 && st * pstage > 216 * 1024) --st;
-    if (st < 2 || st * pstage > 216 * 1024) return set_error(B200_EINVAL, "conv_igemm: pair tile does not fit shared memory");
+    while (st > 2 && st * pstage > kPairDyn) --st;
+    if (st < 2 || st * pstage > kPairDyn) return set_error(B200_EINVAL, "conv_igemm: pair tile does not fit shared memory");
     p.stages = st;
     rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th, in_stride, p.KC * 2);
     if (rc) return rc;
@@ -1404,7 +1582,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     if (pairs > total_tiles) pairs = total_tiles;
     pairs = (pairs / n_tiles) * n_tiles;      // every pair keeps one filter tile
     if (pairs < n_tiles) pairs = n_tiles;
-    conv_igemm_pair_kernel<<<2 * pairs, kThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
+    conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
     return check_launch("conv_igemm(pair)");
   }
   rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
@@ -1413,8 +1591,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   if (rc) return rc;
 
   size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  const char* e_ps = getenv("B200_PERSIST");
-  const int persist = e_ps ? atoi(e_ps) : ((tune >> 20) & 1);
+  const int persist = (tune >> 20) & 1;
   // bit 21: keep the CTA's filter tile resident in shared memory (persistent kernel only)
   int b_res = (tune >> 21) & 1;
   const size_t bres_bytes = (size_t)n_slabs * cin_pad * p.BN * 2;

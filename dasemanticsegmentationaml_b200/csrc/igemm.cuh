@@ -50,6 +50,7 @@ struct ConvParams {
   float mask_slope;
   int stats_sum_only;
   int wide;          // 1: output (and mask) rows are 32-byte aligned -> 256-bit stores / loads
+  int kg;            // K-blocks (of KC channels) per pipeline stage (CTA-pair kernel)
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]

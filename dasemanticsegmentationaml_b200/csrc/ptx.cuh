@@ -57,6 +57,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Long waits of whole warps (the epilogue warps wait for an accumulator during an entire K loop):
+// ONE lane polls, with a suspend-time hint so that the hardware parks it instead of spinning, and the
+// warp is released by __syncwarp.  128 threads spinning on try_wait compete with the producer / MMA
+// threads for the shared-memory barrier unit and issue slots (measured: see DESIGN.md section 3).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) {
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity), "r"(20000u)
+          : "memory");
+    } while (!ok);
+  }
+  __syncwarp();
+}
+
 // wait on a barrier whose arrivals come from the peer CTA of the cluster (remote mbarrier.arrive)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;

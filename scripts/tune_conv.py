@@ -206,7 +206,25 @@ for key, (kind, m) in sorted(records.items()):
                     results.append((timeit(lambda: run(tune), 6), tune, "BNW%d S%d split%d kpix%d" % (bnw, st, sp, 64 * kp)))
                 except Exception:
                     continue
+        if kind == "conv":
+            # CTA-pair kernel (cta_group::2, tune bit 22): BN x pipeline depth
+            # (K-blocks per stage: automatic, 1 or 2; pipeline depth: automatic = as deep as fits)
+            for bn, kg in itertools.product((256, 128, 64, 32), (0, 1, 2)):
+                if m["rows"] % bn:
+                    continue
+                tune = bn | (kg << 24) | (1 << 22)
+                try:
+                    if not correct(tune):
+                        continue
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d KG%d PAIR" % (bn, kg)))
+                except Exception:
+                    continue
         results.sort()
+        pairs_only = [r_ for r_ in results if r_[2].endswith("PAIR")]
+        single_only = [r_ for r_ in results if not r_[2].endswith("PAIR")]
+        if pairs_only and single_only:
+            log("   best 1-CTA %8.1f us %-18s | best pair %8.1f us %s" % (single_only[0][0], single_only[0][2],
+                                                                       pairs_only[0][0], pairs_only[0][2]))
         best_us, best_tune, best_name = results[0]
         if best_us < 0.97 * base:
             tuned[key] = best_tune
