@@ -4,6 +4,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
     python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+    python bench.py --workload eval --gpus 8                 # BASELINE config 5: sharded 1024x2048 eval
 
 Prints ONE JSON line (rank 0).  `value` is whole-job source images per second with the inputs
 resident in HBM; `e2e` is the same step driven from pinned HOST buffers through the public API
@@ -26,11 +27,15 @@ WORKLOADS = {
     "da_dwsep_bn": "config[3]: DA train step, DepthWiseSepBNFCDiscriminator, 512x1024, batch 8/GPU",
     "supervised": "config[1]: supervised train step (3x CE), 720x1280, batch 8",
     "supervised_ohem": "config[1]: supervised train step (3x OHEM CE, radix select), 720x1280, batch 8",
-    "eval": "config[4]: full-resolution eval (forward + fused argmax + 19x19 confusion matrix), 1024x2048",
+    "eval": "config[4]: full-resolution eval (train.val: forward + fused argmax + 19x19 confusion matrix, "
+            "images sharded over the ranks, NCCL int64 sum), 1024x2048",
 }
 # algorithmic dense-conv FLOPs per (source, target) pair / image
 GFLOP_PER_UNIT = {"da_dense": 444.87, "da_dwsep": 226.0, "da_dwsep_bn": 226.0, "supervised": 186.14,
                   "supervised_ohem": 186.14, "eval": 141.04}
+SHAPES = {"supervised": (720, 1280), "supervised_ohem": (720, 1280), "eval": (1024, 2048)}
+# entry points whose launches are tensor-core GEMMs (everything else with a byte count is HBM-bound)
+GEMM_ENTRIES = ("b200_conv_igemm", "b200_conv_wgrad")
 
 
 def parse():
@@ -44,6 +49,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel time table here")
     return ap.parse_args()
@@ -70,7 +76,7 @@ def cpu_da_step_rate(workload, batch, steps, warmup, threads=None):
         avail = os.cpu_count() or 1
     torch.set_num_threads(threads or avail)
     kind = {"da_dense": "dense", "da_dwsep": "dwsep", "da_dwsep_bn": "dwsep_bn"}.get(workload)
-    h, w = (720, 1280) if workload == "supervised" else (H, W)
+    h, w = SHAPES.get(workload, (H, W))
     g = torch.Generator().manual_seed(0)
     seg = O.clone_state(O.make_bisenet_state(seed=0), requires_grad=True)
     opt = torch.optim.SGD([v for v in seg.values() if v.requires_grad], lr=0.01, momentum=0.9, weight_decay=5e-4)
@@ -82,7 +88,10 @@ def cpu_da_step_rate(workload, batch, steps, warmup, threads=None):
         opt_d = torch.optim.Adam([v for v in dsd.values() if v.requires_grad], lr=1e-3, betas=(0.9, 0.99))
 
     def step():
-        if kind:
+        if workload == "eval":
+            with torch.no_grad():
+                O.eval_batch(seg, x, labels)
+        elif kind:
             O.da_step(seg, dsd, kind, x, labels, xt, opt, opt_d)
         else:
             opt.zero_grad()
@@ -99,25 +108,50 @@ def cpu_da_step_rate(workload, batch, steps, warmup, threads=None):
     return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def _cpu_batch(workload, want):
+    """Largest batch <= want whose fp32 autograd step fits the host's free memory (about 5 GB per
+    512x1024 image pair, activations + gradients of the fp32 oracle)."""
+    try:
+        import psutil
+        free = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        free = 32.0
+    h, w = SHAPES.get(workload, (H, W))
+    per_img = 5.0 * (h * w) / (H * W)
+    b = want
+    while b > 2 and b * per_img > 0.7 * free:
+        b //= 2
+    return b
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = args.steps or 2
     warmup = args.warmup if args.warmup is not None else 1
-    batch = 2  # bounded sample: BatchNorm on the 1x1 pooled maps needs >= 2 images per step
+    # the SAME configuration as the GPU arm (batch 8 per step) whenever the host memory allows it;
+    # BatchNorm on the 1x1 pooled maps needs >= 2 images per step in any case
+    batch = _cpu_batch(args.workload, args.batch)
     rate, ms, threads = cpu_da_step_rate(args.workload, batch, steps, warmup)
+    h, w = SHAPES.get(args.workload, (H, W))
     sample = "%d-image %s step(s) of the oracle port (fp32, torch CPU), %d warm-up" % (batch, args.workload, warmup)
     line = {
-        "impl": "reference", "metric": "da_train_step_img_per_s" if args.workload != "supervised" else "train_step_img_per_s",
+        "impl": "reference", "metric": _metric(args.workload),
         "value": rate, "unit": "img/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "batch_per_step": batch, "height": H, "width": W},
+        "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": batch, "height": h, "width": w, "classes": NCLS},
         "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def _metric(workload):
+    if workload.startswith("da_"):
+        return "da_train_step_img_per_s"
+    return "eval_img_per_s" if workload == "eval" else "train_step_img_per_s"
 
 
 # --------------------------------------------------------------------------- clocks
@@ -173,13 +207,258 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- B200 arm
+class Bench(object):
+    """One workload on this rank's GPU: models, optimizers, synthetic host + device buffers."""
+
+    def __init__(self, args, workload, rank, world, dev, batch):
+        import torch
+        from dasemanticsegmentationaml_b200 import optim as B200Optim
+        from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, DepthWiseSepFCDiscriminator,
+                                                          DepthWiseSepBNFCDiscriminator)
+        self.args, self.workload, self.rank, self.world, self.dev, self.nb = args, workload, rank, world, dev, batch
+        self.h, self.w = SHAPES.get(workload, (H, W))
+        torch.manual_seed(0)  # identical initial weights on every rank
+        self.model = BiSeNet("STDCNet813", NCLS).to(dev)
+        # same optimizers and hyper-parameters as train.py:170-172
+        if args.torch_optim:
+            self.opt = torch.optim.SGD(self.model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
+        else:   # one launch per optimizer step (SURVEY 8 f3); same arithmetic as torch.optim.SGD / Adam
+            self.opt = B200Optim.FusedSGD(self.model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+        self.model_d = self.opt_d = None
+        if workload.startswith("da_"):
+            cls = {"da_dense": FCDiscriminator, "da_dwsep": DepthWiseSepFCDiscriminator,
+                   "da_dwsep_bn": DepthWiseSepBNFCDiscriminator}[workload]
+            self.model_d = cls(NCLS).to(dev)
+            if args.torch_optim:
+                self.opt_d = torch.optim.Adam(self.model_d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
+            else:
+                self.opt_d = B200Optim.FusedAdam(self.model_d.parameters(), lr=1e-3, betas=(0.9, 0.99))
+        self.host = self.make_host(rank)
+        self.devbuf = {k: v.to(dev) for k, v in self.host.items()}
+        self.names = [k for k in self.devbuf if not (self.model_d is None and k == "images_t")]
+        self.graphed = None
+        self.graph_note = "eager (--no-graph)"
+        self.eval_state = {}
+
+    def make_host(self, rank, pin=True):
+        import torch
+        g = torch.Generator().manual_seed(100 + rank)  # rank-dependent data
+        host = {
+            "images": torch.randn(self.nb, 3, self.h, self.w, generator=g),
+            "labels": torch.randint(0, NCLS + 1, (self.nb, self.h, self.w), generator=g),
+            "images_t": torch.randn(self.nb, 3, self.h, self.w, generator=g),
+        }
+        if self.workload == "supervised_ohem":
+            host["labels"].clamp_(max=NCLS - 1)  # the reference's OHEM has no ignore_index
+        else:
+            host["labels"][host["labels"] == NCLS] = 255
+        if self.workload == "eval":
+            del host["images_t"]
+        return {k: (v.pin_memory() if pin else v) for k, v in host.items()}
+
+    def eager_step(self, buf):
+        from dasemanticsegmentationaml_b200 import train as T
+        if self.workload == "eval":
+            # the reference's val() (train.py:24-61) over this rank's shard: forward, argmax, confusion
+            # matrix on the device, ONE all-reduce + ONE device->host copy per evaluation
+            import torch
+            precision, miou = T.val(self.model, [(buf["images"], buf["labels"])], NCLS)
+            self.eval_state = {"precision": precision, "miou": miou, "hist": T.val.last_hist}
+            return (torch.tensor(miou, device=self.dev),)
+        if self.workload == "supervised_ohem":
+            return (T.train_step(self.model, self.opt, buf["images"], buf["labels"], loss="ohem"),)
+        if self.model_d is None:
+            return (T.train_step(self.model, self.opt, buf["images"], buf["labels"]),)
+        return T.train_da_step(self.model, self.model_d, self.opt, self.opt_d, buf["images"], buf["labels"], buf["images_t"])
+
+    def capture(self):
+        from dasemanticsegmentationaml_b200 import train as T
+        import torch
+        if self.args.no_graph or self.workload == "eval":   # val() ends in a host read: nothing to replay
+            if self.workload == "eval":
+                self.graph_note = "eager (train.val ends with a device->host copy of the confusion matrix)"
+            return
+        try:
+            self.graphed = T.GraphedStep(lambda **kw: self.eager_step(dict(self.devbuf, **kw)),
+                                         {k: self.devbuf[k] for k in self.names},
+                                         optimizers=[o for o in (self.opt, self.opt_d) if o is not None and not self.args.torch_optim])
+            self.graph_note = "whole step replayed as one CUDA graph"
+        except Exception as ex:  # capture is an optimisation: report and fall back to eager launches
+            self.graphed = None
+            self.graph_note = "eager (graph capture failed: %r)" % (ex,)
+            torch.cuda.synchronize()
+
+    def step(self, buf):
+        if self.graphed is None:
+            return self.eager_step(buf)
+        if buf is self.devbuf:  # already in the graph's static buffers
+            return self.graphed()
+        return self.graphed(**{k: buf[k] for k in self.names})
+
+
+def sync_all(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def time_resident(b, steps, warmup, clocks=None):
+    """Timed region 1: inputs resident in HBM.  -> (ms per step (max over ranks), launches, losses, clk, host ms)"""
+    import torch
+    import torch.distributed as dist
+    from dasemanticsegmentationaml_b200 import _lib
+    for _ in range(warmup):
+        b.step(b.devbuf)
+    sync_all(b.world)
+    t_wall0 = time.time()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_host0 = time.perf_counter()
+    for _ in range(steps):
+        losses = b.step(b.devbuf)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # host time to queue one step
+    e1.record()
+    sync_all(b.world)
+    t_wall1 = time.time()
+    launches = _lib.launch_count - l0
+    if b.graphed is not None:  # replays do not pass through the binding: count one eager step's launches
+        l1 = _lib.launch_count
+        b.eager_step(b.devbuf)
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count - l1) * steps
+    ms = torch.tensor([e0.elapsed_time(e1)], device=b.dev)
+    if b.world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    return float(ms.item()) / steps, launches, [float(v) for v in losses], clk, host_enqueue_ms
+
+
+def time_e2e(b, steps):
+    """Timed region 2: end to end from pinned host buffers.  Every step copies ITS inputs
+    host->device (pinned memory, a dedicated copy stream, double buffered so that the copy of step
+    i+1 overlaps the compute of step i) and reads the step's result back to the host (one D2H +
+    sync per step, as train.py's .item() calls do).  -> (ms per step, h2d bytes, d2h bytes)"""
+    import torch
+    import torch.distributed as dist
+    names = b.names
+    stage = [{k: torch.empty_like(b.devbuf[k]) for k in names} for _ in range(2)]
+    for sbuf in stage:
+        if "images_t" not in sbuf and "images_t" in b.devbuf:
+            sbuf["images_t"] = b.devbuf["images_t"]
+    h2d = sum(b.host[k].numel() * b.host[k].element_size() for k in names)
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])      # the step that last used this slot is done
+            for k in names:
+                stage[slot][k].copy_(b.host[k], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    sync_all(b.world)
+    for ev in consumed:
+        ev.record()
+    d2h_stream = torch.cuda.Stream()
+    host_buf = torch.empty(8, dtype=torch.float32).pin_memory()
+
+    def read_back(item):
+        """Blocking D2H read of one step's stacked results on a side stream (waits for THAT step only)."""
+        stacked, done = item
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
+            host_buf[:stacked.numel()].copy_(stacked, non_blocking=True)
+        d2h_stream.synchronize()
+        return host_buf[:stacked.numel()].clone()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    issue_copy(0)
+    pending = None
+    n_out = 1
+    for i in range(steps):
+        slot = i & 1
+        if i + 1 < steps:
+            issue_copy(slot ^ 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        out = b.step(stage[slot])
+        consumed[slot].record()
+        stacked = torch.stack([o.float() for o in out])
+        n_out = len(out)
+        done = torch.cuda.Event()
+        done.record()
+        # every step's results are read back to the host; the read of step i happens after step i+1
+        # has been queued, so the host-side sync never leaves the GPU idle
+        if pending is not None:
+            read_back(pending)
+        pending = (stacked, done)
+    read_back(pending)
+    e1.record()
+    sync_all(b.world)
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=b.dev)
+    if b.world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    d2h = 4 * n_out + (8 * NCLS * NCLS if b.workload == "eval" else 0)   # eval: + the int64 confusion matrix
+    return float(ms2.item()) / steps, h2d, d2h
+
+
+def weights_checksum(modules):
+    """Bit-level checksum (int64 wrap-around sum of the fp32 bit patterns) of all parameters and buffers."""
+    import torch
+    tot = torch.zeros((), dtype=torch.int64, device=next(modules[0].parameters()).device)
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            if t.dtype == torch.float32:
+                tot += t.detach().contiguous().view(torch.int32).to(torch.int64).sum()
+            else:
+                tot += t.detach().to(torch.int64).sum()
+    return tot
+
+
+def dp_check(b):
+    """Data-parallel consistency: after the timed steps every rank must hold bit-identical weights
+    (same initial weights + identical averaged gradients); checked on a bit-level checksum."""
+    import torch
+    import torch.distributed as dist
+    mods = [m for m in (b.model, b.model_d) if m is not None]
+    mine = weights_checksum(mods).reshape(1)
+    if b.world == 1:
+        return {"ranks": 1, "identical_on_all_ranks": True, "checksum": int(mine.item())}
+    parts = [torch.empty_like(mine) for _ in range(b.world)]
+    dist.all_gather(parts, mine)
+    vals = [int(p.item()) for p in parts]
+    return {"ranks": b.world, "identical_on_all_ranks": all(v == vals[0] for v in vals), "checksum": vals[0]}
+
+
+def eval_hist_check(b):
+    """BASELINE config 5: the all-reduced confusion matrix of the sharded evaluation must equal, bit for
+    bit, the matrix ONE process computes over all ranks' images (rank 0 regenerates the other ranks'
+    shards from their seeds and evaluates them itself with the same weights)."""
+    import torch
+    from dasemanticsegmentationaml_b200 import train as T
+    summed = b.eval_state.get("hist")
+    if summed is None:
+        return None
+    if b.rank != 0:
+        return None
+    single = None
+    with torch.no_grad():
+        for r in range(b.world):
+            host = b.make_host(r, pin=False)
+            single, _ = T.eval_batch(b.model, host["images"].to(b.dev), host["labels"].to(b.dev), NCLS, single)
+    return {"ranks": b.world, "images": b.nb * b.world, "pixels": int(b.nb * b.world * b.h * b.w),
+            "summed_hist_equals_single_process": bool(torch.equal(summed.cpu(), single.cpu())),
+            "hist_total": int(summed.sum().item()), "precision": b.eval_state["precision"], "miou": b.eval_state["miou"]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from dasemanticsegmentationaml_b200 import _lib, build
-    from dasemanticsegmentationaml_b200 import train as T
-    from dasemanticsegmentationaml_b200.model import (BiSeNet, FCDiscriminator, DepthWiseSepFCDiscriminator,
-                                                      DepthWiseSepBNFCDiscriminator)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,175 +479,23 @@ def run_b200(args):
 
     steps = args.steps or 20
     warmup = max(3, args.warmup if args.warmup is not None else 5)
-    nb = args.batch
-    h, w = {"supervised": (720, 1280), "supervised_ohem": (720, 1280), "eval": (1024, 2048)}.get(args.workload, (H, W))
-
-    torch.manual_seed(0)  # identical initial weights on every rank
-    model = BiSeNet("STDCNet813", NCLS).to(dev)
-    # same optimizers and hyper-parameters as train.py:170-172; fused=True only changes how torch
-    # launches the update (one multi-tensor kernel per step)
-    from dasemanticsegmentationaml_b200 import optim as B200Optim
-    if args.torch_optim:
-        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4, fused=True)
-    else:   # one launch per optimizer step; same arithmetic as torch.optim.SGD / Adam
-        opt = B200Optim.FusedSGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
-    model_d = opt_d = None
-    if args.workload.startswith("da_"):
-        cls = {"da_dense": FCDiscriminator, "da_dwsep": DepthWiseSepFCDiscriminator,
-               "da_dwsep_bn": DepthWiseSepBNFCDiscriminator}[args.workload]
-        model_d = cls(NCLS).to(dev)
-        if args.torch_optim:
-            opt_d = torch.optim.Adam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99), fused=True, capturable=True)
-        else:
-            opt_d = B200Optim.FusedAdam(model_d.parameters(), lr=1e-3, betas=(0.9, 0.99))
-
-    g = torch.Generator().manual_seed(100 + rank)  # rank-dependent data
-    host = {
-        "images": torch.randn(nb, 3, h, w, generator=g).pin_memory(),
-        "labels": torch.randint(0, NCLS + 1, (nb, h, w), generator=g).pin_memory(),
-        "images_t": torch.randn(nb, 3, h, w, generator=g).pin_memory(),
-    }
-    if args.workload == "supervised_ohem":
-        host["labels"].clamp_(max=NCLS - 1)  # the reference's OHEM has no ignore_index
-    else:
-        host["labels"][host["labels"] == NCLS] = 255
-    devbuf = {k: v.to(dev) for k, v in host.items()}
-    eval_hist = [None]
-
-    def step(buf):
-        if args.workload == "eval":
-            eval_hist[0], _ = T.eval_batch(model, buf["images"], buf["labels"], NCLS, eval_hist[0])
-            return (eval_hist[0].sum().float(),)
-        if args.workload == "supervised_ohem":
-            return (T.train_step(model, opt, buf["images"], buf["labels"], loss="ohem"),)
-        if model_d is None:
-            return (T.train_step(model, opt, buf["images"], buf["labels"]),)
-        return T.train_da_step(model, model_d, opt, opt_d, buf["images"], buf["labels"], buf["images_t"])
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # eager warm-up (also fills lazy state), then capture the whole step into one CUDA graph
-    eager_step = step
-    for _ in range(2):
-        eager_step(devbuf)
-    graphed = None
-    graph_note = "eager (--no-graph)"
-    if not args.no_graph and args.workload != "eval":
-        try:
-            names_g = [k for k in devbuf if not (model_d is None and k == "images_t")]
-            graphed = T.GraphedStep(lambda **kw: eager_step(dict(devbuf, **kw)), {k: devbuf[k] for k in names_g})
-            graph_note = "whole step replayed as one CUDA graph"
-
-            def step(buf):  # noqa: F811
-                if buf is devbuf:  # already in the graph's static buffers
-                    return graphed()
-                return graphed(**{k: buf[k] for k in names_g})
-        except Exception as ex:  # capture is an optimisation: report and fall back to eager launches
-            graphed = None
-            graph_note = "eager (graph capture failed: %r)" % (ex,)
-            torch.cuda.synchronize()
-
+    b = Bench(args, args.workload, rank, world, dev, args.batch)
+    for _ in range(2):      # eager warm-up (also fills lazy state), then capture the whole step
+        b.eager_step(b.devbuf)
+    b.capture()
     clocks = ClockSampler(local) if rank == 0 else None
-    for _ in range(warmup):
-        step(devbuf)
-    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
-    sync_all()
-    t_wall0 = time.time()
-    l0 = _lib.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t_host0 = time.perf_counter()
-    for _ in range(steps):
-        losses = step(devbuf)
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # host time to queue one step
-    e1.record()
-    sync_all()
-    t_wall1 = time.time()
-    launches = _lib.launch_count - l0
-    if graphed is not None:  # replays do not pass through the binding: count one eager step's launches
-        l1 = _lib.launch_count
-        eager_step(devbuf)
-        torch.cuda.synchronize()
-        launches = (_lib.launch_count - l1) * steps
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
-    loss_vals = [float(v) for v in losses]
-
-    # ---- timed region 2: end to end from pinned host buffers -------------------------------------
-    # Every step copies ITS inputs host->device (pinned memory, a dedicated copy stream, double
-    # buffered so that the copy of step i+1 overlaps the compute of step i) and reads the step's
-    # losses back to the host (one D2H + sync per step, as train.py's .item() calls do).
-    names = [k for k in devbuf if not (model_d is None and k == "images_t")]
-    stage = [{k: torch.empty_like(devbuf[k]) for k in names} for _ in range(2)]
-    for sbuf in stage:
-        if "images_t" not in sbuf:
-            sbuf["images_t"] = devbuf["images_t"]
-    h2d = sum(host[k].numel() * host[k].element_size() for k in names)
-    copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def issue_copy(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])      # the step that last used this slot is done
-            for k in names:
-                stage[slot][k].copy_(host[k], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    sync_all()
-    for ev in consumed:
-        ev.record()
-    d2h_stream = torch.cuda.Stream()
-    host_buf = torch.empty(8, dtype=torch.float32).pin_memory()
-
-    def read_back(item):
-        """Blocking D2H read of one step's stacked losses on a side stream (waits for THAT step only)."""
-        stacked, done = item
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(done)
-            host_buf[:stacked.numel()].copy_(stacked, non_blocking=True)
-        d2h_stream.synchronize()
-        return host_buf[:stacked.numel()].clone()
-
-    e0.record()
-    issue_copy(0)
-    pending = None
-    for i in range(steps):
-        slot = i & 1
-        if i + 1 < steps:
-            issue_copy(slot ^ 1)
-        torch.cuda.current_stream().wait_event(ready[slot])
-        out = step(stage[slot])
-        consumed[slot].record()
-        stacked = torch.stack([o.float() for o in out])
-        done = torch.cuda.Event()
-        done.record()
-        # every step's losses are read back to the host; the read of step i happens after step i+1
-        # has been queued, so the host-side sync never leaves the GPU idle
-        if pending is not None:
-            host_losses = read_back(pending)
-        pending = (stacked, done)
-    host_losses = read_back(pending)
-    e1.record()
-    sync_all()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ms2.item())
+    ms_step, launches, loss_vals, clk, host_ms = time_resident(b, steps, warmup, clocks)
+    e2e_ms, h2d, d2h = time_e2e(b, steps)
+    check = eval_hist_check(b) if args.workload == "eval" else dp_check(b)
 
     # ---- per-kernel profile of ONE step (CUDA events around every launch of ours) -----------------
     prof = None
     if not args.no_profile:
-        sync_all()
+        sync_all(world)
         _lib.profile_start()
-        eager_step(devbuf)
+        b.eager_step(b.devbuf)
         prof = _lib.profile_stop()
+        detail = _lib.last_profile_detail
 
     if world > 1:
         dist.barrier()
@@ -377,50 +504,66 @@ def run_b200(args):
         return
 
     peaks = measured_peaks()
+    nb, h, w = b.nb, b.h, b.w
     unit_per_step = nb * world
-    value = unit_per_step * steps / (ms_total / 1e3)
+    value = unit_per_step / (ms_step / 1e3)
     line = {
-        "metric": "da_train_step_img_per_s" if model_d is not None else ("eval_img_per_s" if args.workload == "eval" else "train_step_img_per_s"),
+        "metric": _metric(args.workload),
         "value": value, "unit": "img/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": nb, "height": h, "width": w,
                    "classes": NCLS, "parallelism": "dp%d" % world,
                    "l2": "inputs (134 MB/step) and activations (>1 GB/step) exceed the 126 MB L2; no explicit flush",
-                   "pairs_per_s": value if model_d is not None else None,
-                   "losses_last_step": loss_vals, "host_enqueue_ms_per_step": host_enqueue_ms,
-                   "launch_mode": graph_note},
-        "e2e": {"value": unit_per_step * steps / (e2e_ms / 1e3), "unit": "img/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(out), "ms_per_step": e2e_ms / steps},
+                   "pairs_per_s": value if b.model_d is not None else None,
+                   "losses_last_step": loss_vals, "host_enqueue_ms_per_step": host_ms,
+                   "launch_mode": b.graph_note,
+                   ("eval_check" if args.workload == "eval" else "dp_check"): check},
+        "e2e": {"value": unit_per_step / (e2e_ms / 1e3), "unit": "img/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
         "gpu_launches": launches,
         "clocks": clk,
     }
-    step_tf = GFLOP_PER_UNIT[args.workload] * nb / 1e3 / (ms_total / steps / 1e3)  # TFLOP/s per GPU, whole step
+    step_tf = GFLOP_PER_UNIT[args.workload] * nb / 1e3 / (ms_step / 1e3)  # TFLOP/s per GPU, whole step
     line["config"]["step_algorithmic_tflops_per_gpu"] = step_tf
     if prof:
-        conv = [v for k, v in prof.items() if k in ("b200_conv_igemm",)]
-        tot_ms = sum(v["ms"] for v in prof.values())
-        table = sorted(((k, v["calls"], v["ms"], v["flops"]) for k, v in prof.items()), key=lambda r: -r[2])
-        if conv and conv[0]["ms"] > 0:
-            c = conv[0]
-            ach = c["flops"] / (c["ms"] / 1e3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_igemm_persistent_kernel (forward + data-gradient launches)",
-                                "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                                "frac": ach / peaks["tf_sustained"], "traffic": conv_traffic(args.workload),
-                                "traffic_source": "profiles/r1_conv_traffic.json (ncu dram__bytes_read+write per launch, da_dense step)",
-                                "peak_source": peaks["source"] + " bf16_tflops_sustained",
-                                "launches_per_step": c["calls"], "avg_launch_ms": c["ms"] / c["calls"],
-                                "share_of_kernel_time": c["ms"] / tot_ms}
-        line["kernel_time_ms_per_step"] = {k: round(ms_, 3) for k, _, ms_, _ in table}
-        if "b200_conv_wgrad" in prof and prof["b200_conv_wgrad"]["ms"] > 0:
-            wg = prof["b200_conv_wgrad"]
-            line["wgrad_tflops"] = wg["flops"] / (wg["ms"] / 1e3) / 1e12
+        add_rooflines(line, prof, peaks, args)
         if args.profile_json:
             with open(args.profile_json, "w") as f:
-                json.dump({"by_kernel": prof, "by_shape": _lib.last_profile_detail}, f, indent=1)
-    if not args.no_cpu_baseline and world == 1 and (args.workload.startswith("da_") or args.workload == "supervised"):
+                json.dump({"by_kernel": prof, "by_shape": detail}, f, indent=1)
+    del b
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, short runs (driver-observed numbers for configs 1, 3, 4) -----
+    if world == 1 and not args.no_extras and args.workload == "da_dense":
+        extras = {}
+        for wl in ("da_dwsep", "da_dwsep_bn", "supervised_ohem", "eval"):
+            try:
+                eb = Bench(args, wl, rank, world, dev, args.batch)
+                for _ in range(2):
+                    eb.eager_step(eb.devbuf)
+                eb.capture()
+                ms_e, _, lv, _, _ = time_resident(eb, 5, 3)
+                ent = {"workload": WORKLOADS[wl], "img_per_s": eb.nb / (ms_e / 1e3), "ms_per_step": ms_e, "steps": 5,
+                       "warmup": 3, "height": eb.h, "width": eb.w, "launch_mode": eb.graph_note, "result_last_step": lv}
+                if wl.startswith("da_dwsep"):
+                    # BASELINE config 4 is judged by HBM GB/s: the depthwise / BatchNorm kernels of this step
+                    _lib.profile_start()
+                    eb.eager_step(eb.devbuf)
+                    pe = _lib.profile_stop()
+                    ent["roofline_mem"] = mem_table(pe, peaks, only=("b200_dwconv", "b200_bn_", "b200_upsample", "b200_act_bwd"))
+                if wl == "eval":
+                    ent["eval_check"] = eval_hist_check(eb)
+                extras[wl] = ent
+                del eb
+            except Exception as ex:   # never lose the headline over an extra
+                extras[wl] = {"failed": repr(ex)}
+            torch.cuda.empty_cache()
+        line["extra"] = extras
+
+    if not args.no_cpu_baseline and world == 1 and args.workload != "supervised_ohem":
         try:
-            cb_batch, cb_steps = 4, 4
+            cb_batch, cb_steps = min(4, args.batch), (4 if args.workload != "eval" else 2)
             rate, cms, threads = cpu_da_step_rate(args.workload, cb_batch, cb_steps, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
                                     "sample": "%d steps of %d source + %d target images (same %dx%d workload, reduced batch) "
@@ -431,6 +574,44 @@ def run_b200(args):
                                     "sample": "failed: %r" % (ex,)}
     emit(line)
     _finish(world)
+
+
+def mem_table(prof, peaks, only=None):
+    """{entry point: achieved GB/s on its algorithmic bytes, fraction of the measured HBM copy rate}
+    for the HBM-bound kernels of one eager step (CUDA events around each launch)."""
+    out = {}
+    for k, v in prof.items():
+        if k in GEMM_ENTRIES or v["bytes"] <= 0 or v["ms"] <= 0:
+            continue
+        if only and not k.startswith(tuple(only)):
+            continue
+        gbs = v["bytes"] / (v["ms"] / 1e3) / 1e9
+        out[k] = {"gbs": round(gbs, 1), "frac_of_hbm": round(gbs / peaks["hbm"], 3), "launches": v["calls"],
+                  "ms": round(v["ms"], 3), "mbytes": round(v["bytes"] / 1e6, 1)}
+    return out
+
+
+def add_rooflines(line, prof, peaks, args):
+    conv = prof.get("b200_conv_igemm")
+    tot_ms = sum(v["ms"] for v in prof.values())
+    table = sorted(((k, v["calls"], v["ms"], v["flops"]) for k, v in prof.items()), key=lambda r: -r[2])
+    if conv and conv["ms"] > 0:
+        ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12
+        traffic, traffic_src = conv_traffic(args.workload)
+        line["roofline"] = {"bound": "tensor",
+                            "kernel": "conv_igemm_pair_kernel (cta_group::2) + conv_igemm_kernel / conv_igemm_persistent_kernel "
+                                      "(forward + data-gradient launches of b200_conv_igemm)",
+                            "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                            "frac": ach / peaks["tf_burst"], "traffic": traffic, "traffic_source": traffic_src,
+                            "peak_source": peaks["source"] + " bf16_tflops (burst: every launch is timed alone with CUDA events)",
+                            "frac_of_sustained": ach / peaks["tf_sustained"],
+                            "launches_per_step": conv["calls"], "avg_launch_ms": conv["ms"] / conv["calls"],
+                            "share_of_kernel_time": conv["ms"] / tot_ms}
+    line["kernel_time_ms_per_step"] = {k: round(ms_, 3) for k, _, ms_, _ in table}
+    wg = prof.get("b200_conv_wgrad")
+    if wg and wg["ms"] > 0:
+        line["wgrad_tflops"] = wg["flops"] / (wg["ms"] / 1e3) / 1e12
+    line["roofline_mem"] = mem_table(prof, peaks)
 
 
 def _finish(world):
@@ -444,11 +625,13 @@ def _finish(world):
 
 def conv_traffic(workload):
     """DRAM bytes per conv launch from the committed ncu capture (only measured for the default workload)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_conv_traffic.json")
-    if workload != "da_dense" or not os.path.exists(path):
-        return None
-    with open(path) as f:
-        return json.load(f).get("traffic_bytes_per_launch")
+    for name in ("r2_conv_traffic.json", "r1_conv_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if workload == "da_dense" and os.path.exists(path):
+            with open(path) as f:
+                return json.load(f).get("traffic_bytes_per_launch"), \
+                    "profiles/%s (ncu dram__bytes_read+write per launch, da_dense step)" % name
+    return None, None
 
 
 _REAL_STDOUT = sys.stdout

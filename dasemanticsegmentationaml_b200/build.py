@@ -18,9 +18,16 @@ LIB = os.path.join(HERE, "libb200seg.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math", "-I", CSRC,
+    "-Xcompiler", "-fPIC", "-I", CSRC,
     "-I", os.path.join(os.path.dirname(HERE), "include"),
 ]
+# --use_fast_math (approximate division / exp / rsqrt, flush-to-zero) only where it pays and is
+# covered by a parity test with the flag ON: the GEMM epilogues (igemm.cu: no transcendental at all)
+# and the issue-bound up-sampling / softmax / cross-entropy kernels (loss.cu: __expf / __logf per
+# pixel and class; tests/test_modules_gpu.py::test_fused_losses_against_torch holds the loss to 1e-4
+# and the gradients to 1e-3 against torch).  BatchNorm statistics, optimizers, depthwise convs, metrics
+# and the input pipeline are compiled with IEEE division / sqrt.
+FAST_MATH_SOURCES = ("igemm.cu", "loss.cu")
 
 
 def _nvcc():
@@ -36,7 +43,7 @@ def _digest(paths):
         with open(p, "rb") as f:
             h.update(p.encode())
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + list(FAST_MATH_SOURCES)).encode())
     return h.hexdigest()
 
 
@@ -64,7 +71,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["--use_fast_math"] if os.path.basename(src) in FAST_MATH_SOURCES else []) + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -78,7 +85,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                  "-cudart", "static", "-Xcompiler", "-fPIC"]
+                                                  "-cudart", "static", "-Xcompiler", "-fPIC", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

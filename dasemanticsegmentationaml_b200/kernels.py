@@ -217,8 +217,9 @@ def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None, scratch=None):
     return dw
 
 
-def wgrad_unscratch(scratch_base, dw_base, table, n_layers):
-    call("b200_wgrad_unscratch", ptr(scratch_base), ptr(dw_base), ptr(table), c_int(n_layers), stream())
+def wgrad_unscratch(scratch_base, dw_base, table, n_layers, n_weights=0):
+    call("b200_wgrad_unscratch", ptr(scratch_base), ptr(dw_base), ptr(table), c_int(n_layers), stream(),
+         nbytes=8.0 * n_weights, tag="%d layers" % n_layers)
 
 
 # ------------------------------------------------------------------ metrics
@@ -229,14 +230,16 @@ def fast_hist_accumulate(label, pred, n, hist, bad):
     pred = pred.contiguous()
     call("b200_fast_hist", ptr(label), c_int(label.element_size()), ptr(pred),
                                c_int(pred.element_size()), c_int64(label.numel()), c_int(n),
-                               ptr(hist), ptr(bad), stream())
+                               ptr(hist), ptr(bad), stream(),
+         nbytes=float(label.numel() * (label.element_size() + pred.element_size())), tag="px%d" % label.numel())
     return hist
 
 
 def count_equal(label, pred, out):
     call("b200_count_equal", ptr(label), c_int(label.element_size()), ptr(pred),
                                  c_int(pred.element_size()), c_int64(label.numel()), ptr(out),
-                                 stream())
+                                 stream(), nbytes=float(label.numel() * (label.element_size() + pred.element_size())),
+         tag="px%d" % label.numel())
     return out
 
 
@@ -262,7 +265,8 @@ def _pix(t):
 
 def channel_stats(x, stats):
     npix, c, ld = _pix(x)
-    call("b200_channel_stats", ptr(x), c_int(ld), c_int(c), c_int64(npix), ptr(stats), stream())
+    call("b200_channel_stats", ptr(x), c_int(ld), c_int(c), c_int64(npix), ptr(stats), stream(),
+         nbytes=2.0 * npix * c, tag="px%d C%d" % (npix, c))
 
 
 def bn_finalize(stats, count, gamma, beta, running_mean, running_var, training, scale, shift,
@@ -330,7 +334,7 @@ def act_bwd_bias(dy1, dy2, a, dz, act, slope, dbias):
     call("b200_act_bwd_bias", 
         ptr(dy1), c_int(dy1.stride(2)), ptr(dy2), c_int(0 if dy2 is None else dy2.stride(2)),
         ptr(a), c_int(a_ld), ptr(dz), c_int(dz.stride(2)), c_int(c), c_int64(npix), c_int(act),
-        c_float(slope), ptr(dbias), stream())
+        c_float(slope), ptr(dbias), stream(), nbytes=(6.0 if dy2 is None else 8.0) * npix * c, tag="px%d C%d" % (npix, c))
 
 
 # ------------------------------------------------------------------ depthwise / stem
@@ -339,21 +343,23 @@ def dwconv_s2_fwd(x, k, w, bias, z, pool, act, slope, stats):
     call("b200_dwconv_s2_fwd", 
         ptr(x), c_int(x_ld), c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(bias),
         ptr(z), c_int(z.stride(2)), ptr(pool), c_int(0 if pool is None else pool.stride(2)),
-        c_int(act), c_float(slope), ptr(stats), stream())
+        c_int(act), c_float(slope), ptr(stats), stream(),
+        nbytes=2.0 * (x.numel() + z.numel() * (2 if pool is not None else 1)), tag="C%d %dx%d k%d" % (c, h, wd, k))
 
 
 def dwconv_s2_dgrad(dz, dpool, k, w, dx):
     n, h, wd, c, dx_ld = _nhwc_meta(dx)
     call("b200_dwconv_s2_dgrad", 
         ptr(dz), c_int(dz.stride(2)), ptr(dpool), c_int(0 if dpool is None else dpool.stride(2)),
-        c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(dx), c_int(dx_ld), stream())
+        c_int(n), c_int(h), c_int(wd), c_int(c), c_int(k), ptr(w), ptr(dx), c_int(dx_ld), stream(),
+        nbytes=2.0 * (dx.numel() + dz.numel() * (2 if dpool is not None else 1)), tag="C%d %dx%d k%d" % (c, h, wd, k))
 
 
 def dwconv_s2_wgrad(dz, x, k, dw, dbias):
     n, h, wd, c, x_ld = _nhwc_meta(x)
     call("b200_dwconv_s2_wgrad", 
         ptr(dz), c_int(dz.stride(2)), ptr(x), c_int(x_ld), c_int(n), c_int(h), c_int(wd), c_int(c),
-        c_int(k), ptr(dw), ptr(dbias), stream())
+        c_int(k), ptr(dw), ptr(dbias), stream(), nbytes=2.0 * (x.numel() + dz.numel()), tag="C%d %dx%d k%d" % (c, h, wd, k))
 
 
 def stem_im2col(img, col):
@@ -361,14 +367,16 @@ def stem_im2col(img, col):
     n, _, h, wd = img.shape
     assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
     assert col.shape[3] == 32 and col.stride(3) == 1
-    call("b200_stem_im2col", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(col), c_int(col.stride(2)), stream())
+    call("b200_stem_im2col", ptr(img), c_int(n), c_int(h), c_int(wd), ptr(col), c_int(col.stride(2)), stream(),
+         nbytes=4.0 * img.numel() + 2.0 * col.numel(), tag="%dx%d" % (h, wd))
     return col
 
 
 # ------------------------------------------------------------------ attention
 def pool_sum(x, out):
     n, h, w, c, ld = _nhwc_meta(x)
-    call("b200_pool_sum", ptr(x), c_int(ld), c_int(n), c_int(h * w), c_int(c), ptr(out), stream())
+    call("b200_pool_sum", ptr(x), c_int(ld), c_int(n), c_int(h * w), c_int(c), ptr(out), stream(),
+         nbytes=2.0 * x.numel(), tag="C%d px%d" % (c, n * h * w))
 
 
 def fc_small_fwd(inp, in_scale, W, bn, training, act, pre, out, mean, rstd, momentum=0.1, eps=1e-5):
@@ -400,7 +408,8 @@ def scale_add_bcast(a, s, s_plus, v, v_scale, t, out):
     call("b200_scale_add_bcast", 
         ptr(a), c_int(a_ld), c_int(hs), c_int(ws), ptr(s), c_float(s_plus), ptr(v), c_float(v_scale),
         ptr(t), c_int(0 if t is None else t.stride(2)), ptr(out), c_int(out_ld), c_int(n), c_int(ho),
-        c_int(wo), c_int(c), stream())
+        c_int(wo), c_int(c), stream(),
+        nbytes=2.0 * (a.numel() + out.numel() + (0 if t is None else t.numel())), tag="C%d %dx%d->%dx%d" % (c, hs, ws, ho, wo))
 
 
 def upsum_dot_reduce(dout, b, dsum, hs, ws, dot, vsum):
@@ -408,7 +417,9 @@ def upsum_dot_reduce(dout, b, dsum, hs, ws, dot, vsum):
     call("b200_upsum_dot_reduce", 
         ptr(dout), c_int(dout_ld), c_int(ho), c_int(wo), ptr(b), c_int(0 if b is None else b.stride(2)),
         ptr(dsum), c_int(0 if dsum is None else dsum.stride(2)), c_int(n), c_int(hs), c_int(ws),
-        c_int(c), ptr(dot), ptr(vsum), stream())
+        c_int(c), ptr(dot), ptr(vsum), stream(),
+        nbytes=2.0 * (dout.numel() + (0 if b is None else b.numel()) + (0 if dsum is None else dsum.numel())),
+        tag="C%d %dx%d->%dx%d" % (c, ho, wo, hs, ws))
 
 
 # ------------------------------------------------------------------ up-sampling / losses
@@ -422,7 +433,11 @@ def upsample_fwd(lr, H, W, n_classes, mode, out=None, out_flag=0, p_ld=0, labels
     call("b200_upsample_fwd", 
         ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
         c_int(mode), ptr(out), c_int(out_flag), c_int(p_ld), ptr(labels), c_int(ignore_index), ptr(acc),
-        ptr(loss_map), stream())
+        ptr(loss_map), stream(),
+        nbytes=float(lr.numel() * 4 + (0 if labels is None else labels.numel() * labels.element_size())
+                     + (0 if out is None else n * H * W * (n_classes if out.dim() == 4 and mode != UP_ARGMAX else 1) * out.element_size())
+                     + (0 if loss_map is None else loss_map.numel() * 4)),
+        tag="mode%d %dx%d" % (mode, H, W))
 
 
 def upsample_bwd(lr, H, W, n_classes, mode, d_lr, grad_in=None, grad_is_bf16=0, p_ld=0, labels=None,
@@ -431,21 +446,26 @@ def upsample_bwd(lr, H, W, n_classes, mode, d_lr, grad_in=None, grad_is_bf16=0, 
     call("b200_upsample_bwd", 
         ptr(lr), c_int(ld), c_int(n), c_int(h_lr), c_int(w_lr), c_int(H), c_int(W), c_int(n_classes),
         c_int(mode), ptr(grad_in), c_int(grad_is_bf16), c_int(p_ld), ptr(labels), c_int(ignore_index),
-        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), ptr(loss_acc), stream())
+        ptr(pixel_weight), ptr(coef_num), ptr(coef_den), c_float(coef_scale), ptr(d_lr), ptr(loss_acc), stream(),
+        nbytes=float(lr.numel() * 8 + (0 if labels is None else labels.numel() * labels.element_size())
+                     + (0 if grad_in is None else n * H * W * n_classes * grad_in.element_size())
+                     + (0 if pixel_weight is None else pixel_weight.numel() * 4)),
+        tag="mode%d %dx%d" % (mode, H, W))
 
 
 def radix_select_desc(x, rank, state, hist):
     call("b200_radix_select_desc", ptr(x), c_int64(x.numel()), c_int64(rank), ptr(state), ptr(hist),
-                                       stream())
+                                       stream(), nbytes=16.0 * x.numel(), tag="n%d" % x.numel())
 
 
 def ohem_reduce(x, state, threshold, keep_num, sums, out):
     call("b200_ohem_reduce", ptr(x), c_int64(x.numel()), ptr(state), c_float(threshold),
-                                 c_int64(keep_num), ptr(sums), ptr(out), stream())
+                                 c_int64(keep_num), ptr(sums), ptr(out), stream(), nbytes=4.0 * x.numel(), tag="n%d" % x.numel())
 
 
 def ohem_weights(x, sel, wout):
-    call("b200_ohem_weights", ptr(x), c_int64(x.numel()), ptr(sel), ptr(wout), stream())
+    call("b200_ohem_weights", ptr(x), c_int64(x.numel()), ptr(sel), ptr(wout), stream(), nbytes=8.0 * x.numel(),
+         tag="n%d" % x.numel())
 
 
 def bce_const_fwd(x, target, out):
@@ -461,29 +481,30 @@ def bce_const_bwd(x, target, gscale, gmul, dx):
 def classifier_fwd(x, w, bias, out):
     n, h, wd, c, ld = _nhwc_meta(x)
     call("b200_classifier_fwd", ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w),
-                                    ptr(bias), ptr(out), stream())
+                                    ptr(bias), ptr(out), stream(), nbytes=2.0 * x.numel(), tag="C%d %dx%d" % (c, h, wd))
 
 
 def classifier_dgrad(dout, w, dx):
     n, h, wd, c, ld = _nhwc_meta(dx)
     call("b200_classifier_dgrad", ptr(dout), c_int(n), c_int(h), c_int(wd), c_int(c), ptr(w), ptr(dx),
-                                      c_int(ld), stream())
+                                      c_int(ld), stream(), nbytes=2.0 * dx.numel(), tag="C%d %dx%d" % (c, h, wd))
 
 
 def classifier_wgrad(dout, x, dw, dbias):
     n, h, wd, c, ld = _nhwc_meta(x)
     call("b200_classifier_wgrad", ptr(dout), ptr(x), c_int(ld), c_int(n), c_int(h), c_int(wd), c_int(c),
-                                      ptr(dw), ptr(dbias), stream())
+                                      ptr(dw), ptr(dbias), stream(), nbytes=2.0 * x.numel(), tag="C%d %dx%d" % (c, h, wd))
 
 
 def cast_f32_bf16(x, y):
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
-    call("b200_cast_f32_bf16", ptr(x), ptr(y), c_int64(x.numel()), stream())
+    call("b200_cast_f32_bf16", ptr(x), ptr(y), c_int64(x.numel()), stream(), nbytes=6.0 * x.numel(), tag="n%d" % x.numel())
     return y
 
 
 def scale_f32(x, num, den, mul, y):
-    call("b200_scale_f32", ptr(x), c_int64(x.numel()), ptr(num), ptr(den), c_float(mul), ptr(y), stream())
+    call("b200_scale_f32", ptr(x), c_int64(x.numel()), ptr(num), ptr(den), c_float(mul), ptr(y), stream(),
+         nbytes=8.0 * x.numel(), tag="n%d" % x.numel())
     return y
 
 
@@ -497,7 +518,7 @@ def image_resize_normalize(src, xb, xk, yb, yk, lut, dst, max_rows):
     assert dst.dtype == torch.float32 and dst.is_contiguous() and dst.shape[1] == 3
     call("b200_image_resize_normalize", ptr(src), c_int(n), c_int(h0), c_int(w0), ptr(xb), ptr(xk),
          c_int(xk.shape[1]), ptr(yb), ptr(yk), c_int(yk.shape[1]), c_int(h), c_int(w), ptr(lut), ptr(dst),
-         c_int(max_rows), stream())
+         c_int(max_rows), stream(), nbytes=float(src.numel() + 4 * dst.numel()), tag="%dx%d->%dx%d" % (h0, w0, h, w))
     return dst
 
 
@@ -508,5 +529,6 @@ def label_resize_remap(src, ix, iy, lut, dst):
     h, w = dst.shape[-2:]
     assert dst.dtype in (torch.uint8, torch.int64)
     call("b200_label_resize_remap", ptr(src), c_int(n), c_int(h0), c_int(w0), ptr(ix), ptr(iy), c_int(h),
-         c_int(w), ptr(lut), ptr(dst), c_int(1 if dst.dtype == torch.int64 else 0), stream())
+         c_int(w), ptr(lut), ptr(dst), c_int(1 if dst.dtype == torch.int64 else 0), stream(),
+         nbytes=float(src.numel() + dst.numel() * dst.element_size()), tag="%dx%d->%dx%d" % (h0, w0, h, w))
     return dst

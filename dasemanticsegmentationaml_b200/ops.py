@@ -79,9 +79,11 @@ def refresh_packs(module, force=False):
             cout, cin, r, s = shape
             rows.append([w.data_ptr(), buf.data_ptr(), cout, cin, r * s, buf.shape[0], buf.shape[2], 1 if tr else 0])
         dev = torch.tensor(rows, dtype=torch.int64).to(stale[0][0].device)
-        tab = (key, dev)
+        nbytes = float(sum(4 * w.numel() + 2 * buf.numel() for w, _, buf in stale))
+        tab = (key, dev, nbytes)
         object.__setattr__(module, "_b200_pack_table", tab)
-    K.call("b200_pack_filters_batched", K.ptr(tab[1]), K.c_int(len(stale)), K.stream())
+    K.call("b200_pack_filters_batched", K.ptr(tab[1]), K.c_int(len(stale)), K.stream(), nbytes=tab[2],
+           tag="%d filters" % len(stale))
     for w, k, buf in stale:
         w._b200_pack[k] = (w._version, w.data_ptr(), buf)
     return len(stale)
@@ -359,7 +361,7 @@ class _WgradScratch(object):
                 raise K._lib.B200Error("weight-gradient scratch layout changed inside a CUDA-graph capture: "
                                        "run the step eagerly (three times) before capturing")
             tab = self.tables[rows] = torch.tensor(rows, dtype=torch.int64).to(schunk.device)
-        K.wgrad_unscratch(schunk, dchunk, tab, len(rows))
+        K.wgrad_unscratch(schunk, dchunk, tab, len(rows), sum(r_[2] * r_[3] * r_[4] for r_ in rows))
         self.flushed.append(rows)
         self.pending = []
 

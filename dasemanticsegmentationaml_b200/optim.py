@@ -38,6 +38,7 @@ class _MultiTensorOptimizer(torch.optim.Optimizer):
         self._hyp_dev = None
         self._hyp_values = None
         self._chunk = None
+        self._n_elems = 0
 
     # -- hyper-parameters ---------------------------------------------------------------------
     def _hyper_row(self, group):
@@ -120,6 +121,7 @@ class _MultiTensorOptimizer(torch.optim.Optimizer):
                 slot[1].record()
             self._table = dev
             self._key, self._n, self._chunks = key, n, chunk0
+            self._n_elems = sum(e[0].numel() for e in entries)
         self.refresh_hyperparameters(device)
         _lib.set_device_index(device.index or 0)
         return True
@@ -162,7 +164,7 @@ class FusedSGD(_MultiTensorOptimizer):
                 loss = closure()
         if self._prepare():
             K.call("b200_sgd_step", K.ptr(self._table), K.c_int(self._n), K.c_int(self._chunks),
-                   K.ptr(self._hyp_dev), K.stream())
+                   K.ptr(self._hyp_dev), K.stream(), nbytes=20.0 * self._n_elems, tag="%d tensors" % self._n)
             for group in self.param_groups:
                 if group["momentum"] != 0:
                     self._stepped.update(id(p) for p in group["params"] if p.grad is not None)
@@ -210,5 +212,6 @@ class FusedAdam(_MultiTensorOptimizer):
                 loss = closure()
         if self._prepare():
             K.call("b200_adam_step", K.ptr(self._table), K.c_int(self._n), K.c_int(self._chunks),
-                   K.ptr(self._hyp_dev), K.ptr(self._counters), K.stream())
+                   K.ptr(self._hyp_dev), K.ptr(self._counters), K.stream(), nbytes=28.0 * self._n_elems,
+                   tag="%d tensors" % self._n)
         return loss

@@ -241,6 +241,22 @@ int b200_count_equal(const void* label, int label_bytes, const void* pred, int p
 int b200_count_equal_batched(const void* label, int label_bytes, const void* pred, int pred_bytes,
                              int n_images, int64_t per_image, int64_t* out, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ collectives (NCCL) */
+/* The two exchange steps of the data-parallel path for callers that do not use torch.distributed
+ * (the Python host of this repository does, and never calls these): one process per GPU, NCCL over
+ * NVLink.  NCCL is dlopen'ed ("libnccl.so.2") at the first call; B200_EDRIVER when it is absent.
+ *   unique_id : rank 0 creates the 128-byte id and hands it to the other ranks out of band
+ *   init      : ncclCommInitRank on the calling thread's current device -> opaque communicator
+ *   allreduce_grads : in-place sum (average != 0: mean) of a flat fp32 gradient bucket over the ranks
+ *                     (the reference's nn.DataParallel gradient reduce, train.py:145-152,497)
+ *   allreduce_hist  : in-place int64 sum of the n*n confusion matrix (train.py:47 over a sharded loader;
+ *                     exact, so the result is bit-identical to a single-process evaluation) */
+int b200_nccl_unique_id(void* id128);
+int b200_nccl_init(const void* id128, int world, int rank, void** comm_out);
+int b200_nccl_allreduce_grads(void* comm, float* flat, int64_t count, int average, cudaStream_t stream);
+int b200_nccl_allreduce_hist(void* comm, int64_t* hist, int count, cudaStream_t stream);
+int b200_nccl_destroy(void* comm);
+
 /* ------------------------------------------------------------------ input pipeline */
 /* pil_loader(path).resize(size, Image.BILINEAR) -> ToTensor() -> Normalize(mean, std)
  * (dataset/cityscapes.py:65,67 and dataset/GTAV.py:85,87; Pillow Resample.c two-pass 8-bit resample).
