@@ -46,7 +46,7 @@ __device__ __forceinline__ float act_grad(float pre, int act, float slope) {
 // and walks pixels in batches of UNR independent 16-byte loads per tensor (memory-level parallelism).
 constexpr int UNR = 4;   // single-tensor kernels
 constexpr int UNR3 = 2;  // kernels streaming three tensors
-constexpr int UNRF = 4;  // the fused BatchNorm backward (register budget of 2 CTAs x 256 threads per SM)
+constexpr int UNRF = 2;  // the fused BatchNorm backward: two batches of UNRF x 3 loads live per thread (double buffering)
 constexpr int kRedRep = 8;  // replicas of the partial-sum buffer of the fused BatchNorm backward
 
 struct Slot {
@@ -160,14 +160,45 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int finalize) {
   const Slot t = slot_of(C);
   float sc[8], sh[8];
+  if (finalize) {
+    // per-channel vectors of this thread's 8 channels with 16-byte loads (the coefficient set-up is a
+    // latency chain every thread runs before its first pixel: it is most of a small layer's time)
+    float a_[8], b_[8], g_[8], be_[8];
+    const int c0 = t.g * 8;
+    auto ld8 = [&](const float* p, float (&o)[8], float dflt) {
+      if (p != nullptr) {
+        const float4 u0 = __ldg(reinterpret_cast<const float4*>(p + c0)), u1 = __ldg(reinterpret_cast<const float4*>(p + c0) + 1);
+        o[0] = u0.x; o[1] = u0.y; o[2] = u0.z; o[3] = u0.w; o[4] = u1.x; o[5] = u1.y; o[6] = u1.z; o[7] = u1.w;
+      } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = t.g * 8 + j;
-    if (finalize) {
-      float mean, var, rstd;
-      bn_coeffs(stats, C, c, count, gamma, beta, running_mean, running_var, eps, training, &mean,
-                &var, &rstd, &sc[j], &sh[j]);
-      if (blockIdx.x == 0 && t.ty == 0) {
+        for (int j = 0; j < 8; ++j) o[j] = dflt;
+      }
+    };
+    if (training) {
+      ld8(stats, a_, 0.f);
+      ld8(stats + C, b_, 0.f);
+    } else {
+      ld8(running_mean, a_, 0.f);
+      ld8(running_var, b_, 1.f);
+    }
+    ld8(gamma, g_, 1.f);
+    ld8(beta, be_, 0.f);
+    const bool publish = blockIdx.x == 0 && t.ty == 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      float mean, var;
+      if (training) {
+        mean = a_[j] / count;
+        var = fmaxf(b_[j] / count - mean * mean, 0.f);
+      } else {
+        mean = a_[j];
+        var = b_[j];
+      }
+      const float rstd = rsqrtf(var + eps);
+      sc[j] = g_[j] * rstd;
+      sh[j] = be_[j] - mean * g_[j] * rstd;
+      if (publish) {
         if (scale != nullptr) {
           scale[c] = sc[j];
           shift[c] = sh[j];
@@ -182,7 +213,11 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
           running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
         }
       }
-    } else {
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = t.g * 8 + j;
       sc[j] = scale != nullptr ? scale[c] : 1.f;
       sh[j] = shift != nullptr ? shift[c] : 0.f;
     }
@@ -320,6 +355,31 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
 // Both backward passes in ONE cooperative launch: reductions, grid-wide barrier, then dz.  The
 // second pass walks the pixels in reverse so that it starts on the lines the first pass touched
 // last (for all but the largest layers dy and z are still L2-resident: no second HBM read).
+//
+// Both passes are software-pipelined: the 16-byte loads of batch i+1 are issued before batch i is
+// reduced / written, so a thread always has loads in flight (the un-pipelined loop paid one full
+// memory latency per batch: 0.30-0.46 of the HBM rate on the large layers, measured with
+// scripts/bench_small.py).  After the grid barrier ONE pass over the kRedRep partial-sum replicas per
+// CTA rebuilds the totals in shared memory (every thread re-reading all replicas for its 8 channels
+// cost 128 L2 loads per thread -- the 12-25 us floor of the small layers).
+struct BwdBatch {
+  uint4 d[UNRF], z[UNRF], e[UNRF];
+};
+
+__device__ __forceinline__ void bwd_load(BwdBatch& b, const __nv_bfloat16* dy1, int dy1_ld, const __nv_bfloat16* dy2,
+                                         int dy2_ld, const __nv_bfloat16* z, int z_ld, int64_t base, int64_t npix,
+                                         const Slot& t) {
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int u = 0; u < UNRF; ++u) {
+    const int64_t p = base + u * t.py + t.ty;
+    const bool ok = base >= 0 && p < npix;
+    b.d[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;  // zero gradient: contributes nothing
+    b.z[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
+    b.e[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
+  }
+}
+
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                         const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
@@ -334,37 +394,37 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   float sc[8], sh[8], a1[8] = {0}, a2[8] = {0};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[t.g * 8 + j];
-    sh[j] = shift[t.g * 8 + j];
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(scale + t.g * 8);
+    const float4* h4 = reinterpret_cast<const float4*>(shift + t.g * 8);
+    const float4 s0 = __ldg(s4), s1 = __ldg(s4 + 1), h0 = __ldg(h4), h1 = __ldg(h4 + 1);
+    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
   }
   const int64_t step = (int64_t)gridDim.x * t.py * UNRF;
-  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int64_t first = (int64_t)blockIdx.x * t.py * UNRF;
   int64_t last_base = -1;
-  for (int64_t base = (int64_t)blockIdx.x * t.py * UNRF; base < npix; base += step) {
-    last_base = base;
-    uint4 rd[UNRF], rz[UNRF], re[UNRF];
+  {
+    BwdBatch cur, nxt;
+    bwd_load(cur, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, first < npix ? first : -1, npix, t);
+    for (int64_t base = first; base < npix; base += step) {
+      last_base = base;
+      const int64_t nb = base + step;
+      bwd_load(nxt, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, nb < npix ? nb : -1, npix, t);
 #pragma unroll
-    for (int u = 0; u < UNRF; ++u) {
-      const int64_t p = base + u * t.py + t.ty;
-      const bool ok = p < npix;
-      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
-      rz[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
-      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
-    }
+      for (int u = 0; u < UNRF; ++u) {
+        float d[8], zz[8], e[8];
+        unpack8(cur.d[u], d);
+        unpack8(cur.z[u], zz);
+        unpack8(cur.e[u], e);
 #pragma unroll
-    for (int u = 0; u < UNRF; ++u) {
-      float d[8], zz[8], e[8];
-      unpack8(rd[u], d);
-      unpack8(rz[u], zz);
-      unpack8(re[u], e);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
-        a1[j] += gg;
-        a2[j] += gg * zz[j];
+        for (int j = 0; j < 8; ++j) {
+          const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+          a1[j] += gg;
+          a2[j] += gg * zz[j];
+        }
       }
+      cur = nxt;
     }
   }
   // block reduction: lanes holding the same channel group fold by shuffles, then one shared-memory
@@ -394,50 +454,45 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
   flush_add_v4(rep, s_acc, 2 * C, threadIdx.x, blockDim.x);
   __threadfence();
   cooperative_groups::this_grid().sync();
+  // totals: one pass over the replicas per CTA, into shared memory
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < kRedRep; ++r) tot += __ldcg(red + (size_t)(1 + r) * 2 * C + i);
+    s_acc[i] = tot;
+    if (blockIdx.x == 0) red[i] = tot;   // for the caller: dbeta = red[0][c], dgamma = red[1][c]
+  }
+  __syncthreads();
   float k0[8], k1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = t.g * 8 + j;
-    float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-    for (int r = 0; r < kRedRep; ++r) {
-      r0 += __ldcg(red + (size_t)(1 + r) * 2 * C + c);
-      r1 += __ldcg(red + (size_t)(1 + r) * 2 * C + C + c);
-    }
-    if (blockIdx.x == 0 && t.ty == 0) {   // totals for the caller: dbeta = red[0][c], dgamma = red[1][c]
-      red[c] = r0;
-      red[C + c] = r1;
-    }
-    r0 *= inv_count;
-    r1 *= inv_count;
+    const float r0 = s_acc[c] * inv_count, r1 = s_acc[C + c] * inv_count;
     k1[j] = -sc[j] * r1 * rstd[c];
     k0[j] = -sc[j] * r0 - k1[j] * mean[c];
   }
-  for (int64_t base = last_base; base >= 0; base -= step) {
-    uint4 rd[UNRF], rz[UNRF], re[UNRF];
+  {
+    BwdBatch cur, nxt;
+    bwd_load(cur, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, last_base, npix, t);
+    for (int64_t base = last_base; base >= 0; base -= step) {
+      bwd_load(nxt, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, base - step, npix, t);   // base - step < 0: nothing
 #pragma unroll
-    for (int u = 0; u < UNRF; ++u) {
-      const int64_t p = base + u * t.py + t.ty;
-      const bool ok = p < npix;
-      rd[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;
-      rz[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
-      re[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
-    }
+      for (int u = 0; u < UNRF; ++u) {
+        const int64_t p = base + u * t.py + t.ty;
+        if (p < npix) {
+          float d[8], zz[8], e[8], o[8];
+          unpack8(cur.d[u], d);
+          unpack8(cur.z[u], zz);
+          unpack8(cur.e[u], e);
 #pragma unroll
-    for (int u = 0; u < UNRF; ++u) {
-      const int64_t p = base + u * t.py + t.ty;
-      if (p < npix) {
-        float d[8], zz[8], e[8], o[8];
-        unpack8(rd[u], d);
-        unpack8(rz[u], zz);
-        unpack8(re[u], e);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
-          o[j] = sc[j] * gg + k1[j] * zz[j] + k0[j];
+          for (int j = 0; j < 8; ++j) {
+            const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+            o[j] = sc[j] * gg + k1[j] * zz[j] + k0[j];
+          }
+          store8(dz + p * dz_ld + t.g * 8, o);
         }
-        store8(dz + p * dz_ld + t.g * 8, o);
       }
+      cur = nxt;
     }
   }
 }

