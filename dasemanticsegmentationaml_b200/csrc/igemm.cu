@@ -149,9 +149,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_bytes = a_sub * p.mt;              // the TMA box spans all sub-tiles
   const uint32_t b_bytes = (uint32_t)p.BN * p.KC * 2u;
   const uint32_t tmem_cols = (uint32_t)(p.mt * p.BN) <= 32 ? 32u : (p.mt * p.BN <= 64 ? 64u : (p.mt * p.BN <= 128 ? 128u : (p.mt * p.BN <= 256 ? 256u : 512u)));
-  const uint32_t stage_bytes = a_bytes + b_bytes;  // both multiples of 1024
   const int cin_blocks = p.cin_pad / p.KC;
-  const int nk = p.n_taps[z] * cin_blocks;
+  // halo mode: a stage = one K-block: the (th+2) x (tw+2) activation box + that block of all taps' filters
+  const uint32_t halo_rows = (uint32_t)(p.th + 2) * (p.tw + 2);
+  const uint32_t halo_tx = halo_rows * p.KC * 2u;
+  const uint32_t halo_bytes = (halo_tx + 1023u) & ~1023u;
+  const uint32_t stage_bytes = p.halo ? halo_bytes + p.n_taps[z] * b_bytes : a_bytes + b_bytes;  // multiples of 1024
+  const int nk = p.halo ? cin_blocks : p.n_taps[z] * cin_blocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -185,6 +189,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int hb = h0 * p.in_stride, wb = w0 * p.in_stride;
       int s = 0;
       uint32_t ph = 0;
+      if (p.halo) {
+        for (int cb = 0; cb < cin_blocks; ++cb) {
+          mbar_wait(empty0 + 8u * s, ph ^ 1u);
+          const uint32_t full = full0 + 8u * s;
+          mbar_expect_tx(full, halo_tx + p.n_taps[z] * b_bytes);
+          const uint32_t sa = smem_base + s * stage_bytes;
+          tma_load_4d(sa, &tmA, full, cb * p.KC, wb - 1, hb - 1, n_img);
+          for (int t = 0; t < p.n_taps[z]; ++t)
+            tma_load_2d(sa + halo_bytes + t * b_bytes, &tmB, full, p.tap_k[z][t] * p.cin_pad + cb * p.KC, n0);
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      } else
       for (int t = 0; t < p.n_taps[z]; ++t) {
         const int hh = hb + p.tap_dh[z][t];
         const int ww = wb + p.tap_dw[z][t];
@@ -218,9 +237,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 0, accum = 0;
       bool ready = false;
+      // halo mode: the A rows of a tap are a window into the halo box -- 8-row groups (one patch row of
+      // tw = 8 pixels) are (tw+2) rows apart, and the window starts (dh+1)*(tw+2) + (dw+1) rows in
+      const uint64_t htmpl = make_smem_desc(0, 16, (uint32_t)(p.tw + 2) * p.KC * 2u, (p.KC == 64) ? 2u : 4u);
+      const uint32_t h_hi = (uint32_t)(htmpl >> 32), h_lo = (uint32_t)htmpl;
       for (int it = 0; it < nk; ++it) {
         if (!ready) mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
+        if (p.halo) {
+          const uint32_t sa = smem_base + s * stage_bytes;
+          for (int t = 0; t < p.n_taps[z]; ++t) {
+            const uint32_t wa = sa + (uint32_t)((p.tap_dh[z][t] + 1) * (p.tw + 2) + (p.tap_dw[z][t] + 1)) * p.KC * 2u;
+            const uint32_t hi = p.halo == 2 ? (h_hi | (((wa >> 7) & 7u) << 17)) : h_hi;
+            const uint32_t a_lo = h_lo | (wa >> 4);
+            const uint32_t b_lo = d_lo | ((sa + halo_bytes + t * b_bytes) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+              umma_f16(tmem, ((uint64_t)hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
+              accum = 1u;
+            }
+          }
+        } else {
         const uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
         const uint32_t b_lo = a_lo + (a_bytes >> 4);
         for (int k = 0; k < ksteps; ++k) {
@@ -228,6 +264,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < p.mt; ++j)
             umma_f16(tmem + j * p.BN, ((uint64_t)d_hi << 32) | (a_lo + j * (a_sub >> 4) + 2u * k), db, idesc, accum);
           accum = 1u;
+        }
         }
         umma_commit(empty0 + 8u * s);  // frees the stage once these MMAs retire
         if (++s == p.stages) {
@@ -674,6 +711,8 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t t
 struct PairBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t fullB[kMaxStages];    // halo mode: the filter ring (full / empty are the activation-halo ring)
+  uint64_t emptyB[kMaxStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
   uint32_t tmem_base;
@@ -750,6 +789,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t a_bytes = 128u * p.KC * 2u;
   const uint32_t b_half = (uint32_t)(p.BN / 2) * p.KC * 2u;
   const uint32_t stage_bytes = (uint32_t)p.kg * (a_bytes + b_half);   // kg K-blocks of A, then kg of B
+  // halo mode (3x3-like stride-1 taps): ring A holds (th+2) x (tw+2) activation boxes, one per K-block;
+  // ring B holds the filter half-tiles of `tb` taps of that K-block
+  const uint32_t halo_tx = (uint32_t)(p.th + 2) * (p.tw + 2) * p.KC * 2u;
+  const uint32_t halo_bytes = (halo_tx + 1023u) & ~1023u;
+  const uint32_t bslot_bytes = (uint32_t)p.tb * b_half;
+  const uint32_t bring_base = smem_base + (uint32_t)p.stages * halo_bytes;
   const int cin_blocks = p.cin_pad / p.KC;
   const int my_n = pair % n_tiles;
   const int m_first = pair / n_tiles, m_step = n_pairs / n_tiles;
@@ -758,9 +803,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_cols = want <= 32 ? 32u : (want <= 64 ? 64u : (want <= 128 ? 128u : (want <= 256 ? 256u : 512u)));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(smem_u32(&bars.full[s]), 1);
       mbar_init(smem_u32(&bars.empty[s]), 1);
+      mbar_init(smem_u32(&bars.fullB[s]), 1);
+      mbar_init(smem_u32(&bars.emptyB[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bars.tfull[b]), 1);
@@ -794,6 +841,38 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int bn_half = p.BN / 2;
       int s = 0;
       uint32_t ph = 0;
+      if (p.halo) {
+        const uint32_t fullB0 = smem_u32(&bars.fullB[0]), emptyB0 = smem_u32(&bars.emptyB[0]);
+        int sb = 0;
+        uint32_t phb = 0;
+        for (int m = m_first; m < m_total; m += m_step) {
+          const TileCoord tc = decode_tile(p, my_n, m);
+          const int h0 = tc.h0 + rank * p.th - 1, w0 = tc.w0 - 1;
+          const int brow = tc.n0 + rank * bn_half;
+          const int ntap = p.n_taps[tc.z];
+          for (int cb = 0; cb < cin_blocks; ++cb) {
+            mbar_wait(empty0 + 8u * s, ph ^ 1u);
+            if (leader) mbar_expect_tx(full0 + 8u * s, 2u * halo_tx);
+            tma_load_4d_pair(smem_base + s * halo_bytes, &tmA, full0 + 8u * s, cb * p.KC, w0, h0, tc.n_img);
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            for (int t0 = 0; t0 < ntap; t0 += p.tb) {
+              mbar_wait(emptyB0 + 8u * sb, phb ^ 1u);
+              const uint32_t fullB = fullB0 + 8u * sb;
+              if (leader) mbar_expect_tx(fullB, 2u * bslot_bytes);
+              uint32_t dst = bring_base + sb * bslot_bytes;
+              for (int j = 0; j < p.tb; ++j, dst += b_half)
+                tma_load_2d_pair(dst, &tmB, fullB, p.tap_k[tc.z][t0 + j] * p.cin_pad + cb * p.KC, brow);
+              if (++sb == p.sb) {
+                sb = 0;
+                phb ^= 1u;
+              }
+            }
+          }
+        }
+      } else
       for (int m = m_first; m < m_total; m += m_step) {
         const TileCoord tc = decode_tile(p, my_n, m);
         const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
@@ -836,6 +915,56 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int s = 0, lt = 0;
       uint32_t ph = 0;
       bool ready = false;
+      if (p.halo) {
+        // A rows of a tap = a window into the halo box: 8-row groups (one patch row of tw = 8 pixels) are
+        // (tw+2) rows apart (SBO), the window starts (dh+1)*(tw+2) + (dw+1) rows in.  The 128-byte swizzle
+        // is a function of the absolute shared-memory address, so a start address that is only 128-byte
+        // aligned addresses the TMA-written box correctly (no descriptor base_offset; measured).
+        const uint64_t htmpl = make_smem_desc(0, 16, (uint32_t)(p.tw + 2) * p.KC * 2u, 2u);
+        const uint32_t h_hi = (uint32_t)(htmpl >> 32), h_lo = (uint32_t)htmpl;
+        const uint32_t fullB0 = smem_u32(&bars.fullB[0]), emptyB0 = smem_u32(&bars.emptyB[0]);
+        int sb = 0;
+        uint32_t phb = 0;
+        for (int m = m_first; m < m_total; m += m_step, ++lt) {
+          const TileCoord tc = decode_tile(p, my_n, m);
+          const int buf = lt & 1;
+          const uint32_t acc = tmem + buf * acc_cols;
+          mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);
+          tc_fence_after();
+          const int ntap = p.n_taps[tc.z];
+          uint32_t accum = 0;
+          for (int cb = 0; cb < cin_blocks; ++cb) {
+            mbar_wait(full0 + 8u * s, ph);
+            const uint32_t abox = smem_base + s * halo_bytes;
+            for (int t0 = 0; t0 < ntap; t0 += p.tb) {
+              if (!ready) mbar_wait(fullB0 + 8u * sb, phb);
+              tc_fence_after();
+              uint32_t b_lo = d_lo | ((bring_base + sb * bslot_bytes) >> 4);
+              for (int j = 0; j < p.tb; ++j, b_lo += b_half >> 4) {
+                const int t = t0 + j;
+                const uint32_t a_lo = h_lo | ((abox + (uint32_t)((p.tap_dh[tc.z][t] + 1) * (p.tw + 2) + p.tap_dw[tc.z][t] + 1) * 128u) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
+                  accum = 1u;
+                }
+              }
+              umma_commit_pair(emptyB0 + 8u * sb, 3);
+              if (++sb == p.sb) {
+                sb = 0;
+                phb ^= 1u;
+              }
+              ready = mbar_try_wait(fullB0 + 8u * sb, phb);
+            }
+            umma_commit_pair(empty0 + 8u * s, 3);   // the halo box is free once all its taps' MMAs retired
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+          umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
+        }
+      } else
       for (int m = m_first; m < m_total; m += m_step, ++lt) {
         const TileCoord tc = decode_tile(p, my_n, m);
         const int buf = lt & 1;
@@ -1467,6 +1596,28 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   int max_wo = 0;
   for (int z = 0; z < n_classes; ++z) max_wo = class_Wo[z] > max_wo ? class_Wo[z] : max_wo;
   pick_patch(max_wo, &p.th, &p.tw, 128);
+  // bits 23 / 27: input-halo reuse (3x3 stride-1 convs, one-CTA kernel): 16 x 8 pixel patches, see ConvParams::halo
+  // Halo reuse applies when every tap of every class lies in [-1, 1]^2 at input stride 1 (3x3 stride-1
+  // convs and their data gradients; the four parity classes of a 4x4 / 3x3 stride-2 data gradient) and
+  // the K blocks are 64 channels (128-byte rows).  tune == 0: on whenever it applies and saves traffic.
+  bool halo_ok = in_stride == 1 && p.KC == 64;
+  int min_taps = kMaxTaps;
+  for (int z = 0; halo_ok && z < n_classes; ++z) {
+    min_taps = class_ntaps[z] < min_taps ? class_ntaps[z] : min_taps;
+    for (int t = 0; halo_ok && t < class_ntaps[z]; ++t) {
+      const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
+      halo_ok = tp[0] >= -1 && tp[0] <= 1 && tp[1] >= -1 && tp[1] <= 1;
+    }
+  }
+  int halo_mode = ((tune >> 23) & 1) ? (((tune >> 27) & 1) ? 2 : 1) : 0;
+  if (tune == 0 && pair_mode && halo_ok && min_taps >= 4) halo_mode = 1;
+  if (halo_mode) {
+    if (!halo_ok || (!pair_mode && n_classes != 1))
+      return set_error(B200_EINVAL, "conv_igemm: halo mode needs stride-1 taps in [-1, 1]^2 and 64-channel K blocks");
+    p.tw = 8;
+    p.th = 16;
+    p.halo = halo_mode;
+  }
   int max_nk = 0;
   for (int z = 0; z < n_classes; ++z) {
     if (class_ntaps[z] > kMaxTaps) return set_error(B200_EINVAL, "conv_igemm: too many taps");
@@ -1535,7 +1686,20 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     p.stages = st;
   }
   if (st_override >= 2) p.stages = st_override;
-  if (!pair_mode && (p.stages < 2 || p.stages * stage_bytes > 222 * 1024))
+  int halo_stage = 0;
+  if (p.halo && !pair_mode) {
+    p.mt = 1;
+    halo_stage = (((p.th + 2) * (p.tw + 2) * p.KC * 2 + 1023) & ~1023) + class_ntaps[0] * p.BN * p.KC * 2;
+    p.stages = (216 * 1024) / halo_stage;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    if (p.stages < 2) return set_error(B200_EINVAL, "conv_igemm: halo tile does not fit shared memory (BN too wide)");
+    for (int z = 0; z < n_classes; ++z) {
+      p.tiles_h[z] = (class_Ho[z] + p.th - 1) / p.th;
+      p.tiles_w[z] = (class_Wo[z] + p.tw - 1) / p.tw;
+    }
+    max_tiles = p.tiles_h[0] * p.tiles_w[0] * N;
+  }
+  if (!pair_mode && !p.halo && (p.stages < 2 || p.stages * stage_bytes > 222 * 1024))
     return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
   p.out = out;
   p.out_ld = out_ld;
@@ -1576,6 +1740,39 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     }
     if (kg > 8) kg = 8;
     const int kPairDyn = 200 * 1024;   // 227 KB - 23 KB static (barriers, statistics, transpose tiles) - alignment slack
+    if (p.halo) {
+      // ring A: activation boxes (3 slots), ring B: filter half-tiles of `tb` taps per slot.  tb (tune bits
+      // 24-26, 0 = automatic): as many taps as keep a slot <= 24 KB, and a divisor of every class's tap count
+      const int halo_slot = ((p.th + 2) * (p.tw + 2) * p.KC * 2 + 1023) & ~1023;
+      const int b_half = (p.BN / 2) * p.KC * 2;
+      int tb = (tune >> 24) & 7;
+      if (tb == 0) tb = 3;   // (measured: one barrier round trip per 3 taps beats per-tap slots at every BN)
+      for (int z = 0; z < n_classes; ++z)
+        while (tb > 1 && class_ntaps[z] % tb) --tb;
+      p.tb = tb;
+      p.stages = st_override >= 2 ? st_override : (tb * b_half >= 48 * 1024 ? 2 : 3);
+      if (p.stages > kMaxStages) p.stages = kMaxStages;
+      int sb = (kPairDyn - p.stages * halo_slot) / (tb * b_half);
+      if (sb > kMaxStages) sb = kMaxStages;
+      if (sb < 2) return set_error(B200_EINVAL, "conv_igemm: halo rings do not fit shared memory");
+      p.sb = sb;
+      rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw + 2, p.th + 2, 1, p.KC * 2);
+      if (rc) return rc;
+      rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN / 2, p.KC * 2);
+      if (rc) return rc;
+      int m_total = 0;
+      for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
+      const int n_tiles = filt_rows / p.BN;
+      const int total_tiles = m_total * n_tiles;
+      const size_t psmem = (size_t)p.stages * halo_slot + (size_t)sb * tb * b_half + 1024;
+      int pairs = max_active_pairs(psmem);
+      if (pairs > total_tiles) pairs = total_tiles;
+      pairs = (pairs / n_tiles) * n_tiles;
+      if (pairs < n_tiles) pairs = n_tiles;
+      p.kg = 1;
+      conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
+      return check_launch("conv_igemm(pair, halo)");
+    }
     while (kg > 1 && (cin_blocks % kg || 3 * kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2) > kPairDyn)) --kg;
     p.kg = kg;
     const int pstage = kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2);
@@ -1600,12 +1797,13 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
     return check_launch("conv_igemm(pair)");
   }
-  rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
+  rc = p.halo ? make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw + 2, p.th + 2, 1, p.KC * 2)
+              : make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
   if (rc) return rc;
   rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);
   if (rc) return rc;
 
-  size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  size_t smem = (size_t)p.stages * (p.halo ? halo_stage : stage_bytes) + 1024;
   const int persist = (tune >> 20) & 1;
   // bit 21: keep the CTA's filter tile resident in shared memory (persistent kernel only)
   int b_res = (tune >> 21) & 1;

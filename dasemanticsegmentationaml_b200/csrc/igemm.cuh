@@ -51,6 +51,9 @@ struct ConvParams {
   int stats_sum_only;
   int wide;          // 1: output (and mask) rows are 32-byte aligned -> 256-bit stores / loads
   int kg;            // K-blocks (of KC channels) per pipeline stage (CTA-pair kernel)
+  int tb, sb;        // halo mode of the pair kernel: taps per filter-ring slot, filter-ring slots
+  int halo;          // 3x3 stride-1 input-halo reuse: ONE (th+2) x (tw+2) activation box per K-block, the taps
+                     // are shifted descriptor windows into it (1: plain start address, 2: + descriptor base_offset)
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]

@@ -83,15 +83,26 @@ log("distinct shapes:", len(records))
 
 
 def timeit(fn, reps=10):
-    best = 1e9
-    for _ in range(2):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    """GPU time per launch INSIDE a CUDA graph (reps launches captured once, the graph replayed): that is
+    how the train step runs the kernels.  Eager back-to-back launches are host-bound below ~15 us (ctypes
+    call + two tensor-map encodes per launch), which hid the differences between small-layer tiles."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
         for _ in range(reps):
             fn()
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / reps * 1e3)
+    del g
     return best
 
 
@@ -217,6 +228,18 @@ for key, (kind, m) in sorted(records.items()):
                     if not correct(tune):
                         continue
                     results.append((timeit(lambda: run(tune)), tune, "BN%d KG%d PAIR" % (bn, kg)))
+                except Exception:
+                    continue
+            # CTA-pair kernel with input-halo reuse (bit 23; the launcher rejects shapes it does not apply
+            # to): BN x taps per filter-ring slot x activation-ring depth
+            for bn, tb, sa in itertools.product((256, 128, 64, 32), (1, 2, 3), (2, 3)):
+                if m["rows"] % bn:
+                    continue
+                tune = bn | (tb << 24) | (sa << 16) | (3 << 22)
+                try:
+                    if not correct(tune):
+                        continue
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d TB%d SA%d HALO PAIR" % (bn, tb, sa)))
                 except Exception:
                     continue
         results.sort()

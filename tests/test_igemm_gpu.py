@@ -239,7 +239,13 @@ def test_conv_pair_kernel(cuda_lib, case, bn):
     bias = torch.randn(filt.shape[0], device="cuda", generator=g)
     ref = F.leaky_relu(ref + bias[:rows], 0.2)
     outs, sts = [], []
-    for word in (bn | (1 << 22), bn | (1 << 22) | (3 << 16), 0):
+    words = [bn | (1 << 22), bn | (1 << 22) | (3 << 16), 0]
+    k_ch = cout if dgrad else cin
+    if k_ch % 64 == 0 and ((r == 3 and stride == 1) or (dgrad and r in (3, 4))):
+        # input-halo reuse (bit 23): shifted descriptor windows into one (th+2) x (tw+2) box per K-block;
+        # bits 24-26 = taps per filter-ring slot
+        words = [bn | (3 << 22), bn | (3 << 22) | (1 << 24), bn | (3 << 22) | (2 << 16)] + words
+    for word in words:
         out = torch.full((n, geom["Hout"], geom["Wout"], filt.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
         stats = torch.zeros(2, filt.shape[0], device="cuda")
         K.conv_igemm(inp, filt, out, geom, bias=bias, act=2, slope=0.2, stats=stats, bn_tile=word)
@@ -250,4 +256,28 @@ def test_conv_pair_kernel(cuda_lib, case, bn):
         assert rel_l2(stats[0], flat.sum(0)) < 1e-3
         assert rel_l2(stats[1], (flat * flat).sum(0)) < 1e-3
         outs.append(out)
-    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2])
+    # same K order (taps outer, channel blocks inner) -> bit-identical across tile shapes / kernels; the
+    # halo mode walks channel blocks outer, taps inner: same tolerance, different fp32 rounding
+    plain = [o for o, wd in zip(outs, words) if not (wd >> 23) & 1 and wd != 0]
+    for o in plain[1:]:
+        assert torch.equal(o, plain[0])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("case", [(2, 64, 64, 32, 32, 3, 1, 1), (2, 128, 64, 19, 37, 3, 1, 1), (1, 256, 32, 48, 24, 3, 1, 1)])
+def test_conv_halo_window(cuda_lib, case, variant):
+    """Input-halo reuse (tune bit 23): one (th+2) x (tw+2) activation box per K-block, the nine taps are
+    shifted UMMA descriptor windows into it (variant 2 additionally sets the descriptor's base_offset)."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = case
+    x, wgt = make_case(*case)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wgt, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    filt = K.pack_filter(wgt)
+    geom = K.fwd_geometry(h, w, r, r, stride, pad)
+    out = torch.full((n, geom["Hout"], geom["Wout"], filt.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
+    word = min(64, cout) | (1 << 23) | ((1 << 27) if variant == 2 else 0)
+    K.conv_igemm(x, filt, out, geom, bn_tile=word)
+    torch.cuda.synchronize()
+    err = rel_l2(out[..., :cout], ref)
+    print("halo variant", variant, case, "rel-L2", err)
+    assert err < 4e-3, err

@@ -96,7 +96,10 @@ def test_tuned_conv_entry(cuda_lib, key):
                 assert rel_l2(stats[1], (flat * flat).sum(0)) < 1e-3, (key, word)
         outs.append(out.clone())
         del obuf
-    assert torch.equal(outs[0], outs[1]), "tuned and heuristic tiles disagree bit-wise: %s" % key
+    # (the input-halo mode -- tune bit 23, or the heuristic on 3x3-like stride-1 taps -- accumulates channel
+    #  blocks outer / taps inner, i.e. in another fp32 order: both are within tolerance, not bit-identical)
+    if rel_l2(outs[0], outs[1]) > 0:
+        assert rel_l2(outs[0], outs[1]) < 4e-3, "tuned and heuristic tiles disagree: %s" % key
 
 
 @pytest.mark.parametrize("key", TC.wgrad_keys())
