@@ -149,13 +149,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_bytes = a_sub * p.mt;              // the TMA box spans all sub-tiles
   const uint32_t b_bytes = (uint32_t)p.BN * p.KC * 2u;
   const uint32_t tmem_cols = (uint32_t)(p.mt * p.BN) <= 32 ? 32u : (p.mt * p.BN <= 64 ? 64u : (p.mt * p.BN <= 128 ? 128u : (p.mt * p.BN <= 256 ? 256u : 512u)));
+  const uint32_t stage_bytes = a_bytes + b_bytes;  // both multiples of 1024
   const int cin_blocks = p.cin_pad / p.KC;
-  // halo mode: a stage = one K-block: the (th+2) x (tw+2) activation box + that block of all taps' filters
-  const uint32_t halo_rows = (uint32_t)(p.th + 2) * (p.tw + 2);
-  const uint32_t halo_tx = halo_rows * p.KC * 2u;
-  const uint32_t halo_bytes = (halo_tx + 1023u) & ~1023u;
-  const uint32_t stage_bytes = p.halo ? halo_bytes + p.n_taps[z] * b_bytes : a_bytes + b_bytes;  // multiples of 1024
-  const int nk = p.halo ? cin_blocks : p.n_taps[z] * cin_blocks;
+  const int nk = p.n_taps[z] * cin_blocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -189,21 +185,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int hb = h0 * p.in_stride, wb = w0 * p.in_stride;
       int s = 0;
       uint32_t ph = 0;
-      if (p.halo) {
-        for (int cb = 0; cb < cin_blocks; ++cb) {
-          mbar_wait(empty0 + 8u * s, ph ^ 1u);
-          const uint32_t full = full0 + 8u * s;
-          mbar_expect_tx(full, halo_tx + p.n_taps[z] * b_bytes);
-          const uint32_t sa = smem_base + s * stage_bytes;
-          tma_load_4d(sa, &tmA, full, cb * p.KC, wb - 1, hb - 1, n_img);
-          for (int t = 0; t < p.n_taps[z]; ++t)
-            tma_load_2d(sa + halo_bytes + t * b_bytes, &tmB, full, p.tap_k[z][t] * p.cin_pad + cb * p.KC, n0);
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-      } else
       for (int t = 0; t < p.n_taps[z]; ++t) {
         const int hh = hb + p.tap_dh[z][t];
         const int ww = wb + p.tap_dw[z][t];
@@ -237,26 +218,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 0, accum = 0;
       bool ready = false;
-      // halo mode: the A rows of a tap are a window into the halo box -- 8-row groups (one patch row of
-      // tw = 8 pixels) are (tw+2) rows apart, and the window starts (dh+1)*(tw+2) + (dw+1) rows in
-      const uint64_t htmpl = make_smem_desc(0, 16, (uint32_t)(p.tw + 2) * p.KC * 2u, (p.KC == 64) ? 2u : 4u);
-      const uint32_t h_hi = (uint32_t)(htmpl >> 32), h_lo = (uint32_t)htmpl;
       for (int it = 0; it < nk; ++it) {
         if (!ready) mbar_wait(full0 + 8u * s, ph);
         tc_fence_after();
-        if (p.halo) {
-          const uint32_t sa = smem_base + s * stage_bytes;
-          for (int t = 0; t < p.n_taps[z]; ++t) {
-            const uint32_t wa = sa + (uint32_t)((p.tap_dh[z][t] + 1) * (p.tw + 2) + (p.tap_dw[z][t] + 1)) * p.KC * 2u;
-            const uint32_t hi = p.halo == 2 ? (h_hi | (((wa >> 7) & 7u) << 17)) : h_hi;
-            const uint32_t a_lo = h_lo | (wa >> 4);
-            const uint32_t b_lo = d_lo | ((sa + halo_bytes + t * b_bytes) >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              umma_f16(tmem, ((uint64_t)hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
-              accum = 1u;
-            }
-          }
-        } else {
         const uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
         const uint32_t b_lo = a_lo + (a_bytes >> 4);
         for (int k = 0; k < ksteps; ++k) {
@@ -264,7 +228,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < p.mt; ++j)
             umma_f16(tmem + j * p.BN, ((uint64_t)d_hi << 32) | (a_lo + j * (a_sub >> 4) + 2u * k), db, idesc, accum);
           accum = 1u;
-        }
         }
         umma_commit(empty0 + 8u * s);  // frees the stage once these MMAs retire
         if (++s == p.stages) {
@@ -774,7 +737,7 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ ConvParams p, int m_total, int n_tiles) {
+                       const __grid_constant__ ConvParams p, int m_total, int n_tiles, int n_slabs) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PairBarriers bars;
   __shared__ float s_stats[2][256];
@@ -789,10 +752,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t a_bytes = 128u * p.KC * 2u;
   const uint32_t b_half = (uint32_t)(p.BN / 2) * p.KC * 2u;
   const uint32_t stage_bytes = (uint32_t)p.kg * (a_bytes + b_half);   // kg K-blocks of A, then kg of B
-  // halo mode (3x3-like stride-1 taps): ring A holds (th+2) x (tw+2) activation boxes, one per K-block;
-  // ring B holds the filter half-tiles of `tb` taps of that K-block
-  const uint32_t halo_tx = (uint32_t)(p.th + 2) * (p.tw + 2) * p.KC * 2u;
-  const uint32_t halo_bytes = (halo_tx + 1023u) & ~1023u;
+  // halo mode: ring A holds the activation boxes of one K-block per slot (np boxes of box_h x box_w pixels);
+  // ring B holds the filter half-tiles of `tb` taps of that K-block (or the whole filter tile, resident)
+  const uint32_t plane_tx = (uint32_t)p.box_h * p.box_w * p.KC * 2u;
+  const uint32_t plane_bytes = (plane_tx + 1023u) & ~1023u;
+  const uint32_t halo_bytes = (uint32_t)p.np * plane_bytes;
   const uint32_t bslot_bytes = (uint32_t)p.tb * b_half;
   const uint32_t bring_base = smem_base + (uint32_t)p.stages * halo_bytes;
   const int cin_blocks = p.cin_pad / p.KC;
@@ -845,19 +809,29 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t fullB0 = smem_u32(&bars.fullB[0]), emptyB0 = smem_u32(&bars.emptyB[0]);
         int sb = 0;
         uint32_t phb = 0;
+        if (p.bres) {   // the pair's filter tile: every slab, every K-block, once
+          const uint32_t fb = fullB0;
+          const int nblk = n_slabs * cin_blocks;
+          if (leader) mbar_expect_tx(fb, 2u * (uint32_t)nblk * b_half);
+          for (int kb = 0; kb < nblk; ++kb)
+            tma_load_2d_pair(bring_base + kb * b_half, &tmB, fb, kb * p.KC, my_n * p.BN + rank * bn_half);
+        }
         for (int m = m_first; m < m_total; m += m_step) {
           const TileCoord tc = decode_tile(p, my_n, m);
-          const int h0 = tc.h0 + rank * p.th - 1, w0 = tc.w0 - 1;
+          const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
           const int brow = tc.n0 + rank * bn_half;
           const int ntap = p.n_taps[tc.z];
           for (int cb = 0; cb < cin_blocks; ++cb) {
             mbar_wait(empty0 + 8u * s, ph ^ 1u);
-            if (leader) mbar_expect_tx(full0 + 8u * s, 2u * halo_tx);
-            tma_load_4d_pair(smem_base + s * halo_bytes, &tmA, full0 + 8u * s, cb * p.KC, w0, h0, tc.n_img);
+            if (leader) mbar_expect_tx(full0 + 8u * s, 2u * (uint32_t)p.np * plane_tx);
+            for (int q = 0; q < p.np; ++q)
+              tma_load_4d_pair(smem_base + s * halo_bytes + q * plane_bytes, &tmA, full0 + 8u * s, cb * p.KC,
+                               w0 + p.pl_dw[q], h0 + p.pl_dh[q], tc.n_img);
             if (++s == p.stages) {
               s = 0;
               ph ^= 1u;
             }
+            if (p.bres) continue;
             for (int t0 = 0; t0 < ntap; t0 += p.tb) {
               mbar_wait(emptyB0 + 8u * sb, phb ^ 1u);
               const uint32_t fullB = fullB0 + 8u * sb;
@@ -916,15 +890,18 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       uint32_t ph = 0;
       bool ready = false;
       if (p.halo) {
-        // A rows of a tap = a window into the halo box: 8-row groups (one patch row of tw = 8 pixels) are
-        // (tw+2) rows apart (SBO), the window starts (dh+1)*(tw+2) + (dw+1) rows in.  The 128-byte swizzle
-        // is a function of the absolute shared-memory address, so a start address that is only 128-byte
-        // aligned addresses the TMA-written box correctly (no descriptor base_offset; measured).
-        const uint64_t htmpl = make_smem_desc(0, 16, (uint32_t)(p.tw + 2) * p.KC * 2u, 2u);
+        // A rows of a tap = a window into one of the K-block's boxes: 8-row groups (one patch row of
+        // tw = 8 pixels) are box_w rows apart (SBO), the window starts tap_off rows in.  The swizzle is a
+        // function of the absolute shared-memory address, so a start address that is only row-aligned
+        // addresses the TMA-written box correctly (no descriptor base_offset; measured).
+        const uint32_t row_bytes = (uint32_t)p.KC * 2u;
+        const uint64_t htmpl = make_smem_desc(0, 16, (uint32_t)p.box_w * row_bytes, (p.KC == 64) ? 2u : 4u);
         const uint32_t h_hi = (uint32_t)(htmpl >> 32), h_lo = (uint32_t)htmpl;
         const uint32_t fullB0 = smem_u32(&bars.fullB[0]), emptyB0 = smem_u32(&bars.emptyB[0]);
+        const int ksteps = p.KC / 16;
         int sb = 0;
         uint32_t phb = 0;
+        if (p.bres) mbar_wait(fullB0, 0);
         for (int m = m_first; m < m_total; m += m_step, ++lt) {
           const TileCoord tc = decode_tile(p, my_n, m);
           const int buf = lt & 1;
@@ -937,26 +914,33 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_wait(full0 + 8u * s, ph);
             const uint32_t abox = smem_base + s * halo_bytes;
             for (int t0 = 0; t0 < ntap; t0 += p.tb) {
-              if (!ready) mbar_wait(fullB0 + 8u * sb, phb);
+              uint32_t b_lo;
+              if (p.bres) {
+                b_lo = 0;
+              } else {
+                if (!ready) mbar_wait(fullB0 + 8u * sb, phb);
+                b_lo = d_lo | ((bring_base + sb * bslot_bytes) >> 4);
+              }
               tc_fence_after();
-              uint32_t b_lo = d_lo | ((bring_base + sb * bslot_bytes) >> 4);
               for (int j = 0; j < p.tb; ++j, b_lo += b_half >> 4) {
                 const int t = t0 + j;
-                const uint32_t a_lo = h_lo | ((abox + (uint32_t)((p.tap_dh[tc.z][t] + 1) * (p.tw + 2) + p.tap_dw[tc.z][t] + 1) * 128u) >> 4);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                if (p.bres) b_lo = d_lo | ((bring_base + (uint32_t)(p.tap_k[tc.z][t] * cin_blocks + cb) * b_half) >> 4);
+                const uint32_t a_lo = h_lo | ((abox + (uint32_t)p.tap_pl[tc.z][t] * plane_bytes + (uint32_t)p.tap_off[tc.z][t] * row_bytes) >> 4);
+                for (int k = 0; k < ksteps; ++k) {
                   umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
                   accum = 1u;
                 }
               }
-              umma_commit_pair(emptyB0 + 8u * sb, 3);
-              if (++sb == p.sb) {
-                sb = 0;
-                phb ^= 1u;
+              if (!p.bres) {
+                umma_commit_pair(emptyB0 + 8u * sb, 3);
+                if (++sb == p.sb) {
+                  sb = 0;
+                  phb ^= 1u;
+                }
+                ready = mbar_try_wait(fullB0 + 8u * sb, phb);
               }
-              ready = mbar_try_wait(fullB0 + 8u * sb, phb);
             }
-            umma_commit_pair(empty0 + 8u * s, 3);   // the halo box is free once all its taps' MMAs retired
+            umma_commit_pair(empty0 + 8u * s, 3);   // the boxes are free once all their taps' MMAs retired
             if (++s == p.stages) {
               s = 0;
               ph ^= 1u;
@@ -1247,10 +1231,14 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
   constexpr uint32_t a_box = kPix * 128u;           // [64 px][64 co] bf16
   constexpr uint32_t b_box = kPix * 64u;            // [64 px][32 ci] bf16
   const uint32_t a_bytes = 2u * a_box;
-  const uint32_t stage_bytes = a_bytes + p.n_taps * b_box;
+  // input as one shifted box per tap (np == 0), or as np halo boxes shared by all taps
+  const uint32_t plane_tx = (uint32_t)p.box_h * p.box_w * 64u;
+  const uint32_t plane_bytes = (plane_tx + 1023u) & ~1023u;
+  const uint32_t b_total = p.np ? (uint32_t)p.np * plane_bytes : p.n_taps * b_box;
+  const uint32_t stage_bytes = a_bytes + b_total;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const bool two_a = (co0 + 64) < p.Cout;
-  const uint32_t tx_bytes = (two_a ? a_bytes : a_box) + p.n_taps * b_box;
+  const uint32_t tx_bytes = (two_a ? a_bytes : a_box) + (p.np ? (uint32_t)p.np * plane_tx : p.n_taps * b_box);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -1297,9 +1285,15 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
         const uint32_t sa = smem_base + s * stage_bytes;
         tma_load_4d(sa, &tmDZ, full, co0, w0, h0, n_img);
         if (two_a) tma_load_4d(sa + a_box, &tmDZ, full, co0 + 64, w0, h0, n_img);
-        for (int t = 0; t < p.n_taps; ++t)
-          tma_load_4d(sa + a_bytes + t * b_box, &tmX, full, 0, w0 * p.in_stride + p.tap_dw[t],
-                      h0 * p.in_stride + p.tap_dh[t], n_img);
+        if (p.np) {
+          for (int q = 0; q < p.np; ++q)
+            tma_load_4d(sa + a_bytes + q * plane_bytes, &tmX, full, 0, w0 * p.in_stride + p.pl_dw[q],
+                        h0 * p.in_stride + p.pl_dh[q], n_img);
+        } else {
+          for (int t = 0; t < p.n_taps; ++t)
+            tma_load_4d(sa + a_bytes + t * b_box, &tmX, full, 0, w0 * p.in_stride + p.tap_dw[t],
+                        h0 * p.in_stride + p.tap_dh[t], n_img);
+        }
       }
     }
   } else if (warp == 1) {
@@ -1313,11 +1307,16 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
         const uint32_t sa = smem_base + s * stage_bytes;
         const uint32_t sb = sa + a_bytes;
         for (int t = 0; t < p.n_taps; ++t) {
+          // B: 64B swizzle, rows of 32 ci (64 B), one MN atom wide.  Per-tap boxes: 8-pixel groups 512 B
+          // apart.  Halo boxes (8 x 8 pixel tiles): an 8-pixel group is one patch row, box_w rows apart, and
+          // the tap's window starts tap_off rows into its box (swizzle by absolute address: no base offset).
+          const uint32_t bt = p.np ? sb + (uint32_t)p.tap_pl[t] * plane_bytes + (uint32_t)p.tap_off[t] * 64u : sb + t * b_box;
+          const uint32_t bstep = p.np ? 2u * p.box_w * 64u : 1024u;
+          const uint32_t bsbo = p.np ? (uint32_t)p.box_w * 64u : 512u;
           for (int k = 0; k < (int)kPix / 16; ++k) {
             // A: 128B swizzle, 8-pixel groups 1024 B apart, 64-co halves one box apart
             const uint64_t da = make_smem_desc(sa + k * 2048, a_box, 1024, 2);
-            // B: 64B swizzle, rows of 32 ci (64 B), 8-pixel groups 512 B apart, one MN atom wide
-            const uint64_t db = make_smem_desc(sb + t * b_box + k * 1024, 16, 512, 4);
+            const uint64_t db = make_smem_desc(bt + k * bstep, 16, bsbo, 4);
             umma_f16(tmem + t * 32, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
         }
@@ -1492,6 +1491,53 @@ static int pick_stages(int stage_bytes, int nk) {
   return s;
 }
 
+
+// d = s * q + r with 0 <= r < s (floor division): a tap offset d at input stride s reads plane r at offset q.
+static void split_tap(int d, int s, int* q, int* r) {
+  *r = ((d % s) + s) % s;
+  *q = (d - *r) / s;
+}
+
+// Decompose `n` taps (dh, dw at taps[3*t], taps[3*t+1]) at input stride s (1 or 2) into s*s input-parity
+// planes; false when a plane's offsets span more than 3 positions.
+static bool plan_planes(const int* taps, int n, int s, TapPlanes* tp) {
+  if ((s != 1 && s != 2) || n > kMaxTaps) return false;
+  memset(tp, 0, sizeof(*tp));
+  tp->np = s * s;
+  int qmin_h[4], qmax_h[4], qmin_w[4], qmax_w[4];
+  for (int q = 0; q < 4; ++q) {
+    qmin_h[q] = qmin_w[q] = 1 << 20;
+    qmax_h[q] = qmax_w[q] = -(1 << 20);
+  }
+  for (int t = 0; t < n; ++t) {
+    int qh, rh, qw, rw;
+    split_tap(taps[3 * t], s, &qh, &rh);
+    split_tap(taps[3 * t + 1], s, &qw, &rw);
+    const int pl = rh * s + rw;
+    qmin_h[pl] = qh < qmin_h[pl] ? qh : qmin_h[pl];
+    qmax_h[pl] = qh > qmax_h[pl] ? qh : qmax_h[pl];
+    qmin_w[pl] = qw < qmin_w[pl] ? qw : qmin_w[pl];
+    qmax_w[pl] = qw > qmax_w[pl] ? qw : qmax_w[pl];
+  }
+  for (int q = 0; q < tp->np; ++q) {
+    if (qmax_h[q] < qmin_h[q]) qmin_h[q] = qmax_h[q] = qmin_w[q] = qmax_w[q] = 0;
+    tp->eh = qmax_h[q] - qmin_h[q] > tp->eh ? qmax_h[q] - qmin_h[q] : tp->eh;
+    tp->ew = qmax_w[q] - qmin_w[q] > tp->ew ? qmax_w[q] - qmin_w[q] : tp->ew;
+    tp->pl_dh[q] = s * qmin_h[q] + q / s;
+    tp->pl_dw[q] = s * qmin_w[q] + q % s;
+  }
+  for (int t = 0; t < n; ++t) {
+    int qh, rh, qw, rw;
+    split_tap(taps[3 * t], s, &qh, &rh);
+    split_tap(taps[3 * t + 1], s, &qw, &rw);
+    const int pl = rh * s + rw;
+    tp->tap_pl[t] = (int8_t)pl;
+    tp->tap_qh[t] = (int8_t)(qh - qmin_h[pl]);
+    tp->tap_qw[t] = (int8_t)(qw - qmin_w[pl]);
+  }
+  return tp->eh <= 2 && tp->ew <= 2;
+}
+
 static int g_smem_optin_done = 0;
 static int ensure_smem_optin() {
   if (g_smem_optin_done) return B200_OK;
@@ -1596,28 +1642,76 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   int max_wo = 0;
   for (int z = 0; z < n_classes; ++z) max_wo = class_Wo[z] > max_wo ? class_Wo[z] : max_wo;
   pick_patch(max_wo, &p.th, &p.tw, 128);
-  // bits 23 / 27: input-halo reuse (3x3 stride-1 convs, one-CTA kernel): 16 x 8 pixel patches, see ConvParams::halo
-  // Halo reuse applies when every tap of every class lies in [-1, 1]^2 at input stride 1 (3x3 stride-1
-  // convs and their data gradients; the four parity classes of a 4x4 / 3x3 stride-2 data gradient) and
-  // the K blocks are 64 channels (128-byte rows).  tune == 0: on whenever it applies and saves traffic.
-  bool halo_ok = in_stride == 1 && p.KC == 64;
+  // Input-halo reuse (tune bit 23; see ConvParams::halo).  Every tap (dh, dw) of every class is
+  // decomposed as  input pixel = in_stride * (h + qh) + rh  with rh = dh mod in_stride: taps with the same
+  // (rh, rw) read the same input-parity plane at offsets (qh, qw).  Applicable when the planes' offset
+  // ranges are small (3x3 / 4x4 filters: extents <= 2): stride-1 convs and data gradients have one plane,
+  // stride-2 convs four.  tune == 0: on whenever a box serves >= 4 taps (CTA-pair kernel only).
+  int halo_mode = (tune >> 23) & 1;
+  bool halo_ok = pair_mode && (in_stride == 1 || in_stride == 2);
   int min_taps = kMaxTaps;
-  for (int z = 0; halo_ok && z < n_classes; ++z) {
-    min_taps = class_ntaps[z] < min_taps ? class_ntaps[z] : min_taps;
-    for (int t = 0; halo_ok && t < class_ntaps[z]; ++t) {
-      const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
-      halo_ok = tp[0] >= -1 && tp[0] <= 1 && tp[1] >= -1 && tp[1] <= 1;
+  if (halo_ok) {
+    const int s = in_stride, np = s * s;
+    int qmin_h[4], qmax_h[4], qmin_w[4], qmax_w[4];
+    for (int q = 0; q < 4; ++q) {
+      qmin_h[q] = qmin_w[q] = 1 << 20;
+      qmax_h[q] = qmax_w[q] = -(1 << 20);
+    }
+    auto split = [s](int d, int* q, int* r) {   // d = s * q + r, 0 <= r < s (floor division)
+      *r = ((d % s) + s) % s;
+      *q = (d - *r) / s;
+    };
+    for (int z = 0; z < n_classes; ++z) {
+      min_taps = class_ntaps[z] < min_taps ? class_ntaps[z] : min_taps;
+      for (int t = 0; t < class_ntaps[z] && t < kMaxTaps; ++t) {
+        const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
+        int qh, rh, qw, rw;
+        split(tp[0], &qh, &rh);
+        split(tp[1], &qw, &rw);
+        const int pl = rh * s + rw;
+        qmin_h[pl] = qh < qmin_h[pl] ? qh : qmin_h[pl];
+        qmax_h[pl] = qh > qmax_h[pl] ? qh : qmax_h[pl];
+        qmin_w[pl] = qw < qmin_w[pl] ? qw : qmin_w[pl];
+        qmax_w[pl] = qw > qmax_w[pl] ? qw : qmax_w[pl];
+      }
+    }
+    int eh = 0, ew = 0;
+    for (int q = 0; q < np; ++q) {
+      if (qmax_h[q] < qmin_h[q]) {   // a plane no tap reads (cannot happen for full filters): give it an empty range
+        qmin_h[q] = qmax_h[q] = qmin_w[q] = qmax_w[q] = 0;
+      }
+      eh = qmax_h[q] - qmin_h[q] > eh ? qmax_h[q] - qmin_h[q] : eh;
+      ew = qmax_w[q] - qmin_w[q] > ew ? qmax_w[q] - qmin_w[q] : ew;
+    }
+    halo_ok = eh <= 2 && ew <= 2 && min_taps / np >= 1;
+    if (halo_ok && (halo_mode || (tune == 0 && min_taps / np >= 4))) {
+      halo_mode = 1;
+      p.tw = 8;
+      p.th = 16;
+      p.halo = 1;
+      p.np = np;
+      p.box_h = p.th + eh;
+      p.box_w = p.tw + ew;
+      for (int q = 0; q < np; ++q) {
+        p.pl_dh[q] = s * qmin_h[q] + q / s;
+        p.pl_dw[q] = s * qmin_w[q] + q % s;
+      }
+      for (int z = 0; z < n_classes; ++z)
+        for (int t = 0; t < class_ntaps[z] && t < kMaxTaps; ++t) {
+          const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
+          int qh, rh, qw, rw;
+          split(tp[0], &qh, &rh);
+          split(tp[1], &qw, &rw);
+          const int pl = rh * s + rw;
+          p.tap_pl[z][t] = (int8_t)pl;
+          p.tap_off[z][t] = (int8_t)((qh - qmin_h[pl]) * p.box_w + (qw - qmin_w[pl]));
+        }
+    } else if (halo_mode) {
+      halo_ok = false;
     }
   }
-  int halo_mode = ((tune >> 23) & 1) ? (((tune >> 27) & 1) ? 2 : 1) : 0;
-  if (tune == 0 && pair_mode && halo_ok && min_taps >= 4) halo_mode = 1;
-  if (halo_mode) {
-    if (!halo_ok || (!pair_mode && n_classes != 1))
-      return set_error(B200_EINVAL, "conv_igemm: halo mode needs stride-1 taps in [-1, 1]^2 and 64-channel K blocks");
-    p.tw = 8;
-    p.th = 16;
-    p.halo = halo_mode;
-  }
+  if (halo_mode && !halo_ok)
+    return set_error(B200_EINVAL, "conv_igemm: halo mode needs the CTA-pair kernel and tap offsets within a 3-wide range per input-parity plane");
   int max_nk = 0;
   for (int z = 0; z < n_classes; ++z) {
     if (class_ntaps[z] > kMaxTaps) return set_error(B200_EINVAL, "conv_igemm: too many taps");
@@ -1686,20 +1780,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     p.stages = st;
   }
   if (st_override >= 2) p.stages = st_override;
-  int halo_stage = 0;
-  if (p.halo && !pair_mode) {
-    p.mt = 1;
-    halo_stage = (((p.th + 2) * (p.tw + 2) * p.KC * 2 + 1023) & ~1023) + class_ntaps[0] * p.BN * p.KC * 2;
-    p.stages = (216 * 1024) / halo_stage;
-    if (p.stages > kMaxStages) p.stages = kMaxStages;
-    if (p.stages < 2) return set_error(B200_EINVAL, "conv_igemm: halo tile does not fit shared memory (BN too wide)");
-    for (int z = 0; z < n_classes; ++z) {
-      p.tiles_h[z] = (class_Ho[z] + p.th - 1) / p.th;
-      p.tiles_w[z] = (class_Wo[z] + p.tw - 1) / p.tw;
-    }
-    max_tiles = p.tiles_h[0] * p.tiles_w[0] * N;
-  }
-  if (!pair_mode && !p.halo && (p.stages < 2 || p.stages * stage_bytes > 222 * 1024))
+  if (!pair_mode && (p.stages < 2 || p.stages * stage_bytes > 222 * 1024))
     return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
   p.out = out;
   p.out_ld = out_ld;
@@ -1741,37 +1822,66 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     if (kg > 8) kg = 8;
     const int kPairDyn = 200 * 1024;   // 227 KB - 23 KB static (barriers, statistics, transpose tiles) - alignment slack
     if (p.halo) {
-      // ring A: activation boxes (3 slots), ring B: filter half-tiles of `tb` taps per slot.  tb (tune bits
-      // 24-26, 0 = automatic): as many taps as keep a slot <= 24 KB, and a divisor of every class's tap count
-      const int halo_slot = ((p.th + 2) * (p.tw + 2) * p.KC * 2 + 1023) & ~1023;
-      const int b_half = (p.BN / 2) * p.KC * 2;
+      // ring A: the K-block's activation boxes per slot (>= 2 slots); ring B: filter half-tiles of `tb` taps
+      // per slot (tune bits 24-26, 0 = automatic; a divisor of every class's tap count; >= 2 slots), or --
+      // when the pair's whole filter tile fits next to ring A -- resident for the life of the CTA
+      const int plane_slot = (p.box_h * p.box_w * p.KC * 2 + 1023) & ~1023;
+      const size_t halo_slot = (size_t)p.np * plane_slot;
+      const size_t b_half = (size_t)(p.BN / 2) * p.KC * 2;
+      const size_t dyn = kPairDyn;
+      auto fix_tb = [&](int tb) {
+        for (int z = 0; z < n_classes; ++z)
+          while (tb > 1 && class_ntaps[z] % tb) --tb;
+        return tb;
+      };
       int tb = (tune >> 24) & 7;
       if (tb == 0) tb = 3;   // (measured: one barrier round trip per 3 taps beats per-tap slots at every BN)
-      for (int z = 0; z < n_classes; ++z)
-        while (tb > 1 && class_ntaps[z] % tb) --tb;
-      p.tb = tb;
-      p.stages = st_override >= 2 ? st_override : (tb * b_half >= 48 * 1024 ? 2 : 3);
-      if (p.stages > kMaxStages) p.stages = kMaxStages;
-      int sb = (kPairDyn - p.stages * halo_slot) / (tb * b_half);
-      if (sb > kMaxStages) sb = kMaxStages;
-      if (sb < 2) return set_error(B200_EINVAL, "conv_igemm: halo rings do not fit shared memory");
-      p.sb = sb;
-      rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw + 2, p.th + 2, 1, p.KC * 2);
-      if (rc) return rc;
-      rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN / 2, p.KC * 2);
-      if (rc) return rc;
-      int m_total = 0;
-      for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
-      const int n_tiles = filt_rows / p.BN;
-      const int total_tiles = m_total * n_tiles;
-      const size_t psmem = (size_t)p.stages * halo_slot + (size_t)sb * tb * b_half + 1024;
-      int pairs = max_active_pairs(psmem);
-      if (pairs > total_tiles) pairs = total_tiles;
-      pairs = (pairs / n_tiles) * n_tiles;
-      if (pairs < n_tiles) pairs = n_tiles;
-      p.kg = 1;
-      conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
-      return check_launch("conv_igemm(pair, halo)");
+      tb = fix_tb(tb);
+      const size_t bres_bytes = (size_t)n_slabs * cin_blocks * b_half;
+      p.bres = (bres_bytes <= 72 * 1024 && bres_bytes + 2 * halo_slot <= dyn) ? 1 : 0;
+      int sa = st_override >= 2 ? st_override : 3;
+      int sb = 1;
+      size_t bring = bres_bytes;
+      bool fits;
+      if (p.bres) {
+        tb = 1;
+        while (sa > 2 && sa * halo_slot + bring > dyn) --sa;
+        fits = sa * halo_slot + bring <= dyn;
+      } else {
+        if (st_override < 2 && 3 * halo_slot + 2 * tb * b_half > dyn) sa = 2;
+        while (tb > 1 && sa * halo_slot + 2 * tb * b_half > dyn) tb = fix_tb(tb - 1);
+        fits = sa * halo_slot + 2 * tb * b_half <= dyn;
+        if (fits) {
+          sb = (int)((dyn - sa * halo_slot) / (tb * b_half));
+          if (sb > kMaxStages) sb = kMaxStages;
+          bring = (size_t)sb * tb * b_half;
+        }
+      }
+      if (sa > kMaxStages) sa = kMaxStages;
+      if (!fits) {
+        if ((tune >> 23) & 1) return set_error(B200_EINVAL, "conv_igemm: halo rings do not fit shared memory at BN = %d", p.BN);
+        p.halo = 0;   // chosen automatically: run the plain pair pipeline on the same 16 x 8 patches instead
+      } else {
+        p.tb = tb;
+        p.sb = sb;
+        p.stages = sa;
+        p.kg = 1;
+        rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.box_w, p.box_h, in_stride, p.KC * 2);
+        if (rc) return rc;
+        rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN / 2, p.KC * 2);
+        if (rc) return rc;
+        int m_total = 0;
+        for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
+        const int n_tiles = filt_rows / p.BN;
+        const int total_tiles = m_total * n_tiles;
+        const size_t psmem = sa * halo_slot + bring + 1024;
+        int pairs = max_active_pairs(psmem);
+        if (pairs > total_tiles) pairs = total_tiles;
+        pairs = (pairs / n_tiles) * n_tiles;
+        if (pairs < n_tiles) pairs = n_tiles;
+        conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles, n_slabs);
+        return check_launch("conv_igemm(pair, halo)");
+      }
     }
     while (kg > 1 && (cin_blocks % kg || 3 * kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2) > kPairDyn)) --kg;
     p.kg = kg;
@@ -1794,16 +1904,15 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     if (pairs > total_tiles) pairs = total_tiles;
     pairs = (pairs / n_tiles) * n_tiles;      // every pair keeps one filter tile
     if (pairs < n_tiles) pairs = n_tiles;
-    conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles);
+    conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles, n_slabs);
     return check_launch("conv_igemm(pair)");
   }
-  rc = p.halo ? make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw + 2, p.th + 2, 1, p.KC * 2)
-              : make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
+  rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);
   if (rc) return rc;
   rc = make_filter_map(&tmB, filt, filt_rows, n_slabs * cin_pad, p.KC, p.BN, p.KC * 2);
   if (rc) return rc;
 
-  size_t smem = (size_t)p.stages * (p.halo ? halo_stage : stage_bytes) + 1024;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024;
   const int persist = (tune >> 20) & 1;
   // bit 21: keep the CTA's filter tile resident in shared memory (persistent kernel only)
   int b_res = (tune >> 21) & 1;
@@ -1858,9 +1967,28 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
     return set_error(B200_EINVAL, "conv_wgrad: scratch needs 16-byte alignment and ci_pad = round_up(Cin, 16)");
   if (scratch != nullptr && Cin <= 32)
     return set_error(B200_EINVAL, "conv_wgrad: the tap-major scratch is for Cin > 32 (thin layers use the all-taps kernel)");
-  if (Cin <= 32 && n_taps * 32 <= 512 && n_taps >= 16 && kp_override != 3 && (int64_t)N * Ho * Wo >= 262144) {
-    // (measured: pays off for the 4x4 filters over >= 256K pixels; 3x3 layers keep the tuned generic path)
-    pick_patch(Wo, &p.th, &p.tw, 64);
+  if (Cin <= 32 && n_taps * 32 <= 512 && n_taps >= 9 && kp_override != 3 && (int64_t)N * Ho * Wo >= 65536) {
+    // every tap's accumulator resident in TMEM; the input is fetched once per pixel tile as halo boxes
+    // (four input-parity planes at stride 2) that all taps window into, instead of one shifted box per tap
+    TapPlanes tpl;
+    const bool planes = plan_planes(taps, n_taps, in_stride, &tpl);
+    if (planes) {
+      p.th = 8;
+      p.tw = 8;
+      p.np = tpl.np;
+      p.box_h = p.th + tpl.eh;
+      p.box_w = p.tw + tpl.ew;
+      for (int q = 0; q < 4; ++q) {
+        p.pl_dh[q] = tpl.pl_dh[q];
+        p.pl_dw[q] = tpl.pl_dw[q];
+      }
+      for (int t = 0; t < n_taps; ++t) {
+        p.tap_pl[t] = tpl.tap_pl[t];
+        p.tap_off[t] = (int8_t)(tpl.tap_qh[t] * p.box_w + tpl.tap_qw[t]);
+      }
+    } else {
+      pick_patch(Wo, &p.th, &p.tw, 64);
+    }
     p.Ho = Ho;
     p.Wo = Wo;
     p.tiles_h = (Ho + p.th - 1) / p.th;
@@ -1879,9 +2007,9 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
     p.co_tiles = (Cout + 127) / 128;
     p.ci_tiles = 1;
     p.BNW = 32;
-    const int stage_bytes = 2 * 64 * 128 + n_taps * 64 * 64;
+    const int stage_bytes = 2 * 64 * 128 + (p.np ? p.np * ((p.box_h * p.box_w * 64 + 1023) & ~1023) : n_taps * 64 * 64);
     p.stages = (216 * 1024) / stage_bytes;
-    if (p.stages > 4) p.stages = 4;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
     if (p.stages < 2) return set_error(B200_EINVAL, "conv_wgrad: all-taps tile does not fit shared memory");
     const int total_tiles = p.tiles_h * p.tiles_w * N;
     int splits = 148 / p.co_tiles;  // one CTA per SM; the generic path's tuned splits do not apply here
@@ -1892,7 +2020,8 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
     CUtensorMap tmDZ, tmX;
     rc = make_act_map(&tmDZ, dz, dz_coff, Cout, dz_ld, N, Ho, Wo, 64, p.tw, p.th, 1, 128);
     if (rc) return rc;
-    rc = make_act_map(&tmX, x, x_coff, Cin, x_ld, N, Hin, Win, 32, p.tw, p.th, in_stride, 64);
+    rc = p.np ? make_act_map(&tmX, x, x_coff, Cin, x_ld, N, Hin, Win, 32, p.box_w, p.box_h, in_stride, 64)
+              : make_act_map(&tmX, x, x_coff, Cin, x_ld, N, Hin, Win, 32, p.tw, p.th, in_stride, 64);
     if (rc) return rc;
     dim3 grid(splits, p.co_tiles, 1);
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;

@@ -51,9 +51,17 @@ struct ConvParams {
   int stats_sum_only;
   int wide;          // 1: output (and mask) rows are 32-byte aligned -> 256-bit stores / loads
   int kg;            // K-blocks (of KC channels) per pipeline stage (CTA-pair kernel)
-  int tb, sb;        // halo mode of the pair kernel: taps per filter-ring slot, filter-ring slots
-  int halo;          // 3x3 stride-1 input-halo reuse: ONE (th+2) x (tw+2) activation box per K-block, the taps
-                     // are shifted descriptor windows into it (1: plain start address, 2: + descriptor base_offset)
+  // Input-halo reuse (CTA-pair kernel): per K-block the activations are fetched ONCE as `np` boxes of
+  // box_h x box_w pixels (one box for a stride-1 conv; four input-parity planes, fetched with TMA element
+  // stride 2, for a stride-2 conv) and every tap is a shifted UMMA descriptor window into one of them.
+  int halo;          // 0 off, 1 on
+  int np;            // boxes (planes) per K-block: 1 or 4
+  int box_h, box_w;  // pixels per box (th + extent, tw + extent)
+  int pl_dh[4], pl_dw[4];                 // input pixel of a box's first element, relative to (h0, w0) * in_stride
+  int8_t tap_pl[kMaxClasses][kMaxTaps];   // plane of a tap
+  int8_t tap_off[kMaxClasses][kMaxTaps];  // first row of the tap's window inside its box (oh * box_w + ow)
+  int tb, sb;        // taps per filter-ring slot, filter-ring slots
+  int bres;          // 1: the pair's whole filter tile (all slabs, all K-blocks) stays resident in shared memory
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]
@@ -78,6 +86,20 @@ struct WgradParams {
   // 3x3 / 4x4 layers cost 0.8 ms of a 15.3 ms step); b200_wgrad_unscratch permutes it into dw.
   float* scratch;
   int ci_pad;
+  // all-taps kernel with input-halo reuse (see ConvParams::halo): np > 0 -> the input is fetched as np
+  // boxes of box_h x box_w pixels per pixel tile and tap t is a shifted window into box tap_pl[t]
+  int np, box_h, box_w;
+  int pl_dh[4], pl_dw[4];
+  int8_t tap_pl[kMaxTaps];
+  int8_t tap_off[kMaxTaps];
+};
+
+// Decomposition of a tap list into input-parity planes and per-tap window offsets (igemm.cu).
+struct TapPlanes {
+  int np, eh, ew;
+  int pl_dh[4], pl_dw[4];
+  int8_t tap_pl[kMaxTaps];
+  int8_t tap_qh[kMaxTaps], tap_qw[kMaxTaps];   // window offset inside the plane, in pixels
 };
 
 }  // namespace b200

@@ -205,6 +205,8 @@ PAIR_CASES = [
     (4, 128, 256, 32, 64, 4, 2, 1, False),       # discriminator conv3 shape
     (2, 64, 64, 16, 32, 3, 1, 1, True),
     (2, 64, 128, 33, 65, 4, 2, 1, True),         # four output-parity classes with different tap lists
+    (2, 32, 64, 37, 61, 4, 2, 1, False),         # odd map, KC = 32: parity planes with 64-byte rows
+    (1, 64, 32, 40, 24, 3, 2, 1, True),          # 3x3 stride-2 data gradient: classes of 1 / 2 / 2 / 4 taps
     (8, 128, 64, 64, 128, 4, 2, 1, True),        # discriminator conv2 data gradient (N = 8)
 ]
 
@@ -240,15 +242,21 @@ def test_conv_pair_kernel(cuda_lib, case, bn):
     ref = F.leaky_relu(ref + bias[:rows], 0.2)
     outs, sts = [], []
     words = [bn | (1 << 22), bn | (1 << 22) | (3 << 16), 0]
-    k_ch = cout if dgrad else cin
-    if k_ch % 64 == 0 and ((r == 3 and stride == 1) or (dgrad and r in (3, 4))):
-        # input-halo reuse (bit 23): shifted descriptor windows into one (th+2) x (tw+2) box per K-block;
-        # bits 24-26 = taps per filter-ring slot
+    if (r == 3 and stride == 1) or (dgrad and r in (3, 4)) or (r == 4 and stride == 2):
+        # input-halo reuse (bit 23): every tap is a shifted descriptor window into one box per K-block (four
+        # input-parity planes for the stride-2 forward convs); bits 24-26 = taps per filter-ring slot
         words = [bn | (3 << 22), bn | (3 << 22) | (1 << 24), bn | (3 << 22) | (2 << 16)] + words
     for word in words:
         out = torch.full((n, geom["Hout"], geom["Wout"], filt.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
         stats = torch.zeros(2, filt.shape[0], device="cuda")
-        K.conv_igemm(inp, filt, out, geom, bias=bias, act=2, slope=0.2, stats=stats, bn_tile=word)
+        try:
+            K.conv_igemm(inp, filt, out, geom, bias=bias, act=2, slope=0.2, stats=stats, bn_tile=word)
+        except K._lib.B200Error as ex:
+            # an explicitly requested halo configuration may not fit shared memory (four parity planes of
+            # 64 channels next to a 256-wide filter ring): the launcher says so instead of launching
+            assert (word >> 23) & 1 and "do not fit" in str(ex), ex
+            outs.append(None)
+            continue
         torch.cuda.synchronize()
         err = rel_l2(out[..., :rows], ref)
         assert err < 4e-3, (word, err)
@@ -258,26 +266,7 @@ def test_conv_pair_kernel(cuda_lib, case, bn):
         outs.append(out)
     # same K order (taps outer, channel blocks inner) -> bit-identical across tile shapes / kernels; the
     # halo mode walks channel blocks outer, taps inner: same tolerance, different fp32 rounding
+    assert any(o is not None for o in outs)
     plain = [o for o, wd in zip(outs, words) if not (wd >> 23) & 1 and wd != 0]
     for o in plain[1:]:
         assert torch.equal(o, plain[0])
-
-
-@pytest.mark.parametrize("variant", [1, 2])
-@pytest.mark.parametrize("case", [(2, 64, 64, 32, 32, 3, 1, 1), (2, 128, 64, 19, 37, 3, 1, 1), (1, 256, 32, 48, 24, 3, 1, 1)])
-def test_conv_halo_window(cuda_lib, case, variant):
-    """Input-halo reuse (tune bit 23): one (th+2) x (tw+2) activation box per K-block, the nine taps are
-    shifted UMMA descriptor windows into it (variant 2 additionally sets the descriptor's base_offset)."""
-    from dasemanticsegmentationaml_b200 import kernels as K
-    n, cin, cout, h, w, r, stride, pad = case
-    x, wgt = make_case(*case)
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wgt, stride=stride, padding=pad).permute(0, 2, 3, 1)
-    filt = K.pack_filter(wgt)
-    geom = K.fwd_geometry(h, w, r, r, stride, pad)
-    out = torch.full((n, geom["Hout"], geom["Wout"], filt.shape[0]), 7.0, device="cuda", dtype=torch.bfloat16)
-    word = min(64, cout) | (1 << 23) | ((1 << 27) if variant == 2 else 0)
-    K.conv_igemm(x, filt, out, geom, bn_tile=word)
-    torch.cuda.synchronize()
-    err = rel_l2(out[..., :cout], ref)
-    print("halo variant", variant, case, "rel-L2", err)
-    assert err < 4e-3, err
