@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--profile-ahead-ms", type=float, default=60.0,
+                    help="park the stream behind a spin kernel of this length before the profiled eager step, so the "
+                         "per-launch CUDA events bracket device time, not the host's launch latency (0 = off)")
     ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--profile-json", default=None, help="write the per-kernel time table here")
@@ -492,7 +495,7 @@ def run_b200(args):
     prof = None
     if not args.no_profile:
         sync_all(world)
-        _lib.profile_start()
+        _lib.profile_start(host_ahead_ms=args.profile_ahead_ms)
         b.eager_step(b.devbuf)
         prof = _lib.profile_stop()
         detail = _lib.last_profile_detail
@@ -548,7 +551,7 @@ def run_b200(args):
                        "warmup": 3, "height": eb.h, "width": eb.w, "launch_mode": eb.graph_note, "result_last_step": lv}
                 if wl.startswith("da_dwsep"):
                     # BASELINE config 4 is judged by HBM GB/s: the depthwise / BatchNorm kernels of this step
-                    _lib.profile_start()
+                    _lib.profile_start(host_ahead_ms=args.profile_ahead_ms)
                     eb.eager_step(eb.devbuf)
                     pe = _lib.profile_stop()
                     ent["roofline_mem"] = mem_table(pe, peaks, only=("b200_dwconv", "b200_bn_", "b200_upsample", "b200_act_bwd"))

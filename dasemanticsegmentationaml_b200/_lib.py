@@ -90,8 +90,15 @@ def call(name, *args, flops=0.0, nbytes=0.0, tag=None):
     launch_count += _MULTI.get(name, 1)
 
 
-def profile_start():
+def profile_start(host_ahead_ms=0.0):
+    """Start bracketing every entry-point call with CUDA events.  An eager step is HOST bound (Python +
+    ctypes + tensor-map encoding per launch), so a start event recorded on an idle GPU would charge the
+    host's launch latency to the kernel; host_ahead_ms > 0 first parks the stream behind a spin kernel of
+    about that length so that the events and launches queue up and the events bracket device time only."""
     global _profile
+    if host_ahead_ms > 0:
+        import torch
+        torch.cuda._sleep(int(host_ahead_ms * 1e-3 * 1.9e9))
     _profile = []
 
 

@@ -1684,7 +1684,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
       ew = qmax_w[q] - qmin_w[q] > ew ? qmax_w[q] - qmin_w[q] : ew;
     }
     halo_ok = eh <= 2 && ew <= 2 && min_taps / np >= 1;
-    if (halo_ok && (halo_mode || (tune == 0 && min_taps / np >= 4))) {
+    // (automatic only for the one-box stride-1 case: the four parity planes of a stride-2 conv cost 80 KB per
+    //  K-block at 64 channels and measured slower than per-tap boxes on the discriminator's layers)
+    if (halo_ok && (halo_mode || (tune == 0 && np == 1 && min_taps >= 4))) {
       halo_mode = 1;
       p.tw = 8;
       p.th = 16;
@@ -1967,11 +1969,14 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
     return set_error(B200_EINVAL, "conv_wgrad: scratch needs 16-byte alignment and ci_pad = round_up(Cin, 16)");
   if (scratch != nullptr && Cin <= 32)
     return set_error(B200_EINVAL, "conv_wgrad: the tap-major scratch is for Cin > 32 (thin layers use the all-taps kernel)");
-  if (Cin <= 32 && n_taps * 32 <= 512 && n_taps >= 9 && kp_override != 3 && (int64_t)N * Ho * Wo >= 65536) {
-    // every tap's accumulator resident in TMEM; the input is fetched once per pixel tile as halo boxes
-    // (four input-parity planes at stride 2) that all taps window into, instead of one shifted box per tap
+  if (Cin <= 32 && n_taps * 32 <= 512 && n_taps >= 16 && kp_override != 3 && (int64_t)N * Ho * Wo >= 262144) {
+    // every tap's accumulator resident in TMEM (measured: pays off for the 4x4 filters over >= 256K pixels;
+    // 3x3 layers keep the tuned generic path).  The input tile is one shifted box per tap; with the tune
+    // field kpix == 1 it is fetched once as halo boxes (four input-parity planes at stride 2) that all taps
+    // window into -- a third of the L2 traffic, but measured SLOWER on the 19 -> 64 4x4 layer (0.71 vs
+    // 0.60 ms per step: 8 x 8 pixel tiles instead of 64-pixel rows), so it stays opt-in.
     TapPlanes tpl;
-    const bool planes = plan_planes(taps, n_taps, in_stride, &tpl);
+    const bool planes = kp_override == 1 && plan_planes(taps, n_taps, in_stride, &tpl);
     if (planes) {
       p.th = 8;
       p.tw = 8;

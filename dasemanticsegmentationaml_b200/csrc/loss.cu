@@ -3,6 +3,9 @@
 // is only materialised when the caller asks for it.
 //   reference: F.interpolate(..., mode='bilinear', align_corners=True)  model/model_stages.py:240-242
 //              CrossEntropyLoss(ignore_index=255)                       train.py:66,86-89,135,214-217
+//              (a label outside [0, classes) that is not ignore_index is EXCLUDED from the loss, its
+//               gradient and the pixel count -- torch raises a device-side assert for such a label; the
+//               Python wrapper can check for it first, losses.VALIDATE_LABELS)
 //              F.softmax(output, dim=1) feeding the discriminator       train.py:230,248,257
 //              reverse_one_hot (argmax over classes)                    utils.py:98-122
 //              OHEM_CrossEntroy_Loss                                    utils.py:256-271
@@ -160,7 +163,7 @@ upsample_fwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
     } else if (mode == 1) {
       const int64_t lab = labels[p];
       float l = 0.f;
-      if (lab != ignore_index) {
+      if (lab != ignore_index && (unsigned long long)lab < (unsigned long long)NC) {
         float tgt = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) tgt = (c == lab) ? v[c] : tgt;
@@ -268,7 +271,7 @@ upsample_fwd_tiled_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_
     } else if (mode == 1) {
       const int64_t lab = labels[p];
       float l = 0.f;
-      if (lab != ignore_index) {
+      if (lab != ignore_index && (unsigned long long)lab < (unsigned long long)NC) {
         float tgt = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) tgt = (c == lab) ? v[c] : tgt;
@@ -392,7 +395,7 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
       softmax_inplace<NC>(v, &lse);
       if (mode == 1) {
         const int64_t lab = lab_ce;
-        if (lab != ignore_index) {
+        if (lab != ignore_index && (unsigned long long)lab < (unsigned long long)NC) {
           my_loss = fmaxf(lse - tgt, 0.f);
           my_valid = 1.f;
           float cf = coef_scale * (coef_num != nullptr ? *coef_num : 1.f);
@@ -572,7 +575,7 @@ upsample_bwd_strip_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_
         sample_smem<NC>(s_lr, ih, iw, i_min, j_min, g);
         if (mode == 1) {
           const int64_t lab = labels[p];
-          if (lab != ignore_index) {
+          if (lab != ignore_index && (unsigned long long)lab < (unsigned long long)NC) {
             float tgt = 0.f;
 #pragma unroll
             for (int c = 0; c < NC; ++c) tgt = (c == lab) ? g[c] : tgt;

@@ -74,18 +74,32 @@ class _UpsampleCE(torch.autograd.Function):
         return d_lr, None, None, None, None, None
 
 
-def _check_labels(labels, n, H, W):
+# torch.nn.CrossEntropyLoss raises (device-side assert) on a label outside [0, classes) other than
+# ignore_index -- an un-remapped GTA5 id, a wrong label file.  The fused kernels EXCLUDE such pixels from
+# the loss, the gradient and the pixel count instead of training on them; set VALIDATE_LABELS = True to
+# get the reference's behaviour (an IndexError) at the price of one extra pass + host sync per call.
+VALIDATE_LABELS = False
+
+
+def _check_labels(labels, n, H, W, n_classes=None, ignore_index=None):
     if labels.dim() == 4 and labels.shape[1] == 1:
         labels = labels[:, 0]
     assert labels.shape == (n, H, W), "labels must be [N, H, W] (or [N, 1, H, W])"
     if labels.dtype != torch.int64:
         labels = labels.long()
-    return labels.contiguous()
+    labels = labels.contiguous()
+    if VALIDATE_LABELS and n_classes is not None:
+        bad = (labels < 0) | (labels >= n_classes)
+        if ignore_index is not None:
+            bad &= labels != ignore_index
+        if bool(bad.any()):
+            raise IndexError("Target %d is out of bounds." % int(labels[bad][0]))
+    return labels
 
 
 def upsample_cross_entropy(lr, labels, n_classes=19, ignore_index=255):
     """mean over non-ignored pixels of -log softmax(upsample(lr))[label]."""
-    labels = _check_labels(labels, lr.shape[0], labels.shape[-2], labels.shape[-1])
+    labels = _check_labels(labels, lr.shape[0], labels.shape[-2], labels.shape[-1], n_classes, ignore_index)
     H, W = labels.shape[1:]
     return _UpsampleCE.apply(lr, labels, H, W, n_classes, ignore_index)
 
@@ -174,8 +188,9 @@ class _UpsampleOhemCE(torch.autograd.Function):
 
 def upsample_ohem_cross_entropy(lr, labels, threshold, keep_num, n_classes=19):
     """OHEM_CrossEntroy_Loss(threshold, keep_num)(upsample(lr), labels) with a radix-select k-th
-    largest instead of torch.sort.  Labels must lie in [0, n_classes) (the reference raises otherwise)."""
-    labels = _check_labels(labels, lr.shape[0], labels.shape[-2], labels.shape[-1])
+    largest instead of torch.sort.  Labels must lie in [0, n_classes): the reference raises otherwise; here such
+    pixels contribute a zero loss (see VALIDATE_LABELS)."""
+    labels = _check_labels(labels, lr.shape[0], labels.shape[-2], labels.shape[-1], n_classes, None)
     H, W = labels.shape[1:]
     if not (0 <= keep_num < labels.numel()):
         raise IndexError("keep_num %d out of range for %d pixels" % (keep_num, labels.numel()))

@@ -219,6 +219,27 @@ def test_fused_losses_against_torch(cuda_lib, shape):
     (l1 * 3.0).backward()
     (l2 * 3.0).backward()
     assert rel_l2(a.grad, b.grad) < 1e-3
+    # labels outside [0, 19) other than 255 (an un-remapped id): excluded from loss, gradient and pixel count
+    # (torch raises a device assert for them); with VALIDATE_LABELS the wrapper raises like the reference
+    bad_labels = labels.clone()
+    bad_labels[:, ::7, ::5] = 77
+    bad_labels[0, 3, 3] = -4
+    a = lr.clone().requires_grad_(True)
+    b = lr.clone().requires_grad_(True)
+    l1 = L.upsample_cross_entropy(a, bad_labels)
+    masked = torch.where((bad_labels < 0) | (bad_labels >= 19), torch.full_like(bad_labels, 255), bad_labels)
+    l2 = F.cross_entropy(full(b), masked, ignore_index=255)
+    assert abs(l1.item() - l2.item()) < 1e-4 * abs(l2.item())
+    l1.backward()
+    l2.backward()
+    assert rel_l2(a.grad, b.grad) < 1e-3
+    L.VALIDATE_LABELS = True
+    try:
+        with pytest.raises(IndexError):
+            L.upsample_cross_entropy(lr, bad_labels)
+        L.upsample_cross_entropy(lr, labels)
+    finally:
+        L.VALIDATE_LABELS = False
     # softmax for the discriminator
     a = lr.clone().requires_grad_(True)
     b = lr.clone().requires_grad_(True)
