@@ -180,7 +180,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     // (lean on purpose, like the MMA loop below: no divisions, barrier addresses by increment)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       const int hb = h0 * p.in_stride, wb = w0 * p.in_stride;
       int s = 0;
@@ -208,7 +208,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // The tensor pipe queues only about one instruction ahead of the issuing thread, so scalar work
     // between two tcgen05.mma is idle tensor time: descriptors come from a precomputed template,
     // stage / phase advance by increment, the next stage's barrier is polled while MMAs execute.
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
       const uint32_t sbo = 8u * p.KC * 2u;              // 8 rows of KC bf16
       const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
@@ -398,7 +398,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       int s = 0;
       uint32_t ph = 0;
@@ -432,7 +432,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer (lean: see conv_igemm_kernel)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
       const uint32_t sbo = 8u * p.KC * 2u;
       const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
@@ -681,6 +681,15 @@ struct PairBarriers {
   uint32_t tmem_base;
 };
 
+constexpr int kDbgTiles = 30;       // tiles of pair 0 a debug timeline records (buffer: 8 + 4 * kDbgTiles int64)
+__device__ __forceinline__ void dbg_mark(const ConvParams& p, int slot) {
+  if (p.dbg != nullptr && blockIdx.x < 2) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[slot] = t;
+  }
+}
+
 constexpr int kPairThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 template <bool F32, bool STATS>
@@ -716,6 +725,7 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
     const uint32_t acc = tmem + buf * acc_cols + ((uint32_t)(q * 32) << 16);
     mbar_wait_warp(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1, lane);
     tc_fence_after();
+    if (warp == 2 && lane == 0 && rank == 0 && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 2);
     const int h = tc.h0 + rank * p.th + hl, w = tc.w0 + wl;
     const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
     const size_t pix =
@@ -727,6 +737,7 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_leader(smem_u32(&bars.tempty[buf]));
+    if (warp == 2 && lane == 0 && rank == 0 && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 3);
   }
   if (STATS && cur_n0 >= 0) {
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -748,6 +759,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int rank = (int)cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  if (threadIdx.x == 0 && blockIdx.x == 0) dbg_mark(p, 0);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = 128u * p.KC * 2u;
   const uint32_t b_half = (uint32_t)(p.BN / 2) * p.KC * 2u;
@@ -793,13 +805,14 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
+  if (threadIdx.x == 0 && blockIdx.x == 0) dbg_mark(p, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer (both CTAs)
     // One elected thread.  The loop is kept lean on purpose (no divisions, barrier addresses by
     // increment): a single thread runs at ~0.2 IPC, and every cycle it spends between two stages is
     // a cycle the loads start later.
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       const uint32_t tx = 2u * stage_bytes;
       const int bn_half = p.BN / 2;
@@ -851,22 +864,33 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const TileCoord tc = decode_tile(p, my_n, m);
         const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
         const int brow = tc.n0 + rank * bn_half;
-        const int ntap = p.n_taps[tc.z];
-        for (int t = 0; t < ntap; ++t) {
-          const int hh = h0 + p.tap_dh[tc.z][t];
-          const int ww = w0 + p.tap_dw[tc.z][t];
-          const int kb = p.tap_k[tc.z][t] * p.cin_pad;
-          for (int cb = 0; cb < cin_blocks; cb += p.kg) {
-            mbar_wait(empty0 + 8u * s, ph ^ 1u);
-            const uint32_t full = full0 + 8u * s;
-            if (leader) mbar_expect_tx(full, tx);
-            uint32_t sa = smem_base + s * stage_bytes;
-            for (int j = 0; j < p.kg; ++j, sa += a_bytes) tma_load_4d_pair(sa, &tmA, full, (cb + j) * p.KC, ww, hh, tc.n_img);
-            for (int j = 0; j < p.kg; ++j, sa += b_half) tma_load_2d_pair(sa, &tmB, full, kb + (cb + j) * p.KC, brow);
-            if (++s == p.stages) {
-              s = 0;
-              ph ^= 1u;
+        // the tile's K-blocks in (tap, channel block) order, kg of them per stage -- a stage may span taps
+        // (64-channel layers have ONE block per tap; the launcher picks kg dividing taps x blocks)
+        const int nblk = p.n_taps[tc.z] * cin_blocks;
+        int t = 0, cb = 0;
+        for (int q = 0; q < nblk; q += p.kg) {
+          mbar_wait(empty0 + 8u * s, ph ^ 1u);
+          const uint32_t full = full0 + 8u * s;
+          if (leader) mbar_expect_tx(full, tx);
+          uint32_t sa = smem_base + s * stage_bytes;
+          int t2 = t, cb2 = cb;
+          for (int j = 0; j < p.kg; ++j, sa += a_bytes) {
+            tma_load_4d_pair(sa, &tmA, full, cb * p.KC, w0 + p.tap_dw[tc.z][t], h0 + p.tap_dh[tc.z][t], tc.n_img);
+            if (++cb == cin_blocks) {
+              cb = 0;
+              ++t;
             }
+          }
+          for (int j = 0; j < p.kg; ++j, sa += b_half) {
+            tma_load_2d_pair(sa, &tmB, full, p.tap_k[tc.z][t2] * p.cin_pad + cb2 * p.KC, brow);
+            if (++cb2 == cin_blocks) {
+              cb2 = 0;
+              ++t2;
+            }
+          }
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
       }
@@ -878,14 +902,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // work between two tcgen05.mma is idle tensor time unless it fits under one MMA: descriptors are
     // built by adding to a precomputed template, stage / phase advance by increment, the K steps are
     // unrolled, and the next stage's barrier is polled right after this stage's MMAs were queued.
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       const uint32_t idesc = make_idesc_bf16(256, p.BN, 0, 0);
       const uint32_t sbo = 8u * p.KC * 2u;
       const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
       const uint32_t d_hi = (uint32_t)(dtmpl >> 32), d_lo = (uint32_t)dtmpl;
       const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       const uint32_t b_off = (uint32_t)p.kg * a_bytes;
-      const int groups = cin_blocks / p.kg;
       int s = 0, lt = 0;
       uint32_t ph = 0;
       bool ready = false;
@@ -910,8 +933,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc_fence_after();
           const int ntap = p.n_taps[tc.z];
           uint32_t accum = 0;
+          if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
           for (int cb = 0; cb < cin_blocks; ++cb) {
             mbar_wait(full0 + 8u * s, ph);
+            if (lt == 0 && cb == 0) dbg_mark(p, 2);
             const uint32_t abox = smem_base + s * halo_bytes;
             for (int t0 = 0; t0 < ntap; t0 += p.tb) {
               uint32_t b_lo;
@@ -947,6 +972,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
           umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
+          if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
         }
       } else
       for (int m = m_first; m < m_total; m += m_step, ++lt) {
@@ -955,10 +981,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // both epilogues drained it
         tc_fence_after();
-        const int nk = p.n_taps[tc.z] * groups;
+        const int nk = p.n_taps[tc.z] * cin_blocks / p.kg;
         uint32_t accum = 0;
+        if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
         for (int kit = 0; kit < nk; ++kit) {
           if (!ready) mbar_wait(full0 + 8u * s, ph);
+          if (lt == 0 && kit == 0) dbg_mark(p, 2);
           tc_fence_after();
           uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
           uint32_t b_lo = a_lo + (b_off >> 4);
@@ -987,6 +1015,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           ready = mbar_try_wait(full0 + 8u * s, ph);   // poll the next stage while the MMAs above execute
         }
         umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
+        if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
       }
     }
   } else {
@@ -1010,6 +1039,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tc_fence_after();
     tmem_dealloc_pair(tmem, tmem_cols);
   }
+  if (threadIdx.x == 0 && blockIdx.x == 0) dbg_mark(p, 3);
 }
 
 // ------------------------------------------------------------------------ wgrad
@@ -1067,7 +1097,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
   const uint32_t tmem = bars.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
       const uint32_t full0 = smem_u32(&bars.full[0]), empty0 = smem_u32(&bars.empty[0]);
       // tile coordinates advance by increment (no divisions in the loop)
@@ -1101,7 +1131,7 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // (lean issue loop: see conv_igemm_kernel)
       const uint32_t idesc = make_idesc_bf16(128, p.BNW, 1, 1);
       // MN-major, 128B swizzle: 64 channels contiguous, 8-pixel groups 1024 B apart (SBO),
@@ -1270,7 +1300,7 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
   const uint32_t tmem = bars.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < nk; ++it) {
         const int tile = tile_begin + it;
         const int n_img = tile / tiles_per_img;
@@ -1297,7 +1327,7 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, 32, 1, 1);
       for (int it = 0; it < nk; ++it) {
         const int s = it % p.stages;
@@ -1359,6 +1389,24 @@ wgrad_alltaps_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_cons
 // --------------------------------------------------------- filter repacking
 // PyTorch [Cout][Cin][RS] fp32  ->  bf16 [rows_pad][RS][inner_pad] (zero padded), with
 // (rows, inner) = (Cout, Cin) for forward or (Cin, Cout) for the data gradient.
+//
+// Pair view (transpose bit 1; RS = 8, 64 "input channels"): a 4x4 / stride-2 / pad-1 filter over a map stored
+// zero-bordered, [H+2][W+2][32], is a filter of 4 x 2 taps over COLUMN PAIRS of that map (pair channel
+// ci2 = s*32 + c, c < Cin <= 32): tap t = kh*2 + b covers kernel column kw = 2b + s, so
+//   packed[co][t][s*32 + c] = w[co][c][kh][2b + s]  =  w[co*Cin*16 + c*16 + 2t + s].
+__device__ __forceinline__ size_t pair_view_source(int co, int ci2, int t, int Cin) {
+  return ((size_t)co * Cin + (ci2 & 31)) * 16 + 2 * t + (ci2 >> 5);
+}
+
+// scratch[t][co][ci2] (fp32, tap-major accumulators of the pair-view weight gradient) -> dw[co][c][kh][kw]
+__global__ void wgrad_unscratch_pairview_kernel(const float* __restrict__ sc, float* __restrict__ dw, int Cout, int Cin) {
+  const int total = Cout * Cin * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 15, c = (i >> 4) % Cin, co = i / (16 * Cin);
+    const int kh = k >> 2, kw = k & 3, b = kw >> 1, s = kw & 1;
+    dw[i] = sc[((size_t)(kh * 2 + b) * Cout + co) * 64 + s * 32 + c];
+  }
+}
 __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                    int Cout, int Cin, int RS, int rows_pad, int inner_pad,
                                    int transpose) {
@@ -1368,10 +1416,15 @@ __global__ void pack_filter_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int inner = i % inner_pad;
     const int t = (i / inner_pad) % RS;
     const int row = i / ((size_t)inner_pad * RS);
-    const int co = transpose ? inner : row;
-    const int ci = transpose ? row : inner;
+    const int co = (transpose & 1) ? inner : row;
+    const int ci = (transpose & 1) ? row : inner;
     float v = 0.f;
-    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * RS + t];
+    if (transpose & 2) {
+      const size_t src = pair_view_source(co, ci, t, Cin);
+      if (co < Cout && ci < 64 && (ci & 31) < Cin) v = w[src];
+    } else if (co < Cout && ci < Cin) {
+      v = w[((size_t)co * Cin + ci) * RS + t];
+    }
     out[i] = __float2bfloat16(v);
   }
 }
@@ -1388,11 +1441,17 @@ __global__ void pack_filters_batched_kernel(const long long* __restrict__ table)
   const int pairs = rows_pad * inner_pad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += gridDim.x * blockDim.x) {
     const int row = i / inner_pad, inner = i - row * inner_pad;
-    const int co = transpose ? inner : row;
-    const int ci = transpose ? row : inner;
+    const int co = (transpose & 1) ? inner : row;
+    const int ci = (transpose & 1) ? row : inner;
+    __nv_bfloat16* dst = out + (size_t)row * RS * inner_pad + inner;
+    if (transpose & 2) {
+      const bool ok = co < Cout && ci < 64 && (ci & 31) < Cin;
+      for (int tt = 0; tt < RS; ++tt)
+        dst[(size_t)tt * inner_pad] = __float2bfloat16(ok ? __ldg(w + pair_view_source(co, ci, tt, Cin)) : 0.f);
+      continue;
+    }
     const bool ok = co < Cout && ci < Cin;
     const float* src = w + ((size_t)co * Cin + ci) * RS;
-    __nv_bfloat16* dst = out + (size_t)row * RS * inner_pad + inner;
     for (int tt = 0; tt < RS; ++tt) dst[(size_t)tt * inner_pad] = __float2bfloat16(ok ? __ldg(src + tt) : 0.f);
   }
 }
@@ -1606,6 +1665,18 @@ int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStrea
   return check_launch("pack_filters_batched");
 }
 
+static long long* g_debug_timeline = nullptr;
+int b200_debug_timeline(int64_t* buf) {
+  g_debug_timeline = reinterpret_cast<long long*>(buf);
+  return B200_OK;
+}
+
+int b200_wgrad_unscratch_pairview(const float* scratch, float* dw, int Cout, int Cin, cudaStream_t stream) {
+  if (Cin > 32 || Cout < 1) return set_error(B200_EINVAL, "wgrad_unscratch_pairview: needs Cin <= 32");
+  wgrad_unscratch_pairview_kernel<<<(Cout * Cin * 16 + 255) / 256, 256, 0, stream>>>(scratch, dw, Cout, Cin);
+  return check_launch("wgrad_unscratch_pairview");
+}
+
 // Generic implicit-GEMM launch.  `taps` is [n_classes][n_taps_max][3] = (dh, dw, k-slab).
 int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int Hin, int Win,
                     const void* filt, int filt_rows, int cin_pad, int n_slabs,
@@ -1651,24 +1722,54 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   bool halo_ok = pair_mode && (in_stride == 1 || in_stride == 2);
   int min_taps = kMaxTaps;
   if (halo_ok) {
-    const int s = in_stride, np = s * s;
+    const int s = in_stride;
+    // Planes.  Stride 2: the s*s input parities (d = s*q + r, floor division; plane = (rh, rw), window
+    // offset = (qh, qw)).  Stride 1: taps are grouped by their dw -- a tap joins the group whose smallest
+    // dw is within 2 of its own -- so an ordinary 3x3 window is ONE plane and the pair view of the
+    // zero-bordered probability map (taps at dw = b and dw = (W+2)/2 + b, kernels.pairview_fwd_geometry)
+    // is TWO, one per bordered row of a view row.
+    int cl_min[4], n_cl = 0;
+    if (s == 1) {
+      int dws[kMaxClasses * kMaxTaps], nd = 0;
+      for (int z = 0; z < n_classes; ++z)
+        for (int t = 0; t < class_ntaps[z] && t < kMaxTaps; ++t) dws[nd++] = taps[((size_t)z * taps_stride + t) * 3 + 1];
+      for (int i = 1; i < nd; ++i)   // insertion sort (<= 64 values)
+        for (int j = i; j > 0 && dws[j - 1] > dws[j]; --j) {
+          const int tmp = dws[j];
+          dws[j] = dws[j - 1];
+          dws[j - 1] = tmp;
+        }
+      for (int i = 0; i < nd && halo_ok; ++i)
+        if (n_cl == 0 || dws[i] - cl_min[n_cl - 1] > 2) {
+          if (n_cl == 4) halo_ok = false;
+          else cl_min[n_cl++] = dws[i];
+        }
+    }
+    const int np = s == 1 ? n_cl : s * s;
+    auto classify = [&](const int* tp, int* pl, int* qh, int* qw) {
+      if (s == 1) {
+        int c = 0;
+        while (c + 1 < n_cl && tp[1] >= cl_min[c + 1]) ++c;
+        *pl = c;
+        *qh = tp[0];
+        *qw = tp[1];
+      } else {
+        const int rh = ((tp[0] % s) + s) % s, rw = ((tp[1] % s) + s) % s;
+        *pl = rh * s + rw;
+        *qh = (tp[0] - rh) / s;
+        *qw = (tp[1] - rw) / s;
+      }
+    };
     int qmin_h[4], qmax_h[4], qmin_w[4], qmax_w[4];
     for (int q = 0; q < 4; ++q) {
       qmin_h[q] = qmin_w[q] = 1 << 20;
       qmax_h[q] = qmax_w[q] = -(1 << 20);
     }
-    auto split = [s](int d, int* q, int* r) {   // d = s * q + r, 0 <= r < s (floor division)
-      *r = ((d % s) + s) % s;
-      *q = (d - *r) / s;
-    };
-    for (int z = 0; z < n_classes; ++z) {
+    for (int z = 0; z < n_classes && halo_ok; ++z) {
       min_taps = class_ntaps[z] < min_taps ? class_ntaps[z] : min_taps;
       for (int t = 0; t < class_ntaps[z] && t < kMaxTaps; ++t) {
-        const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
-        int qh, rh, qw, rw;
-        split(tp[0], &qh, &rh);
-        split(tp[1], &qw, &rw);
-        const int pl = rh * s + rw;
+        int pl, qh, qw;
+        classify(taps + ((size_t)z * taps_stride + t) * 3, &pl, &qh, &qw);
         qmin_h[pl] = qh < qmin_h[pl] ? qh : qmin_h[pl];
         qmax_h[pl] = qh > qmax_h[pl] ? qh : qmax_h[pl];
         qmin_w[pl] = qw < qmin_w[pl] ? qw : qmin_w[pl];
@@ -1676,17 +1777,18 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
       }
     }
     int eh = 0, ew = 0;
-    for (int q = 0; q < np; ++q) {
+    for (int q = 0; q < np && halo_ok; ++q) {
       if (qmax_h[q] < qmin_h[q]) {   // a plane no tap reads (cannot happen for full filters): give it an empty range
         qmin_h[q] = qmax_h[q] = qmin_w[q] = qmax_w[q] = 0;
       }
       eh = qmax_h[q] - qmin_h[q] > eh ? qmax_h[q] - qmin_h[q] : eh;
       ew = qmax_w[q] - qmin_w[q] > ew ? qmax_w[q] - qmin_w[q] : ew;
     }
-    halo_ok = eh <= 2 && ew <= 2 && min_taps / np >= 1;
-    // (automatic only for the one-box stride-1 case: the four parity planes of a stride-2 conv cost 80 KB per
-    //  K-block at 64 channels and measured slower than per-tap boxes on the discriminator's layers)
-    if (halo_ok && (halo_mode || (tune == 0 && np == 1 && min_taps >= 4))) {
+    halo_ok = halo_ok && np >= 1 && eh <= 2 && ew <= 2 && min_taps / np >= 1;
+    // (automatic only at stride 1 -- one box, or two boxes serving >= 4 taps each: the four parity planes
+    //  of a stride-2 conv cost 80 KB per K-block at 64 channels and measured slower than per-tap boxes on
+    //  the discriminator's layers)
+    if (halo_ok && (halo_mode || (tune == 0 && s == 1 && np <= 2 && min_taps >= 4 * np))) {
       halo_mode = 1;
       p.tw = 8;
       p.th = 16;
@@ -1695,16 +1797,13 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
       p.box_h = p.th + eh;
       p.box_w = p.tw + ew;
       for (int q = 0; q < np; ++q) {
-        p.pl_dh[q] = s * qmin_h[q] + q / s;
-        p.pl_dw[q] = s * qmin_w[q] + q % s;
+        p.pl_dh[q] = s == 1 ? qmin_h[q] : s * qmin_h[q] + q / s;
+        p.pl_dw[q] = s == 1 ? qmin_w[q] : s * qmin_w[q] + q % s;
       }
       for (int z = 0; z < n_classes; ++z)
         for (int t = 0; t < class_ntaps[z] && t < kMaxTaps; ++t) {
-          const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
-          int qh, rh, qw, rw;
-          split(tp[0], &qh, &rh);
-          split(tp[1], &qw, &rw);
-          const int pl = rh * s + rw;
+          int pl, qh, qw;
+          classify(taps + ((size_t)z * taps_stride + t) * 3, &pl, &qh, &qw);
           p.tap_pl[z][t] = (int8_t)pl;
           p.tap_off[z][t] = (int8_t)((qh - qmin_h[pl]) * p.box_w + (qw - qmin_w[pl]));
         }
@@ -1760,7 +1859,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     for (int t = 0; t < class_ntaps[z]; ++t) {
       const int* tp = taps + ((size_t)z * taps_stride + t) * 3;
       p.tap_dh[z][t] = (int8_t)tp[0];
-      p.tap_dw[z][t] = (int8_t)tp[1];
+      p.tap_dw[z][t] = (int16_t)tp[1];
       p.tap_k[z][t] = (int8_t)tp[2];
       if (tp[2] < 0 || tp[2] >= n_slabs) return set_error(B200_EINVAL, "conv_igemm: tap slab out of range");
     }
@@ -1800,6 +1899,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   p.mask_ld = mask_ld;
   p.mask_slope = mask_slope;
   p.stats_sum_only = stats_sum_only;
+  p.dbg = g_debug_timeline;
   {
     const int esz = out_f32 ? 4 : 2;
     const bool out_ok = (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (out_ld * esz) % 32 == 0 && (out_coff * esz) % 32 == 0;
@@ -1885,7 +1985,12 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
         return check_launch("conv_igemm(pair, halo)");
       }
     }
-    while (kg > 1 && (cin_blocks % kg || 3 * kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2) > kPairDyn)) --kg;
+    auto kg_divides = [&](int k) {
+      for (int z = 0; z < n_classes; ++z)
+        if ((class_ntaps[z] * cin_blocks) % k) return false;
+      return true;
+    };
+    while (kg > 1 && (!kg_divides(kg) || 3 * kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2) > kPairDyn)) --kg;
     p.kg = kg;
     const int pstage = kg * (128 * p.KC * 2 + (p.BN / 2) * p.KC * 2);
     int st = st_override >= 2 ? st_override : kPairDyn / pstage;
@@ -2003,7 +2108,7 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
     p.n_taps = n_taps;
     for (int t = 0; t < n_taps; ++t) {
       p.tap_dh[t] = (int8_t)taps[3 * t];
-      p.tap_dw[t] = (int8_t)taps[3 * t + 1];
+      p.tap_dw[t] = (int16_t)taps[3 * t + 1];
       p.tap_rs[t] = (int8_t)taps[3 * t + 2];
     }
     p.RS = RS;
@@ -2043,7 +2148,7 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
   p.n_taps = n_taps;
   for (int t = 0; t < n_taps; ++t) {
     p.tap_dh[t] = (int8_t)taps[3 * t];
-    p.tap_dw[t] = (int8_t)taps[3 * t + 1];
+    p.tap_dw[t] = (int16_t)taps[3 * t + 1];
     p.tap_rs[t] = (int8_t)taps[3 * t + 2];
   }
   p.RS = RS;

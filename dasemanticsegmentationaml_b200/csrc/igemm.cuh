@@ -17,7 +17,7 @@ struct ConvParams {
   int tiles_h[kMaxClasses], tiles_w[kMaxClasses];
   int n_taps[kMaxClasses];
   int8_t tap_dh[kMaxClasses][kMaxTaps];
-  int8_t tap_dw[kMaxClasses][kMaxTaps];
+  int16_t tap_dw[kMaxClasses][kMaxTaps];  // (16 bits: the zero-bordered pair view of the probabilities puts its second row a map width away)
   int8_t tap_k[kMaxClasses][kMaxTaps];  // index of the tap's K-slab in the packed filter
   int oa[kMaxClasses], ob[kMaxClasses];  // output pixel offset of the class
   int n_img;
@@ -62,6 +62,10 @@ struct ConvParams {
   int8_t tap_off[kMaxClasses][kMaxTaps];  // first row of the tap's window inside its box (oh * box_w + ow)
   int tb, sb;        // taps per filter-ring slot, filter-ring slots
   int bres;          // 1: the pair's whole filter tile (all slabs, all K-blocks) stays resident in shared memory
+  // diagnostic (b200_debug_timeline): CTA pair 0 records %globaltimer at its phase boundaries here
+  //   [0] kernel entry  [1] set-up done  [2] first operands landed  [3] exit
+  //   [8 + 4*lt + {0: MMAs of tile lt start, 1: committed, 2: epilogue starts (accumulator full), 3: epilogue done}]
+  long long* dbg;
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]
@@ -71,7 +75,7 @@ struct WgradParams {
   int in_stride;
   int n_taps;
   int8_t tap_dh[kMaxTaps];
-  int8_t tap_dw[kMaxTaps];
+  int16_t tap_dw[kMaxTaps];
   int RS;           // taps in the PyTorch filter (dW is [Cout][Cin][RS])
   int8_t tap_rs[kMaxTaps];
   int Cout, Cin;

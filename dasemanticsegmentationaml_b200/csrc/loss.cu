@@ -125,6 +125,29 @@ __device__ __forceinline__ void sample_smem(const float* s_lr, const Interp& ih,
   }
 }
 
+// Zero-bordered probability layout (out_flag / grad flag == 2 in mode 2): the map is stored as
+// [N][H+2][W+2][p_ld] with the image at rows/cols 1..H / 1..W and a zero border, i.e. the conv padding is
+// materialised.  The dense discriminator's 4x4/stride-2/pad-1 first layer then reads column PAIRS of it as
+// 128-byte, stride-1 TMA rows (model/discriminator.py); the forward writes the border zeros itself.
+__device__ __forceinline__ int64_t padded_pixel(int n, int h, int w, int H, int W) {
+  return ((int64_t)n * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+}
+__device__ __forceinline__ void zero_pixel(__nv_bfloat16* q, int p_ld) {
+  for (int c = 0; c < p_ld / 8; ++c) reinterpret_cast<uint4*>(q)[c] = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void zero_border(__nv_bfloat16* base, int n, int h, int w, int H, int W, int p_ld) {
+  const bool top = h == 0, bot = h == H - 1, left = w == 0, right = w == W - 1;
+  if (!(top | bot | left | right)) return;
+  if (top) zero_pixel(base + padded_pixel(n, -1, w, H, W) * p_ld, p_ld);
+  if (bot) zero_pixel(base + padded_pixel(n, H, w, H, W) * p_ld, p_ld);
+  if (left) zero_pixel(base + padded_pixel(n, h, -1, H, W) * p_ld, p_ld);
+  if (right) zero_pixel(base + padded_pixel(n, h, W, H, W) * p_ld, p_ld);
+  if (top && left) zero_pixel(base + padded_pixel(n, -1, -1, H, W) * p_ld, p_ld);
+  if (top && right) zero_pixel(base + padded_pixel(n, -1, W, H, W) * p_ld, p_ld);
+  if (bot && left) zero_pixel(base + padded_pixel(n, H, -1, H, W) * p_ld, p_ld);
+  if (bot && right) zero_pixel(base + padded_pixel(n, H, W, H, W) * p_ld, p_ld);
+}
+
 // ------------------------------------------------------------------ forward
 // mode 0: full-resolution logits, NCHW (fp32 or bf16)        -> out_full
 // mode 1: cross-entropy: acc[0] += sum loss, acc[1] += #valid; optional per-pixel loss map
@@ -178,6 +201,10 @@ upsample_fwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
       float lse;
       softmax_inplace<NC>(v, &lse);
       __nv_bfloat16* q = static_cast<__nv_bfloat16*>(out) + p * p_ld;
+      if (out_is_bf16_or_u8 == 2) {
+        q = static_cast<__nv_bfloat16*>(out) + padded_pixel(n, h, w, H, W) * p_ld;
+        zero_border(static_cast<__nv_bfloat16*>(out), n, h, w, H, W, p_ld);
+      }
       uint32_t pk[kMaxCls / 2];
 #pragma unroll
       for (int c = 0; c < kMaxCls / 2; ++c) {
@@ -286,6 +313,10 @@ upsample_fwd_tiled_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_
       float lse;
       softmax_inplace<NC>(v, &lse);
       __nv_bfloat16* q = static_cast<__nv_bfloat16*>(out) + p * p_ld;
+      if (out_is_bf16_or_u8 == 2) {
+        q = static_cast<__nv_bfloat16*>(out) + padded_pixel(n, h, w, H, W) * p_ld;
+        zero_border(static_cast<__nv_bfloat16*>(out), n, h, w, H, W, p_ld);
+      }
       uint32_t pk[kMaxCls / 2];
 #pragma unroll
       for (int c = 0; c < kMaxCls / 2; ++c) {
@@ -405,7 +436,8 @@ upsample_bwd_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_lr, in
           for (int c = 0; c < NC; ++c) g[c] = (v[c] - (c == lab ? 1.f : 0.f)) * cf;
         }
       } else {
-        const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(grad_in) + p * p_ld;
+        const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(grad_in) +
+                                 (grad_is_bf16 == 2 ? padded_pixel(n, h, w, H, W) : p) * p_ld;
         float dp[NC];
         float dot = 0.f;
 #pragma unroll
@@ -593,7 +625,8 @@ upsample_bwd_strip_kernel(const float* __restrict__ lr, int lr_ld, int N, int h_
           float lse;
           softmax_inplace<NC>(g, &lse);
           float dp[NC];
-          const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(grad_in) + p * p_ld;
+          const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(grad_in) +
+                                   (grad_is_bf16 == 2 ? padded_pixel(n, h, w, H, W) : p) * p_ld;
           if ((p_ld & 7) == 0) {  // 16-byte aligned pixel rows: three vector loads cover 24 classes
             uint32_t raw[12];
 #pragma unroll

@@ -115,6 +115,34 @@ def dgrad_geometry(hin, win, r, s, stride, pad):
     return g
 
 
+def pairview_fwd_geometry(h, w):
+    """Conv2d(k=4, s=2, p=1) over an [h, w] map stored zero-bordered as [h+2][w+2][32], seen as the
+    [(h+2)/2][w+2][64] view of its column pairs (a view row = two bordered rows side by side): tap
+    (a, r, b) = kernel row 2a + r, kernel columns 2b, 2b+1 reads view pixel (ho + a, r*(w+2)/2 + wo + b) --
+    a stride-1 filter of 8 taps with 128-byte rows and no padding left to do."""
+    key = ("pvf", h, w)
+    g = _geom_cache.get(key)
+    if g is None:
+        assert h % 2 == 0 and w % 2 == 0
+        half = (w + 2) // 2
+        taps = [(a, r * half + b, (2 * a + r) * 2 + b) for a in range(2) for r in range(2) for b in range(2)]
+        g = _geom_cache[key] = Geometry([dict(Ho=h // 2, Wo=w // 2, oa=0, ob=0, taps=taps)], 1, 1, h // 2, w // 2, "pvf4x4s2p1")
+    return g
+
+
+def pairview_dgrad_geometry(h, w):
+    """Data gradient of the same layer, written straight into the pair view [(h+2)/2][w+2][64] of the
+    zero-bordered gradient map: view row-half r (class r) gets the taps with kernel row parity r."""
+    key = ("pvd", h, w)
+    g = _geom_cache.get(key)
+    if g is None:
+        half = (w + 2) // 2
+        classes = [dict(Ho=(h + 2) // 2, Wo=half, oa=0, ob=r * half,
+                        taps=[(-a, -b, (2 * a + r) * 2 + b) for a in range(2) for b in range(2)]) for r in range(2)]
+        g = _geom_cache[key] = Geometry(classes, 1, 1, (h + 2) // 2, w + 2, "pvd4x4s2p1")
+    return g
+
+
 # ------------------------------------------------------------------ tuned tile table
 # Produced on a B200 by scripts/tune_conv.py (exhaustive sweep per layer shape); a missing key falls
 # back to the launcher's heuristic.  RECORD, when a list, collects the keys a workload touches.
@@ -187,34 +215,49 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
 _wgrad_taps = {}
 
 
-def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None, scratch=None):
+def conv_wgrad(dz, x, dw, r, s, stride, pad, tune=None, scratch=None, taps=None, flops=None):
     """dw[Cout,Cin,R,S] (fp32) += sum_pixels dz (x) x ; dz [N,Ho,Wo,>=Cout], x [N,Hin,Win,>=Cin].
     scratch: zeroed fp32 [R*S, Cout, round_up(Cin, 16)] -- accumulate there instead (dw untouched until
-    wgrad_unscratch)."""
+    wgrad_unscratch).  taps: explicit [(dh, dw, rs)] list of r*s taps instead of the (r, s, pad) window."""
     n, ho, wo, _, dz_ld = _nhwc_meta(dz)
     n2, hin, win, _, x_ld = _nhwc_meta(x)
     cout, cin = dw.shape[0], dw.shape[1]
     assert n2 == n and dw.dtype == torch.float32 and dw.is_contiguous()
-    taps = _wgrad_taps.get((r, s, pad))
-    if taps is None:
+    tkey = (r, s, pad) if taps is None else tuple(taps)
+    taps_c = _wgrad_taps.get(tkey)
+    if taps_c is None:
         flat = []
-        for i in range(r):
-            for j in range(s):
-                flat += [i - pad, j - pad, i * s + j]
-        taps = _wgrad_taps[(r, s, pad)] = int_array(flat)
+        if taps is None:
+            for i in range(r):
+                for j in range(s):
+                    flat += [i - pad, j - pad, i * s + j]
+        else:
+            assert len(taps) == r * s
+            for t in taps:
+                flat += list(t)
+        taps_c = _wgrad_taps[tkey] = int_array(flat)
+    tap_list, taps = taps, taps_c
     if tune is None:
-        key = wgrad_key(n, ho, wo, cout, cin, r, s, stride)
+        key = wgrad_key(n, ho, wo, cout, cin, r, s, stride) + ("" if tap_list is None else " v%d" % max(t[1] for t in tap_list))
         tune = TUNED.get(key, 0)
         if RECORD is not None:
             RECORD.append(("wgrad", key, dict(n=n, ho=ho, wo=wo, cout=cout, cin=cin, r=r, s=s, stride=stride, pad=pad,
-                                               hin=hin, win=win, dz_c=dz.shape[3], x_c=x.shape[3], dz_ld=dz_ld, x_ld=x_ld)))
+                                               hin=hin, win=win, dz_c=dz.shape[3], x_c=x.shape[3], dz_ld=dz_ld, x_ld=x_ld,
+                                               taps=tap_list, scratch=scratch is not None)))
     call("b200_conv_wgrad",
         ptr(dz), c_int(dz_ld), c_int(0), c_int(cout), c_int(n), c_int(ho), c_int(wo),
         ptr(x), c_int(x_ld), c_int(0), c_int(cin), c_int(hin), c_int(win),
         c_int(r * s), taps, c_int(r * s), c_int(stride), ptr(dw), ptr(scratch),
         c_int(0 if scratch is None else scratch.shape[2]), c_int(tune), stream(),
-        flops=2.0 * n * ho * wo * r * s * cout * cin, tag="px%d co%d ci%d taps%d s%d" % (n * ho * wo, cout, cin, r * s, stride))
+        flops=flops or 2.0 * n * ho * wo * r * s * cout * cin, tag="px%d co%d ci%d taps%d s%d" % (n * ho * wo, cout, cin, r * s, stride))
     return dw
+
+
+def wgrad_unscratch_pairview(scratch, dw):
+    """dw[Cout, Cin<=32, 4, 4] = pair-view scratch [8, Cout, 64] (see b200_pack_filter in include/b200seg.h)."""
+    assert scratch.shape == (8, dw.shape[0], 64) and dw.is_contiguous() and dw.shape[2:] == (4, 4)
+    call("b200_wgrad_unscratch_pairview", ptr(scratch), ptr(dw), c_int(dw.shape[0]), c_int(dw.shape[1]), stream(),
+         nbytes=8.0 * dw.numel(), tag="pair view")
 
 
 def wgrad_unscratch(scratch_base, dw_base, table, n_layers, n_weights=0):

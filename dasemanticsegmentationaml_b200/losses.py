@@ -106,10 +106,16 @@ def upsample_cross_entropy(lr, labels, n_classes=19, ignore_index=255):
 
 class _UpsampleSoftmax(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, lr, H, W, n_classes):
+    def forward(ctx, lr, H, W, n_classes, zero_border):
         n = lr.shape[0]
-        p = torch.empty((n, H, W, 32), dtype=BF16, device=lr.device)
-        K.upsample_fwd(lr, H, W, n_classes, K.UP_SOFTMAX, out=p, p_ld=32)
+        if zero_border:
+            # [N, H+2, W+2, 32] with the map at rows / cols 1..H / 1..W; the kernel writes the zero border
+            p = torch.empty((n, H + 2, W + 2, 32), dtype=BF16, device=lr.device)
+            K.upsample_fwd(lr, H, W, n_classes, K.UP_SOFTMAX, out=p, out_flag=2, p_ld=32)
+            p = p[:, 1:H + 1, 1:W + 1]
+        else:
+            p = torch.empty((n, H, W, 32), dtype=BF16, device=lr.device)
+            K.upsample_fwd(lr, H, W, n_classes, K.UP_SOFTMAX, out=p, p_ld=32)
         ctx.save_for_backward(lr)
         ctx.meta = (H, W, n_classes)
         return p.permute(0, 3, 1, 2)[:, :n_classes]
@@ -118,17 +124,27 @@ class _UpsampleSoftmax(torch.autograd.Function):
     def backward(ctx, dp):
         (lr,) = ctx.saved_tensors
         H, W, n_classes = ctx.meta
-        from .model._glue import to_nhwc
-        d = to_nhwc(dp)
+        from .model._glue import padded_base, padded_strides, to_nhwc
         d_lr = ops.zeros_f32(lr.shape, lr.device)
-        K.upsample_bwd(lr, H, W, n_classes, K.UP_SOFTMAX, d_lr, grad_in=d, grad_is_bf16=1, p_ld=d.stride(2))
-        return d_lr, None, None, None
+        if padded_strides(dp):   # the dense discriminator's pair-view data gradient: read it where it lies
+            K.upsample_bwd(lr, H, W, n_classes, K.UP_SOFTMAX, d_lr, grad_in=padded_base(dp), grad_is_bf16=2, p_ld=32)
+        else:
+            d = to_nhwc(dp)
+            K.upsample_bwd(lr, H, W, n_classes, K.UP_SOFTMAX, d_lr, grad_in=d, grad_is_bf16=1, p_ld=d.stride(2))
+        return d_lr, None, None, None, None
 
 
-def upsample_softmax(lr, H, W, n_classes=19):
+def upsample_softmax(lr, H, W, n_classes=19, zero_border=False):
     """softmax(upsample(lr), dim=1) as a bf16 channels-last ``[N, n_classes, H, W]`` tensor (a view of
-    a 32-channel NHWC buffer whose padding channels are zero) — the discriminator's input."""
-    return _UpsampleSoftmax.apply(lr, H, W, n_classes)
+    a 32-channel NHWC buffer whose padding channels are zero) — the discriminator's input.
+    zero_border=True (even H, W): the buffer is [N, H+2, W+2, 32] with a zero one-pixel border and the result
+    is a ``ZeroBordered`` view of its interior; ``FCDiscriminator`` then runs its first 4x4/stride-2/pad-1 layer
+    over 128-byte column pairs of that buffer (stride-1 TMA rows) instead of 64-byte stride-2 pixels.  Any other
+    consumer sees an ordinary strided tensor."""
+    if zero_border and H % 2 == 0 and W % 2 == 0:
+        from .model._glue import ZeroBordered
+        return _UpsampleSoftmax.apply(lr, H, W, n_classes, True).as_subclass(ZeroBordered)
+    return _UpsampleSoftmax.apply(lr, H, W, n_classes, False)
 
 
 class _BCEConst(torch.autograd.Function):

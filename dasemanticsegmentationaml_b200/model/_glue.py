@@ -50,6 +50,38 @@ def to_nchw(a):
     return a.permute(0, 3, 1, 2)
 
 
+class ZeroBordered(torch.Tensor):
+    """Marker type of ``losses.upsample_softmax(..., zero_border=True)``: a logical ``[N, C, H, W]`` bf16
+    tensor that is the interior of a ``[N, H+2, W+2, 32]`` NHWC buffer whose one-pixel border and padding
+    channels are ZERO (Conv2d's padding=1 materialised).  Views (``detach()``) keep the type and the strides;
+    anything that allocates new memory loses the stride pattern, so type + strides together identify it."""
+
+
+def padded_strides(x):
+    """True when the logical NCHW tensor x has the strides of the interior of a [N, H+2, W+2, 32] buffer."""
+    if x.dim() != 4 or x.dtype != BF16:
+        return False
+    n, c, h, w = x.shape
+    row = (w + 2) * 32
+    return (c <= 32 and h % 2 == 0 and w % 2 == 0 and tuple(x.stride()) == ((h + 2) * row, 1, row, 32)
+            and x.storage_offset() >= row + 32 and x.data_ptr() % 64 == 0)
+
+
+def padded_base(x):
+    """The whole [N, H+2, W+2, 32] buffer behind a tensor with padded_strides."""
+    n, c, h, w = x.shape
+    row = (w + 2) * 32
+    return torch.Tensor.as_strided(x.detach().as_subclass(torch.Tensor), (n, h + 2, w + 2, 32), ((h + 2) * row, row, 32, 1),
+                                   x.storage_offset() - row - 32)
+
+
+def zero_bordered_base(x):
+    """-> the zero-bordered [N, H+2, W+2, 32] buffer when x is one (see ZeroBordered), else None."""
+    if isinstance(x, ZeroBordered) and padded_strides(x):
+        return padded_base(x)
+    return None
+
+
 def module_params(module):
     ps = getattr(module, "_b200_params", None)
     if ps is None:

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .. import kernels as K
 from .. import ops
-from ._glue import B200Module, bn_tuple, to_nhwc
+from ._glue import B200Module, bn_tuple, to_nhwc, zero_bordered_base
 
 F32 = torch.float32
 BF16 = torch.bfloat16
@@ -81,11 +81,25 @@ class FCDiscriminator(_DiscriminatorBase):
         self.classifier = nn.Conv2d(ndf * 8, 1, kernel_size=4, stride=2, padding=1)
         self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
 
-    def _fwd(self, x):
+    # train.py asks losses.upsample_softmax for the zero-bordered layout when the discriminator says so
+    wants_zero_bordered_input = True
+
+    def _fwd_api(self, x):
+        xpad = zero_bordered_base(x) if self.conv1.weight.shape[0] % 64 == 0 else None
+        if xpad is None:
+            return super(FCDiscriminator, self)._fwd_api(x)
+        out, ctx = self._fwd(None, xpad=xpad)
+        ctx["in_c"] = x.shape[1]
+        return out, ctx
+
+    def _fwd(self, x, xpad=None):
         ctxs = []
         cur = x
         for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            cur, c = ops.conv_bias_act_fwd(cur, conv.weight, conv.bias.detach(), 2, 1, K.ACT_LEAKY, SLOPE)
+            if conv is self.conv1 and xpad is not None:
+                cur, c = ops.conv_pairview_fwd(xpad, conv.weight, conv.bias.detach(), K.ACT_LEAKY, SLOPE)
+            else:
+                cur, c = ops.conv_bias_act_fwd(cur, conv.weight, conv.bias.detach(), 2, 1, K.ACT_LEAKY, SLOPE)
             ctxs.append(c)
         out = _Classifier.fwd(self.classifier, cur)
         return out, {"convs": ctxs, "a4": cur}

@@ -30,7 +30,7 @@ def packed_filter(weight, transpose, shape=None):
         except AttributeError:
             pass
     shape = tuple(shape) if shape is not None else tuple(weight.shape)
-    key = (bool(transpose), shape)
+    key = (int(transpose), shape)
     ver, ptr_now = weight._version, weight.data_ptr()
     hit = cache.get(key)
     if hit is not None and hit[0] == ver and hit[1] == ptr_now and not FORCE_REPACK:
@@ -40,9 +40,35 @@ def packed_filter(weight, transpose, shape=None):
         buf = hit[2]  # repack in place: stable pointer for graphs, no allocator churn
         cout, cin, r, s = shape
         K.call("b200_pack_filter", K.ptr(w), K.ptr(buf), K.c_int(cout), K.c_int(cin), K.c_int(r * s),
-               K.c_int(buf.shape[0]), K.c_int(buf.shape[2]), K.c_int(1 if transpose else 0), K.stream())
+               K.c_int(buf.shape[0]), K.c_int(buf.shape[2]), K.c_int(int(transpose)), K.stream())
     else:
         buf = K.pack_filter(w, transpose)
+    cache[key] = (ver, ptr_now, buf)
+    return buf
+
+
+def packed_filter_pairview(weight, transpose):
+    """Pair-view packing [64][8][64] of a 4x4 / stride-2 / pad-1 filter with <= 32 input channels (the dense
+    discriminator's first layer over the zero-bordered probability map, see include/b200seg.h
+    b200_pack_filter); cached and batch-refreshed like every other packing (mode 2 / 3 of the pack kernels)."""
+    cout, cin, r, s = weight.shape
+    assert (r, s) == (4, 4) and cin <= 32 and cout % 16 == 0
+    mode = 3 if transpose else 2
+    cache = getattr(weight, "_b200_pack", None)
+    if cache is None:
+        cache = {}
+        weight._b200_pack = cache
+    key = (mode, (cout, cin, 8, 1))
+    ver, ptr_now = weight._version, weight.data_ptr()
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver and hit[1] == ptr_now and not FORCE_REPACK:
+        return hit[2]
+    if hit is not None and hit[2].device == weight.device:
+        buf = hit[2]
+    else:
+        buf = torch.empty((64, 8, cout) if transpose else (cout, 8, 64), dtype=BF16, device=weight.device)
+    K.call("b200_pack_filter", K.ptr(weight.detach()), K.ptr(buf), K.c_int(cout), K.c_int(cin), K.c_int(8),
+           K.c_int(buf.shape[0]), K.c_int(buf.shape[2]), K.c_int(mode), K.stream())
     cache[key] = (ver, ptr_now, buf)
     return buf
 
@@ -77,7 +103,7 @@ def refresh_packs(module, force=False):
         rows = []
         for w, (tr, shape), buf in stale:
             cout, cin, r, s = shape
-            rows.append([w.data_ptr(), buf.data_ptr(), cout, cin, r * s, buf.shape[0], buf.shape[2], 1 if tr else 0])
+            rows.append([w.data_ptr(), buf.data_ptr(), cout, cin, r * s, buf.shape[0], buf.shape[2], int(tr)])
         dev = torch.tensor(rows, dtype=torch.int64).to(stale[0][0].device)
         nbytes = float(sum(4 * w.numel() + 2 * buf.numel() for w, _, buf in stale))
         tab = (key, dev, nbytes)
@@ -427,7 +453,49 @@ def conv_bn_act_bwd(ctx, dy1, dy2=None, need_dx=True):
 
 # --------------------------------------------------------------------------- biased conv + LeakyReLU
 class ConvBiasCtx:
-    __slots__ = ("x", "weight", "stride", "pad", "a", "act", "slope", "has_bias")
+    __slots__ = ("x", "weight", "stride", "pad", "a", "act", "slope", "has_bias", "pairview")
+
+
+def conv_pairview_fwd(xpad, weight, bias_padded, act, slope):
+    """FCDiscriminator.conv1 (discriminator.py:9,18: Conv2d(C<=32, ndf, 4, 2, 1) + LeakyReLU) over the
+    zero-bordered probability buffer xpad [N, H+2, W+2, 32]: a stride-1 filter of 8 taps over its column-pair
+    view [N, (H+2)/2, W+2, 64] (kernels.pairview_fwd_geometry) -- 128-byte stride-1 TMA rows and K = 8 x 64
+    instead of 16 taps of 64-byte stride-2 rows."""
+    n, hp, wp, c = xpad.shape
+    assert c == 32 and xpad.is_contiguous() and hp % 2 == 0 and wp % 2 == 0
+    h, w = hp - 2, wp - 2
+    cout, cin = weight.shape[0], weight.shape[1]
+    xv = xpad.view(n, hp // 2, wp, 64)
+    a = torch.empty((n, h // 2, w // 2, cout), dtype=BF16, device=xpad.device)
+    K.conv_igemm(xv, packed_filter_pairview(weight, False), a, K.pairview_fwd_geometry(h, w), bias=bias_padded, act=act,
+                 slope=slope, k_real=2 * cin, n_real=cout)
+    ctx = ConvBiasCtx()
+    ctx.x, ctx.weight, ctx.stride, ctx.pad, ctx.a, ctx.act, ctx.slope = xv, weight, 2, 1, a, act, slope
+    ctx.pairview = (h, w)
+    return a, ctx
+
+
+def _pairview_wgrad(ctx, dz):
+    h, w = ctx.pairview
+    cout, cin = ctx.weight.shape[0], ctx.weight.shape[1]
+    sc = zeros_f32((8, cout, 64), dz.device)
+    taps = K.pairview_fwd_geometry(h, w).classes[0]["taps"]
+    K.conv_wgrad(dz, ctx.x, sc.view(cout, 64, 8, 1), 8, 1, 1, 0, scratch=sc, taps=taps,
+                 flops=2.0 * dz.shape[0] * dz.shape[1] * dz.shape[2] * 16 * cout * cin)
+    dw = zeros_f32(ctx.weight.shape, dz.device)
+    K.wgrad_unscratch_pairview(sc, dw)
+    return dw
+
+
+def _pairview_dgrad(ctx, dz):
+    """-> d(probabilities) as the interior view [N, H, W, 32] of a [N, H+2, W+2, 32] buffer (border = junk)."""
+    h, w = ctx.pairview
+    cout, cin = ctx.weight.shape[0], ctx.weight.shape[1]
+    n = dz.shape[0]
+    dxv = torch.empty((n, (h + 2) // 2, w + 2, 64), dtype=BF16, device=dz.device)
+    K.conv_igemm(dz, packed_filter_pairview(ctx.weight, True), dxv, K.pairview_dgrad_geometry(h, w), k_real=cout,
+                 n_real=2 * cin)
+    return dxv.view(n, h + 2, w + 2, 32)[:, 1:h + 1, 1:w + 1]
 
 
 def conv_bias_act_fwd(x, weight, bias_padded, stride, pad, act, slope):
@@ -435,6 +503,7 @@ def conv_bias_act_fwd(x, weight, bias_padded, stride, pad, act, slope):
     a = conv_raw_fwd(x, weight, stride, pad, bias=bias_padded, act=act, slope=slope)
     ctx = ConvBiasCtx()
     ctx.x, ctx.weight, ctx.stride, ctx.pad, ctx.a, ctx.act, ctx.slope = x, weight, stride, pad, a, act, slope
+    ctx.pairview = None
     return a, ctx
 
 
@@ -453,6 +522,12 @@ def conv_bias_act_bwd(ctx, dy1, dy2=None, need_dx=True, need_dw=True, dz_dbias=N
         dz = torch.empty(ctx.a.shape, dtype=BF16, device=ctx.a.device)
         dbias = zeros_f32((c,), ctx.a.device) if need_dw else None
         K.act_bwd_bias(dy1, dy2, ctx.a, dz, ctx.act, ctx.slope, dbias)
+    if ctx.pairview is not None:
+        dw = _pairview_wgrad(ctx, dz) if need_dw else None
+        dx = _pairview_dgrad(ctx, dz) if need_dx else None
+        if dbias is not None:
+            dbias = dbias[:ctx.weight.shape[0]]
+        return dx, dw, dbias
     dw = conv_wgrad(dz, ctx.x, ctx.weight, ctx.stride, ctx.pad) if need_dw else None
     dx = None
     if need_dx and producer is not None and producer.act == K.ACT_LEAKY and producer.a.shape[3] % 16 == 0:

@@ -75,6 +75,12 @@ def _opt_params(optimizer):
     return [p for g in optimizer.param_groups for p in g["params"]]
 
 
+def _zb(model_D):
+    """The dense FCDiscriminator reads its input as 128-byte column pairs of a zero-bordered buffer
+    (losses.upsample_softmax(zero_border=True)); the depthwise-separable variants take the plain layout."""
+    return bool(getattr(model_D, "wants_zero_bordered_input", False))
+
+
 def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images_t, lambda_adv=0.001):
     """One adversarial domain-adaptation iteration (train.py:192-262).
 
@@ -96,7 +102,7 @@ def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images
     # adversarial term on the target batch, through the frozen discriminator (train.py:223-237)
     lr_tgt = model.forward_lowres(images_t)
     optimizer.zero_grad()
-    p_tgt = losses.upsample_softmax(lr_tgt[0], H, W)
+    p_tgt = losses.upsample_softmax(lr_tgt[0], H, W, zero_border=_zb(model_D))
     d_out = model_D(p_tgt)
     loss_adv_g = losses.bce_with_logits_const(d_out, 0.0)
     (loss_adv_g * lambda_adv).backward()
@@ -107,7 +113,7 @@ def train_da_step(model, model_D, optimizer, optimizer_D, images, labels, images
     for p in model_D.parameters():
         p.requires_grad = True
     out_src = lr_src[0].detach()
-    d_out = model_D(losses.upsample_softmax(out_src, H, W))
+    d_out = model_D(losses.upsample_softmax(out_src, H, W, zero_border=_zb(model_D)))
     loss_d_src = losses.bce_with_logits_const(d_out, 0.0)
     loss_d_src.backward()
     allreduce_grads(_opt_params(optimizer_D))
@@ -142,7 +148,7 @@ def train_da_step_nni(model, model_D, optimizer, optimizer_D, images, labels, im
     loss.backward()
 
     lr_tgt = model.forward_lowres(images_t)                         # train_nni.py:132-139
-    d_out = model_D(losses.upsample_softmax(lr_tgt[2], H, W))
+    d_out = model_D(losses.upsample_softmax(lr_tgt[2], H, W, zero_border=_zb(model_D)))
     loss_d1 = losses.bce_with_logits_const(d_out, 0.0) * lambda_adv
     loss_d1.backward()
 
@@ -150,10 +156,10 @@ def train_da_step_nni(model, model_D, optimizer, optimizer_D, images, labels, im
         p.requires_grad = True
     out32_src = lr_src[2].detach()
     out32_tgt = lr_tgt[2].detach()
-    d_out = model_D(losses.upsample_softmax(out32_src, H, W))      # train_nni.py:147-151
+    d_out = model_D(losses.upsample_softmax(out32_src, H, W, zero_border=_zb(model_D)))      # train_nni.py:147-151
     loss_d_src = losses.bce_with_logits_const(d_out, 0.0)
     loss_d_src.backward()
-    d_out = model_D(losses.upsample_softmax(out32_tgt, H, W))      # train_nni.py:153-157
+    d_out = model_D(losses.upsample_softmax(out32_tgt, H, W, zero_border=_zb(model_D)))      # train_nni.py:153-157
     loss_d_tgt = losses.bce_with_logits_const(d_out, 1.0)
     loss_d_tgt.backward()
 

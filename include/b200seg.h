@@ -53,6 +53,12 @@ int b200_check_device(void);
  * model/model_stages.py:14-19, model/discriminator.py:9-13. */
 int b200_pack_filter(const float* w, void* out_bf16, int Cout, int Cin, int RS, int rows_pad,
                      int inner_pad, int transpose, cudaStream_t stream);
+/* transpose | 2 ("pair view", RS = 8, inner/rows = 64): the 4x4 / stride-2 / pad-1 filter of
+ * FCDiscriminator.conv1 (discriminator.py:9,18) re-expressed over COLUMN PAIRS of the zero-bordered
+ * probability map [N][H+2][W+2][32] that b200_upsample_fwd(mode 2, out_flag 2) writes: pair channel
+ * ci2 = s*32 + c, tap t = kh*2 + b  <->  w[co][c][kh][2b + s].  The layer then runs through b200_conv_igemm /
+ * b200_conv_wgrad as a stride-1 filter of 8 taps with 128-byte input rows (tap (a, r, b): dh = a,
+ * dw = r*(W+2)/2 + b over the [N][(H+2)/2][W+2][64] view, slab (2a + r)*2 + b). */
 
 /* The same for many filters in one launch: table_dev = int64 [n][8] on the device =
  * {src, dst, Cout, Cin, RS, rows_pad, inner_pad, transpose} (repacking after an optimizer step). */
@@ -80,6 +86,12 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
                     int stats_ld, const void* mask, int mask_ld, float mask_slope, int stats_sum_only,
                     int tune, cudaStream_t stream);
 
+/* Diagnostic: buf != NULL (device int64 [8 + 4*30]) makes CTA pair 0 of every following CTA-pair conv launch
+ * record %globaltimer at its phase boundaries (kernel entry, set-up done, first operands landed, exit; per
+ * tile: MMAs start / committed / epilogue starts / done) -- scripts/pair_timeline.py prints them.  NULL
+ * (the default) turns it off; never set on a production path. */
+int b200_debug_timeline(int64_t* buf);
+
 /* Weight gradient dW[Cout][Cin][RS] (fp32, PyTorch layout, accumulated) of the same convolutions:
  * dW[co][ci][rs] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]; taps = [n_taps][3] = (dh, dw, rs).
  * tune: 0 = automatic, else ci-tile | (stages << 12) | (pixel splits << 16) | (K pixels / 64 << 28). */
@@ -95,6 +107,9 @@ int b200_conv_wgrad(const void* dz, int dz_ld, int dz_coff, int Cout, int N, int
  * pointers, Cout, Cin, RS, ci_pad}). */
 int b200_wgrad_unscratch(const float* scratch_base, float* dw_base, const int64_t* table_dev, int n_layers,
                          cudaStream_t stream);
+/* Pair-view weight gradient (see b200_pack_filter): dw[co][c][kh][2b+s] = scratch[kh*2+b][co][s*32+c],
+ * scratch = fp32 [8][Cout][64] accumulated by b200_conv_wgrad over the pair view. */
+int b200_wgrad_unscratch_pairview(const float* scratch, float* dw, int Cout, int Cin, cudaStream_t stream);
 
 /* Stem ConvX(3, 32, 3, 2) (stdcnet.py:171, 6-15): K = 27 is too thin for a tap-by-tap implicit GEMM,
  * so the fp32 NCHW image is unfolded ONCE into bf16 rows col[n, ho, wo, k], k = ci*9 + r*3 + s
@@ -190,7 +205,11 @@ int b200_upsum_dot_reduce(const void* dout, int dout_ld, int Ho, int Wo, const v
  * (model_stages.py:240-242) fused with: mode 0 nothing (NCHW logits out), mode 1
  * CrossEntropyLoss(ignore_index=255) (train.py:66,86-89,214-217; acc[0] += sum, acc[1] += #valid;
  * optional per-pixel loss map for OHEM), mode 2 F.softmax(dim=1) (train.py:230,248,257; bf16 NHWC out),
- * mode 3 argmax (utils.py:120-121).  lr: fp32 NHWC low-resolution logits, pixel stride lr_ld. */
+ * mode 3 argmax (utils.py:120-121).  lr: fp32 NHWC low-resolution logits, pixel stride lr_ld.
+ * mode 2 with out_flag == 2 (forward) / grad_is_bf16 == 2 (backward): the probability map (its gradient) is
+ * the zero-bordered [N][H+2][W+2][p_ld] layout -- Conv2d's padding=1 materialised -- that the dense
+ * discriminator's first layer reads as 128-byte column pairs (discriminator.py:9,18); the forward writes
+ * the border zeros, the backward ignores the border. */
 int b200_upsample_fwd(const float* lr, int lr_ld, int N, int h_lr, int w_lr, int H, int W,
                       int n_classes, int mode, void* out, int out_flag, int p_ld,
                       const int64_t* labels, int ignore_index, double* acc, float* loss_map,

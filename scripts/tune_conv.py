@@ -21,7 +21,7 @@ import torch
 import torch.nn.functional as F
 
 from dasemanticsegmentationaml_b200 import build, kernels as K, train as T
-from tests.tuned_cases import igemm_reference
+from tests.tuned_cases import igemm_reference, wgrad_reference
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -180,13 +180,22 @@ for key, (kind, m) in sorted(records.items()):
             xx = torch.randn(m["n"], m["hin"], m["win"], m["x_ld"], device=dev).to(BF)[..., :m["x_c"]]
             dw = torch.zeros(m["cout"], m["cin"], m["r"], m["s"], device=dev)
             results = []
-            wref = torch.zeros(m["cout"], m["cin"], m["r"], m["s"], device=dev, requires_grad=True)
-            F.conv2d(xx[..., :m["cin"]].float().permute(0, 3, 1, 2), wref, stride=m["stride"], padding=m["pad"]).backward(
-                dz[..., :m["cout"]].float().permute(0, 3, 1, 2))
-            wref = wref.grad
+            tap_list = m.get("taps")
+            if tap_list is not None:   # explicit tap list (pair view): tap-major scratch, checked against the tap-table restatement
+                wref = wgrad_reference(dz[..., :m["cout"]], xx[..., :m["cin"]], tap_list, m["stride"]).permute(2, 0, 1).contiguous()
+                dw = torch.zeros(m["r"] * m["s"], m["cout"], m["cin"], device=dev)
+            else:
+                wref = torch.zeros(m["cout"], m["cin"], m["r"], m["s"], device=dev, requires_grad=True)
+                F.conv2d(xx[..., :m["cin"]].float().permute(0, 3, 1, 2), wref, stride=m["stride"], padding=m["pad"]).backward(
+                    dz[..., :m["cout"]].float().permute(0, 3, 1, 2))
+                wref = wref.grad
 
             def run(tune):
-                K.conv_wgrad(dz, xx, dw, m["r"], m["s"], m["stride"], m["pad"], tune=tune)
+                if tap_list is not None:
+                    K.conv_wgrad(dz, xx, dw.view(m["cout"], m["cin"], m["r"], m["s"]), m["r"], m["s"], m["stride"], m["pad"], tune=tune,
+                                 scratch=dw, taps=tap_list)
+                else:
+                    K.conv_wgrad(dz, xx, dw, m["r"], m["s"], m["stride"], m["pad"], tune=tune)
 
             def correct(tune):
                 dw.zero_()
@@ -220,7 +229,7 @@ for key, (kind, m) in sorted(records.items()):
         if kind == "conv":
             # CTA-pair kernel (cta_group::2, tune bit 22): BN x pipeline depth
             # (K-blocks per stage: automatic, 1 or 2; pipeline depth: automatic = as deep as fits)
-            for bn, kg in itertools.product((256, 128, 64, 32), (0, 1, 2)):
+            for bn, kg in itertools.product((256, 128, 64, 32), (0, 1, 2, 3, 4)):
                 if m["rows"] % bn:
                     continue
                 tune = bn | (kg << 24) | (1 << 22)

@@ -183,6 +183,67 @@ def test_discriminator_forward_backward(cuda_lib, kind):
          min(0.995, cosine(po2.grad, po.grad) - 0.03) if kind == "dwsep_bn" else 0.998)
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 32, 128, 256), (1, 12, 20, 100, 168), (8, 64, 128, 512, 1024)])
+def test_dense_discriminator_pair_view(cuda_lib, shape):
+    """FCDiscriminator.conv1 over column pairs of the zero-bordered probability buffer
+    (losses.upsample_softmax(zero_border=True); discriminator.py:9,18) against the SAME module on the plain
+    layout: same operands, another K order -> outputs / every gradient within bf16 accumulation noise, the
+    border really zero, and the gradient reaching the low-resolution logits identical to 1e-2.
+    The last case is BASELINE config[2]'s shape (N = 8, 512 x 1024), the one the benchmark runs."""
+    from dasemanticsegmentationaml_b200 import losses as L, ops
+    from dasemanticsegmentationaml_b200.model import FCDiscriminator
+    from dasemanticsegmentationaml_b200.model._glue import ZeroBordered, zero_bordered_base
+    n, h, w, H, W = shape
+    sd = O.make_discriminator_state("dense", seed=11)
+    d = load_oracle_state(FCDiscriminator(19), sd).to(DEV).train()
+    g = torch.Generator().manual_seed(21)
+    lr = torch.zeros(n, h, w, 32)
+    lr[..., :19] = 3 * torch.randn(n, h, w, 19, generator=g)
+    lr = lr.to(DEV)
+    res = []
+    for zb in (False, True):
+        a = lr.clone().requires_grad_(True)
+        p = L.upsample_softmax(a, H, W, zero_border=zb)
+        if zb:
+            assert isinstance(p, ZeroBordered)
+            base = zero_bordered_base(p)
+            assert base is not None and base.shape == (n, H + 2, W + 2, 32)
+            assert zero_bordered_base(p.detach()) is not None          # what train_da_step passes to the D step
+            assert zero_bordered_base((p.float() * 1.0).to(torch.bfloat16)) is None   # new memory: not the layout
+            border = torch.cat([base[:, 0].flatten(), base[:, -1].flatten(), base[:, :, 0].flatten(), base[:, :, -1].flatten()])
+            assert float(border.float().abs().max()) == 0.0
+            assert float(base[..., 19:].float().abs().max()) == 0.0
+            assert torch.equal(p, res[0][4])                           # same probabilities in either layout
+        d.zero_grad()
+        y = d(p)
+        loss = L.bce_with_logits_const(y, 0.0)
+        loss.backward()
+        res.append((y.detach().clone(), a.grad.clone(), {k: v.grad.clone() for k, v in d.named_parameters()}, loss.item(),
+                    p.detach().clone()))
+    (y0, g0, pg0, l0, _), (y1, g1, pg1, l1, _) = res
+    print("pair view: out", rel_l2(y1, y0), "d_lr", rel_l2(g1, g0), "loss", l0, l1)
+    assert rel_l2(y1, y0) < 5e-3
+    assert abs(l1 - l0) < 1e-3 * abs(l0)
+    for k in pg0:
+        gate("pair view %s" % k, cosine(pg1[k], pg0[k]), 0.9995)
+        assert rel_l2(pg1[k], pg0[k]) < 3e-2, k
+    gate("pair view d_lr", cosine(g1, g0), 0.9995)
+    assert rel_l2(g1, g0) < 3e-2
+    # conv1's weight gradient directly against torch on the same operands (exact products, fp32 sums)
+    if n * H * W <= 2 * 128 * 256:
+        pq = res[1][4].float()
+        wq = bf16_round(d.conv1.weight.detach())
+        wq.requires_grad_(True)
+        z = F.conv2d(pq, wq, stride=2, padding=1)
+        dz = bf16_round(torch.randn(z.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)) * 0.1)
+        z.backward(dz)
+        pz = L.upsample_softmax(lr, H, W, zero_border=True)
+        _, ctx = ops.conv_pairview_fwd(zero_bordered_base(pz), d.conv1.weight, d.conv1.bias.detach(), 2, 0.2)
+        _, dw, _ = ops.conv_bias_act_bwd(ctx, None, need_dx=False, need_dw=True,
+                                         dz_dbias=(dz.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), None))
+        assert rel_l2(dw, wq.grad) < 1e-3
+
+
 @pytest.mark.parametrize("shape", [(16, 32, 128, 256),    # 8x: strip / tiled fast kernels
                                    (12, 20, 100, 168),    # ragged strips and tiles
                                    (16, 32, 96, 192)])    # 6x: generic kernels

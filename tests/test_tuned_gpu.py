@@ -43,7 +43,14 @@ def test_tuned_conv_entry(cuda_lib, key):
     in_ld = cin_pad + (32 if (hin * win) % 3 == 0 else 0)
     xbuf = torch.randn(n, hin, win, in_ld, device="cuda", generator=g).to(BF)
     x = xbuf[..., :cin_pad]
-    if not c["dgrad"]:
+    if c.get("pairview"):
+        # the dense discriminator's first layer over column pairs of the zero-bordered map: checked against the
+        # tap-table restatement (tests/test_modules_gpu.py::test_dense_discriminator_pair_view ties the pair view
+        # itself to Conv2d(19, 64, 4, 2, 1))
+        geom = (K.pairview_dgrad_geometry if c["dgrad"] else K.pairview_fwd_geometry)(*c["pairview"])
+        filt = (torch.randn(rows, 8, 64, device="cuda", generator=g) / 512 ** 0.5).to(BF)
+        ref = TC.igemm_reference(x, filt, geom)
+    elif not c["dgrad"]:
         cout, cin = rows, cin_pad
         wgt = (torch.randn(cout, cin, r, s, device="cuda", generator=g) / (cin * r * s) ** 0.5).to(BF).float()
         filt = K.pack_filter(wgt, transpose=False)
@@ -69,7 +76,7 @@ def test_tuned_conv_entry(cuda_lib, key):
     if with_bias:
         ref = F.leaky_relu(ref + bias, 0.2)
     # their data gradients carry the producer's LeakyReLU backward + bias gradient
-    with_mask = c["dgrad"] and (r == 4 or (r == 1 and pad == 1)) and not c["stats"] and rows % 16 == 0
+    with_mask = c["dgrad"] and (r == 4 or (r == 1 and pad == 1)) and not c["stats"] and rows % 16 == 0 and not c.get("pairview")
     mask = None
     if with_mask:
         mask = torch.randn(n, geom.Hout, geom.Wout, rows, device="cuda", generator=g).to(BF)
@@ -110,6 +117,17 @@ def test_tuned_wgrad_entry(cuda_lib, key):
     n, ho, wo, cout, cin = c["n"], c["ho"], c["wo"], c["cout"], c["cin"]
     r, s, stride, pad, hin, win = c["r"], c["s"], c["stride"], c["pad"], c["hin"], c["win"]
     g = _gen(zlib.crc32(key.encode()) % 1000)
+    if c.get("pairview"):
+        taps = K.pairview_fwd_geometry(*c["pairview"]).classes[0]["taps"]
+        x = torch.randn(n, hin, win, 64, device="cuda", generator=g).to(BF)
+        dz = (torch.randn(n, ho, wo, cout, device="cuda", generator=g) * 0.1).to(BF)
+        ref = TC.wgrad_reference(dz, x, taps, 1)
+        for word in (tune, 0):
+            sc = torch.zeros(8, cout, 64, device="cuda")
+            K.conv_wgrad(dz, x, sc.view(cout, 64, 8, 1), 8, 1, 1, 0, tune=word, scratch=sc, taps=taps)
+            torch.cuda.synchronize()
+            assert rel_l2(sc.permute(1, 2, 0), ref) < 1e-3, (key, word)
+        return
     x_c = K.round_up(cin, 8)
     xbuf = torch.zeros(n, hin, win, K.round_up(cin, 32), device="cuda", dtype=BF)
     xbuf[..., :cin] = torch.randn(n, hin, win, cin, device="cuda", generator=g).to(BF)

@@ -33,6 +33,12 @@ def wgrad_keys():
 
 
 def parse_conv_key(key):
+    m = re.match(r"conv (\d+) (\d+) (\d+) c64 r(\d+) pv([fd])4x4s2p1$", key)
+    if m:   # pair view of the zero-bordered probability map (kernels.pairview_*_geometry)
+        n, hin, win, rows = (int(m.group(i)) for i in range(1, 5))
+        fwd = m.group(5) == "f"
+        return dict(n=n, hin=hin, win=win, cin_pad=64, rows=rows, dgrad=not fwd, r=4, s=4, stride=2, pad=1, f32=False,
+                    stats=False, pairview=(2 * hin - 2, win - 2) if fwd else (2 * hin, 2 * win))
     m = re.match(r"conv (\d+) (\d+) (\d+) c(\d+) r(\d+) ([fd])(\d+)x(\d+)s(\d+)p(\d+)( f32)?( st)?$", key)
     assert m, key
     n, hin, win, cin_pad, rows = (int(m.group(i)) for i in range(1, 6))
@@ -42,6 +48,11 @@ def parse_conv_key(key):
 
 
 def parse_wgrad_key(key):
+    m = re.match(r"wgrad (\d+) (\d+) (\d+) co(\d+) ci64 8x1s1 v(\d+)$", key)
+    if m:   # pair view: 8 taps over the [N, Ho + 1, 2 Wo + 2, 64] view
+        n, ho, wo, cout = (int(m.group(i)) for i in range(1, 5))
+        return dict(n=n, ho=ho, wo=wo, cout=cout, cin=64, r=8, s=1, stride=1, pad=0, hin=ho + 1, win=2 * wo + 2,
+                    pairview=(2 * ho, 2 * wo))
     m = re.match(r"wgrad (\d+) (\d+) (\d+) co(\d+) ci(\d+) (\d+)x(\d+)s(\d+)(?:p(\d+))?$", key)
     assert m, key
     n, ho, wo, cout, cin, r, s, stride = (int(m.group(i)) for i in range(1, 9))
@@ -90,4 +101,24 @@ def igemm_reference(x, filt, geom, n_out_rows=None):
             sub = xp[:, dh + top: dh + top + (ho - 1) * ist + 1: ist, dw + left: dw + left + (wo - 1) * ist + 1: ist]
             acc += torch.einsum("nhwc,oc->nhwo", sub, wf[:, slab])
         out[:, cl["oa"]::ost, cl["ob"]::ost][:, :ho, :wo] = acc
+    return out
+
+
+def wgrad_reference(dz, x, taps, stride):
+    """fp32 restatement of ONE b200_conv_wgrad launch from its tap list:
+        dW[co, ci, rs] = sum_{n, h, w} dz[n, h, w, co] * x[n, h*stride + dh, w*stride + dw, ci]   for (dh, dw, rs) in taps
+    (out-of-range input pixels read as zero)."""
+    import torch
+    import torch.nn.functional as F
+    n, ho, wo, cout = dz.shape
+    _, hin, win, cin = x.shape
+    dzf, xf = dz.float(), x.float()
+    out = torch.zeros((cout, cin, len(taps)), dtype=torch.float32, device=x.device)
+    for dh, dw, rs in taps:
+        top, left = max(0, -dh), max(0, -dw)
+        bottom = max(0, (ho - 1) * stride + dh - (hin - 1))
+        right = max(0, (wo - 1) * stride + dw - (win - 1))
+        xp = F.pad(xf, (0, 0, left, right, top, bottom))
+        sub = xp[:, dh + top: dh + top + (ho - 1) * stride + 1: stride, dw + left: dw + left + (wo - 1) * stride + 1: stride]
+        out[:, :, rs] = torch.einsum("nhwo,nhwc->oc", dzf, sub)
     return out
