@@ -753,6 +753,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   __shared__ PairBarriers bars;
   __shared__ float s_stats[2][256];
   __shared__ __align__(16) float s_tr[8][32 * kTrStride];   // per-warp transpose tiles of the epilogue
+  // per-tap operand offsets, looked up by the two issuing threads (an indexed load from the parameter block
+  // costs them hundreds of cycles per tap): [z][t] = {A window offset inside the K-block's boxes (>> 4),
+  // resident-filter offset of the tap's slab (>> 4), filter K coordinate of the slab}
+  __shared__ uint32_t s_tapA[kMaxClasses][kMaxTaps + 1], s_tapB[kMaxClasses][kMaxTaps + 1], s_tapK[kMaxClasses][kMaxTaps + 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -792,6 +796,14 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 512; i += kPairThreads) (&s_stats[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < kMaxClasses * (kMaxTaps + 1); i += kPairThreads) {
+    const int z = i / (kMaxTaps + 1), t = i - z * (kMaxTaps + 1);
+    const bool live = t < kMaxTaps && t < p.n_taps[z];
+    const int tk = live ? p.tap_k[z][t] : 0;
+    s_tapA[z][t] = live ? ((uint32_t)p.tap_pl[z][t] * plane_bytes + (uint32_t)p.tap_off[z][t] * (uint32_t)p.KC * 2u) >> 4 : 0u;
+    s_tapB[z][t] = ((uint32_t)(tk * cin_blocks) * b_half) >> 4;
+    s_tapK[z][t] = (uint32_t)(tk * p.cin_pad);
+  }
   if (warp == 1) {
     tmem_alloc_pair(smem_u32(&bars.tmem_base), tmem_cols);
     tmem_relinquish_pair();
@@ -851,7 +863,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               if (leader) mbar_expect_tx(fullB, 2u * bslot_bytes);
               uint32_t dst = bring_base + sb * bslot_bytes;
               for (int j = 0; j < p.tb; ++j, dst += b_half)
-                tma_load_2d_pair(dst, &tmB, fullB, p.tap_k[tc.z][t0 + j] * p.cin_pad + cb * p.KC, brow);
+                tma_load_2d_pair(dst, &tmB, fullB, (int)s_tapK[tc.z][t0 + j] + cb * p.KC, brow);
               if (++sb == p.sb) {
                 sb = 0;
                 phb ^= 1u;
@@ -921,7 +933,6 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint64_t htmpl = make_smem_desc(0, 16, (uint32_t)p.box_w * row_bytes, (p.KC == 64) ? 2u : 4u);
         const uint32_t h_hi = (uint32_t)(htmpl >> 32), h_lo = (uint32_t)htmpl;
         const uint32_t fullB0 = smem_u32(&bars.fullB[0]), emptyB0 = smem_u32(&bars.emptyB[0]);
-        const int ksteps = p.KC / 16;
         int sb = 0;
         uint32_t phb = 0;
         if (p.bres) mbar_wait(fullB0, 0);
@@ -934,26 +945,41 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int ntap = p.n_taps[tc.z];
           uint32_t accum = 0;
           if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
+          const uint32_t* tapA = s_tapA[tc.z];
+          const uint32_t* tapB = s_tapB[tc.z];
           for (int cb = 0; cb < cin_blocks; ++cb) {
             mbar_wait(full0 + 8u * s, ph);
             if (lt == 0 && cb == 0) dbg_mark(p, 2);
-            const uint32_t abox = smem_base + s * halo_bytes;
+            // (descriptor start-address fields are 14 bits of (address >> 4) below the template's other
+            //  fields: offsets are ADDED to the template, no carries out of the field at < 256 KB)
+            const uint32_t abase = h_lo + ((smem_base + s * halo_bytes) >> 4);
+            const uint32_t bres_base = d_lo + (bring_base >> 4) + (uint32_t)cb * (b_half >> 4);
+            uint32_t next_a = tapA[0], next_b = tapB[0];   // the table entry of tap t + 1 is fetched while tap t's MMAs issue
             for (int t0 = 0; t0 < ntap; t0 += p.tb) {
-              uint32_t b_lo;
-              if (p.bres) {
-                b_lo = 0;
-              } else {
+              uint32_t b_lo = 0;
+              if (!p.bres) {
                 if (!ready) mbar_wait(fullB0 + 8u * sb, phb);
-                b_lo = d_lo | ((bring_base + sb * bslot_bytes) >> 4);
+                b_lo = d_lo + ((bring_base + sb * bslot_bytes) >> 4);
               }
               tc_fence_after();
               for (int j = 0; j < p.tb; ++j, b_lo += b_half >> 4) {
                 const int t = t0 + j;
-                if (p.bres) b_lo = d_lo | ((bring_base + (uint32_t)(p.tap_k[tc.z][t] * cin_blocks + cb) * b_half) >> 4);
-                const uint32_t a_lo = h_lo | ((abox + (uint32_t)p.tap_pl[tc.z][t] * plane_bytes + (uint32_t)p.tap_off[tc.z][t] * row_bytes) >> 4);
-                for (int k = 0; k < ksteps; ++k) {
-                  umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (b_lo + 2u * k), idesc, accum);
-                  accum = 1u;
+                const uint32_t a_lo = abase + next_a;
+                const uint32_t bb = p.bres ? bres_base + next_b : b_lo;
+                next_a = tapA[t + 1];
+                next_b = tapB[t + 1];
+                if (p.KC == 64) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (bb + 2u * k), idesc, accum);
+                    accum = 1u;
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (bb + 2u * k), idesc, accum);
+                    accum = 1u;
+                  }
                 }
               }
               if (!p.bres) {
