@@ -78,10 +78,13 @@ __device__ __forceinline__ void apply_mask16(float (&v)[16], const __nv_bfloat16
     w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w; w[4] = u1.x; w[5] = u1.y; w[6] = u1.z; w[7] = u1.w;
   }
 #pragma unroll
+  // factor = a > 0 ? 1 : slope as s + (1 - s) * slope with s = [a > 0] as 1.0f / 0.0f (exact for both values of
+  // s): sixteen select-on-predicate sequences end up serialised on ONE predicate register by ptxas
   for (int k = 0; k < 8; ++k) {
     const float2 a = unpack_bf16(w[k]);
-    v[2 * k] *= a.x > 0.f ? 1.f : slope;
-    v[2 * k + 1] *= a.y > 0.f ? 1.f : slope;
+    const float sx = a.x > 0.f ? 1.f : 0.f, sy = a.y > 0.f ? 1.f : 0.f;
+    v[2 * k] *= fmaf(1.f - sx, slope, sx);
+    v[2 * k + 1] *= fmaf(1.f - sy, slope, sy);
   }
 }
 
@@ -565,6 +568,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
 
 
+constexpr int kDbgTiles = 30;       // tiles of pair 0 a debug timeline records (buffer: 8 + 4 * kDbgTiles int64)
+__device__ __forceinline__ void dbg_mark(const ConvParams& p, int slot) {
+  if (p.dbg != nullptr && blockIdx.x < 2) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.dbg[slot] = t;
+  }
+}
+
 // ------------------------------------------------------------------ batched epilogue
 // 32 accumulator columns of one output pixel per thread: ONE tcgen05.ld + wait, then bias /
 // activation (branch-free: v > 0 ? v : v * ns with ns = 1 none, 0 ReLU, slope LeakyReLU) / LeakyReLU
@@ -577,11 +589,18 @@ constexpr int kTrStride = 20;   // floats per row of the transpose tile
 
 template <bool F32, bool STATS>
 __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t taddr, bool valid, size_t obase,
-                                                 size_t pix, int gcol, float ns, float* tb, float* s_sum,
-                                                 float* s_sq, int lane) {
+                                                 size_t pix, int gcol, float ns, float* tb, float (&r_sum)[2],
+                                                 float (&r_sq)[2], int lane, bool mark = false) {
   uint32_t r[32];
-  tmem_ld32(taddr, r);
-  tmem_ld_wait();
+  if (p.dbg_knob & 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = (uint32_t)lane;
+  } else {
+    tmem_ld32(taddr, r);
+    tmem_ld_wait();
+  }
+  if (mark) dbg_mark(p, 4);
+  if (p.dbg_knob & 1) valid = false;
 #pragma unroll
   for (int hv = 0; hv < 2; ++hv) {
     const int cc = 16 * hv;
@@ -600,8 +619,9 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t t
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[cc + j]);
     }
+    // act(v) = max(v, 0) + ns * min(v, 0): no predicates (see apply_mask16)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * ns;
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(ns, fminf(v[j], 0.f), fmaxf(v[j], 0.f));
     if (p.mask != nullptr && valid)
       apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + gcol + cc, p.mask_slope, p.wide);
     float x[16];
@@ -613,6 +633,7 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t t
       uint32_t pk[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      if (mark && hv == 0) dbg_mark(p, 5);
       if (valid) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
         if (p.wide) {
@@ -632,7 +653,8 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t t
         }
       }
     }
-    if (STATS) {
+    if (mark && hv == 0) dbg_mark(p, 6);
+    if (STATS && !(p.dbg_knob & 4)) {
       __syncwarp();   // the previous chunk's column reads are done
       float4* w4 = reinterpret_cast<float4*>(tb + lane * kTrStride);
 #pragma unroll
@@ -647,13 +669,13 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t t
         s1 += t;
         s2 = fmaf(t, t, s2);
       }
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-      if (lane < 16) {
-        atomicAdd(s_sum + cc + col, s1);
-        if (!p.stats_sum_only) atomicAdd(s_sq + cc + col, s2);
-      }
+      // lane (col, hf) keeps its 16-row partial of column gcol + cc + col in REGISTERS across the tiles of
+      // this CTA (fp32 atomicAdd on shared memory is a compare-and-swap loop: with eight warps on the same
+      // columns it was most of the epilogue); pair_epilogue folds them once per filter tile
+      r_sum[hv] += s1;
+      r_sq[hv] += s2;
     }
+    if (mark && hv == 0) dbg_mark(p, 7);
   }
 }
 
@@ -681,15 +703,6 @@ struct PairBarriers {
   uint32_t tmem_base;
 };
 
-constexpr int kDbgTiles = 30;       // tiles of pair 0 a debug timeline records (buffer: 8 + 4 * kDbgTiles int64)
-__device__ __forceinline__ void dbg_mark(const ConvParams& p, int slot) {
-  if (p.dbg != nullptr && blockIdx.x < 2) {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.dbg[slot] = t;
-  }
-}
-
 constexpr int kPairThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 template <bool F32, bool STATS>
@@ -703,12 +716,35 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
   const int t = threadIdx.x - 64;      // 0..255 among the epilogue threads
   const float ns = p.act == 0 ? 1.f : (p.act == 1 ? 0.f : p.slope);
   const uint32_t acc_cols = (uint32_t)p.BN;
+  // per-lane statistics partials: [32-column batch of this warp][16-column half]
+  float r_sum[4][2], r_sq[4][2];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) r_sum[b][0] = r_sum[b][1] = r_sq[b][0] = r_sq[b][1] = 0.f;
+  auto fold_stats = [&]() {   // registers -> the CTA's shared column sums (once per filter tile)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = 32 * half + 64 * b;
+      if (c < p.BN) {
+#pragma unroll
+        for (int hv = 0; hv < 2; ++hv) {
+          const float s1 = r_sum[b][hv] + __shfl_xor_sync(0xffffffffu, r_sum[b][hv], 16);
+          const float s2 = r_sq[b][hv] + __shfl_xor_sync(0xffffffffu, r_sq[b][hv], 16);
+          if (lane < 16) {
+            atomicAdd(&s_stats[0][c + 16 * hv + lane], s1);
+            if (!p.stats_sum_only) atomicAdd(&s_stats[1][c + 16 * hv + lane], s2);
+          }
+          r_sum[b][hv] = r_sq[b][hv] = 0.f;
+        }
+      }
+    }
+  };
   int lt = 0, cur_n0 = -1;
   for (int m = m_first; m < m_total; m += m_step, ++lt) {
     const TileCoord tc = decode_tile(p, my_n, m);
     const int z = tc.z;
     if (STATS && tc.n0 != cur_n0) {
       if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
+        fold_stats();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 256);
         if (!p.stats_sum_only) flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 256);
@@ -731,8 +767,13 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
     const size_t pix =
         ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
     const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
-    for (int c = 32 * half; c < p.BN; c += 64)
-      epilogue_batch32<F32, STATS>(p, acc + c, valid, obase + c, pix, tc.n0 + c, ns, tb, &s_stats[0][c], &s_stats[1][c], lane);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = 32 * half + 64 * b;
+      if (c < p.BN)
+        epilogue_batch32<F32, STATS>(p, acc + c, valid, obase + c, pix, tc.n0 + c, ns, tb, r_sum[b], r_sq[b], lane,
+                                     p.dbg != nullptr && warp == 2 && lane == 0 && rank == 0 && lt == 1 && c == 0);
+    }
     // this warp is done with the buffer: tell the leader's MMA warp (count 16 = both CTAs)
     tc_fence_before();
     __syncwarp();
@@ -740,6 +781,7 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
     if (warp == 2 && lane == 0 && rank == 0 && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 3);
   }
   if (STATS && cur_n0 >= 0) {
+    fold_stats();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 256);
     if (!p.stats_sum_only) flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 256);
@@ -1691,6 +1733,11 @@ int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStrea
   return check_launch("pack_filters_batched");
 }
 
+static int g_debug_knob = 0;
+int b200_debug_knob(int knob) {
+  g_debug_knob = knob;
+  return B200_OK;
+}
 static long long* g_debug_timeline = nullptr;
 int b200_debug_timeline(int64_t* buf) {
   g_debug_timeline = reinterpret_cast<long long*>(buf);
@@ -1926,6 +1973,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   p.mask_slope = mask_slope;
   p.stats_sum_only = stats_sum_only;
   p.dbg = g_debug_timeline;
+  p.dbg_knob = g_debug_knob;
   {
     const int esz = out_f32 ? 4 : 2;
     const bool out_ok = (reinterpret_cast<uintptr_t>(out) & 31) == 0 && (out_ld * esz) % 32 == 0 && (out_coff * esz) % 32 == 0;

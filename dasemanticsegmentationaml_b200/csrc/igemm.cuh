@@ -66,6 +66,7 @@ struct ConvParams {
   //   [0] kernel entry  [1] set-up done  [2] first operands landed  [3] exit
   //   [8 + 4*lt + {0: MMAs of tile lt start, 1: committed, 2: epilogue starts (accumulator full), 3: epilogue done}]
   long long* dbg;
+  int dbg_knob;      // diagnostic (b200_debug_knob): epilogue parts switched off for timing experiments (WRONG results)
 };
 
 // dW[co, ci, tap] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]

@@ -249,7 +249,11 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
 }
 // Arrive on the mbarrier at this offset in the pair's leader CTA (local for the leader itself).
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+  // .relaxed: the default .release.cluster costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per arrival, i.e. the warp
+  // waits for its 16 KB of global stores to become visible GPU-wide (~1 us per tile).  Nothing the waiter (the
+  // MMA thread, about to overwrite the TMEM buffer) reads was written by this warp: the accumulator values are
+  // already in registers (tcgen05.wait::ld) and tcgen05.fence::before_thread_sync orders the TMEM reads.
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 
 // ------------------------------------------------------------ descriptors

@@ -49,6 +49,21 @@ def upsample_logits(lr, H, W, n_classes=19, dtype=F32):
     return _UpsampleLogits.apply(lr, H, W, n_classes, dtype)
 
 
+# The reference trains under nn.DataParallel (train.py:145-152,497): the batch is split over the GPUs for the
+# forward only and CrossEntropyLoss runs ONCE on the gathered logits, i.e. its mean is over the valid pixels
+# of the GLOBAL batch (train.py:214-217).  With one process per GPU the same value needs the (loss sum,
+# valid count) pair summed over ranks -- one 16-byte all-reduce per CE term -- and every rank's gradient
+# scaled by world / global count, so that the AVG gradient exchange that follows yields d(global mean)/dW.
+# False: each rank normalises by its own valid count (identical when every rank sees the same number of
+# labelled pixels, and what a rank-local loss would do).
+GLOBAL_BATCH_MEAN = True
+
+
+def _dist_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 class _UpsampleCE(torch.autograd.Function):
     """Training: ONE pass computes the loss and the un-normalised gradient w.r.t. the low-resolution
     logits (the interpolation + softmax of every pixel is needed for both); backward only scales it
@@ -64,13 +79,19 @@ class _UpsampleCE(torch.autograd.Function):
             ctx.save_for_backward(d_lr, acc)
         else:
             K.upsample_fwd(lr, H, W, n_classes, K.UP_CE, labels=labels, ignore_index=ignore_index, acc=acc)
+        ctx.grad_mul = 1.0
+        world = _dist_world()
+        if GLOBAL_BATCH_MEAN and world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(acc)          # (sum of losses, valid pixels) of the global batch, in place
+            ctx.grad_mul = float(world)
         return (acc[0] / acc[1]).to(F32)
 
     @staticmethod
     def backward(ctx, g):
         d_unscaled, acc = ctx.saved_tensors
         d_lr = torch.empty_like(d_unscaled)
-        K.scale_f32(d_unscaled, g.to(F32).contiguous(), acc[1:], 1.0, d_lr)
+        K.scale_f32(d_unscaled, g.to(F32).contiguous(), acc[1:], ctx.grad_mul, d_lr)
         return d_lr, None, None, None, None, None
 
 

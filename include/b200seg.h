@@ -91,6 +91,10 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
  * tile: MMAs start / committed / epilogue starts / done) -- scripts/pair_timeline.py prints them.  NULL
  * (the default) turns it off; never set on a production path. */
 int b200_debug_timeline(int64_t* buf);
+/* Diagnostic: switches parts of the CTA-pair kernel's epilogue off for timing experiments (bit 0: no global
+ * stores, bit 1: no TMEM loads, bit 2: no BatchNorm statistics).  Results are WRONG while it is non-zero;
+ * 0 (the default) is the only value a production path may see. */
+int b200_debug_knob(int knob);
 
 /* Weight gradient dW[Cout][Cin][RS] (fp32, PyTorch layout, accumulated) of the same convolutions:
  * dW[co][ci][rs] += sum_pixels dz[pixel, co] * x[pixel*stride + tap, ci]; taps = [n_taps][3] = (dh, dw, rs).

@@ -33,6 +33,8 @@ def shapes():
 
 
 def main():
+    knob = int(os.environ.get("KNOB", "0"))
+    call("b200_debug_knob", K.c_int(knob))
     names = sys.argv[1:] or list(shapes())
     tunes = {}
     for a in list(names):
@@ -81,6 +83,10 @@ def main():
         rel = lambda v: (v - t0) / 1e3 if v else float("nan")
         print("%-8s tune=%#x  %.1f us/launch in a graph; pair 0: set-up %.2f  first operands %.2f  exit %.2f us" %
               (name, tune, us, rel(t[1]), rel(t[2]), rel(t[3])))
+        if t[4]:
+            e1 = t[8 + 4 + 2]
+            print("  tile 1, first 32-column batch of warp 2 (us after the accumulator was full): TMEM load done %.2f, first 16 "
+                  "columns packed %.2f, stored %.2f, statistics done %.2f" % tuple((v - e1) / 1e3 for v in t[4:8]))
         rows = []
         for lt in range(NT):
             a = t[8 + 4 * lt: 12 + 4 * lt]

@@ -489,3 +489,16 @@ def test_overlapped_gradient_exchange_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29531",
                         os.path.join(root, "scripts", "check_reducer.py")], capture_output=True, text=True, timeout=300)
     assert "REDUCER CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL)")
+def test_global_batch_cross_entropy_two_gpus():
+    """losses.GLOBAL_BATCH_MEAN on real NCCL (scripts/check_global_ce.py): the CE mean is over the valid
+    pixels of the global batch, as under the reference's nn.DataParallel (train.py:145-152,214-217)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "scripts", "check_global_ce.py")], capture_output=True, text=True, timeout=300)
+    assert "GLOBAL CE CHECK PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
