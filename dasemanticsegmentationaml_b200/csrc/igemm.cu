@@ -33,7 +33,7 @@ struct PipeBarriers {
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return v > 0.f ? v : v * slope;
+  if (act == 2) return fmaf(slope, fminf(v, 0.f), fmaxf(v, 0.f));   // (no predicates: see apply_mask16)
   return v;
 }
 
@@ -133,7 +133,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PipeBarriers bars;
-  __shared__ float s_stats[2][256];
+  __shared__ float s_stats[4][2][256];   // one slice per epilogue warp: plain += instead of shared-memory CAS loops
 
   const int z = blockIdx.z;
   const int tiles_per_img = p.tiles_h[z] * p.tiles_w[z];
@@ -165,7 +165,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_mbar_init();
   }
   if (p.stats != nullptr) {
-    for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 2048; i += kThreads) (&s_stats[0][0][0])[i] = 0.f;
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(&bars.tmem_base), tmem_cols);
@@ -283,8 +283,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float t2 = p.stats_sum_only ? 0.f : column_sums16(s2, lane);
           if ((lane & 1) == 0) {
             const int col = c + column_of_lane(lane);
-            atomicAdd(&s_stats[0][col], t1);
-            if (!p.stats_sum_only) atomicAdd(&s_stats[1][col], t2);
+            s_stats[q][0][col] += t1;
+            if (!p.stats_sum_only) s_stats[q][1][col] += t2;
           }
         }
       }
@@ -292,8 +292,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       const int t = threadIdx.x - 64;
-      flush_add_v4(p.stats + n0, s_stats[0], p.BN, t, 128);
-      flush_add_v4(p.stats + p.stats_ld + n0, s_stats[1], p.BN, t, 128);
+      flush_add4_v4(p.stats + n0, &s_stats[0][0][0], 512, p.BN, t, 128);
+      if (!p.stats_sum_only) flush_add4_v4(p.stats + p.stats_ld + n0, &s_stats[0][1][0], 512, p.BN, t, 128);
     }
   }
 
@@ -345,13 +345,70 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int n_tile
   return t;
 }
 
+// A CTA pair walks a CONTIGUOUS range of pixel tiles [m, m_end) of one filter tile: the coordinates advance
+// by increment (decode_tile's divisions and indexed parameter loads once per CTA instead of once per tile
+// and role -- for 16-MMA tiles they cost the issuing threads as much as the tile itself) and neighbouring
+// tiles, which share halo rows, are fetched by the same SM back to back.
+struct TileIter {
+  int z, n_img, th_i, tw_i, th_n, tw_n, m, m_end, n0;
+  __device__ __forceinline__ TileIter(const ConvParams& p, int n_tile, int m_begin, int m_stop) {
+    m = m_begin;
+    m_end = m_stop;
+    n0 = n_tile * p.BN;
+    int rem = m;
+    z = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses - 1; ++k) {
+      const int cnt = p.tiles_h[z] * p.tiles_w[z] * p.n_img;
+      if (rem >= cnt && p.n_taps[z + 1] > 0) {
+        rem -= cnt;
+        ++z;
+      }
+    }
+    th_n = p.tiles_h[z];
+    tw_n = p.tiles_w[z];
+    const int per_img = th_n * tw_n;
+    n_img = rem / per_img;
+    const int t_in = rem - n_img * per_img;
+    th_i = t_in / tw_n;
+    tw_i = t_in - th_i * tw_n;
+  }
+  __device__ __forceinline__ bool valid() const { return m < m_end; }
+  __device__ __forceinline__ TileCoord coord(const ConvParams& p) const {
+    TileCoord t;
+    t.z = z;
+    t.n_img = n_img;
+    t.h0 = th_i * p.th * p.mt;
+    t.w0 = tw_i * p.tw;
+    t.n0 = n0;
+    return t;
+  }
+  __device__ __forceinline__ void next(const ConvParams& p) {
+    ++m;
+    if (++tw_i == tw_n) {
+      tw_i = 0;
+      if (++th_i == th_n) {
+        th_i = 0;
+        if (++n_img == p.n_img) {
+          n_img = 0;
+          if (z + 1 < kMaxClasses) {
+            ++z;
+            th_n = p.tiles_h[z];
+            tw_n = p.tiles_w[z];
+          }
+        }
+      }
+    }
+  }
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ ConvParams p, int m_total, int n_tiles, int b_resident,
                              int n_slabs) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PersistBarriers bars;
-  __shared__ float s_stats[2][256];
+  __shared__ float s_stats[4][2][256];   // one slice per epilogue warp (see conv_igemm_kernel)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -385,7 +442,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     mbar_init(smem_u32(&bars.bfull), 1);
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 512; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 2048; i += kThreads) (&s_stats[0][0][0])[i] = 0.f;
   if (warp == 1) {
     tmem_alloc(smem_u32(&bars.tmem_base), tmem_cols);
     tmem_relinquish();
@@ -492,13 +549,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const int t = threadIdx.x - 64;
-          flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
-          flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
+          flush_add4_v4(p.stats + cur_n0, &s_stats[0][0][0], 512, p.BN, t, 128);
+          if (!p.stats_sum_only) flush_add4_v4(p.stats + p.stats_ld + cur_n0, &s_stats[0][1][0], 512, p.BN, t, 128);
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int col = t; col < p.BN; col += 128) {
-            s_stats[0][col] = 0.f;
-            s_stats[1][col] = 0.f;
-          }
+          for (int i = t; i < 2048; i += 128) (&s_stats[0][0][0])[i] = 0.f;
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         cur_n0 = tc.n0;
@@ -539,8 +593,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             const float t2 = p.stats_sum_only ? 0.f : column_sums16(s2, lane);
             if ((lane & 1) == 0) {
               const int col = c + column_of_lane(lane);
-              atomicAdd(&s_stats[0][col], t1);
-              if (!p.stats_sum_only) atomicAdd(&s_stats[1][col], t2);
+              s_stats[q][0][col] += t1;
+              if (!p.stats_sum_only) s_stats[q][1][col] += t2;
             }
           }
         }
@@ -553,8 +607,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     if (p.stats != nullptr && cur_n0 >= 0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int t = threadIdx.x - 64;
-      flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 128);
-      flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 128);
+      flush_add4_v4(p.stats + cur_n0, &s_stats[0][0][0], 512, p.BN, t, 128);
+      if (!p.stats_sum_only) flush_add4_v4(p.stats + p.stats_ld + cur_n0, &s_stats[0][1][0], 512, p.BN, t, 128);
     }
   }
 
@@ -707,7 +761,7 @@ constexpr int kPairThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 
 template <bool F32, bool STATS>
 __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers& bars, float (*s_stats)[256], float* tb,
-                                              uint32_t tmem, int rank, int my_n, int m_first, int m_step, int m_total,
+                                              uint32_t tmem, int rank, int my_n, int m_first, int m_stop,
                                               int warp, int lane) {
   const int q = warp & 3;              // TMEM lane quarter this warp may read
   const int half = (warp - 2) >> 2;    // which 32-column batches: b % 2 == half
@@ -720,27 +774,42 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
   float r_sum[4][2], r_sq[4][2];
 #pragma unroll
   for (int b = 0; b < 4; ++b) r_sum[b][0] = r_sum[b][1] = r_sq[b][0] = r_sq[b][1] = 0.f;
-  auto fold_stats = [&]() {   // registers -> the CTA's shared column sums (once per filter tile)
+  // registers -> the CTA's shared column sums (once per filter tile), without atomics: every warp parks its
+  // partials in its OWN transpose tile ([batch][half][column][sum, sumsq]), then thread `col` adds the four
+  // warps (one per TMEM lane quarter) that cover its column
+  auto fold_stats = [&]() {
+    __syncwarp();
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int c = 32 * half + 64 * b;
-      if (c < p.BN) {
+      if (32 * half + 64 * b < p.BN) {
 #pragma unroll
         for (int hv = 0; hv < 2; ++hv) {
           const float s1 = r_sum[b][hv] + __shfl_xor_sync(0xffffffffu, r_sum[b][hv], 16);
           const float s2 = r_sq[b][hv] + __shfl_xor_sync(0xffffffffu, r_sq[b][hv], 16);
-          if (lane < 16) {
-            atomicAdd(&s_stats[0][c + 16 * hv + lane], s1);
-            if (!p.stats_sum_only) atomicAdd(&s_stats[1][c + 16 * hv + lane], s2);
-          }
+          if (lane < 16) *reinterpret_cast<float2*>(tb + ((b * 2 + hv) * 16 + lane) * 2) = make_float2(s1, s2);
           r_sum[b][hv] = r_sq[b][hv] = 0.f;
         }
       }
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float* tiles = tb - (warp - 2) * (32 * kTrStride);
+    for (int col = t; col < p.BN; col += 256) {
+      const int cb = col >> 6, chalf = (col >> 5) & 1, chv = (col >> 4) & 1;
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float2 v = *reinterpret_cast<const float2*>(tiles + (chalf * 4 + qq) * (32 * kTrStride) +
+                                                           ((cb * 2 + chv) * 16 + (col & 15)) * 2);
+        a1 += v.x;
+        a2 += v.y;
+      }
+      s_stats[0][col] += a1;
+      s_stats[1][col] += a2;
+    }
   };
   int lt = 0, cur_n0 = -1;
-  for (int m = m_first; m < m_total; m += m_step, ++lt) {
-    const TileCoord tc = decode_tile(p, my_n, m);
+  for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
+    const TileCoord tc = it.coord(p);
     const int z = tc.z;
     if (STATS && tc.n0 != cur_n0) {
       if (cur_n0 >= 0) {  // flush the statistics of the filter tile we are leaving
@@ -819,7 +888,10 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t bring_base = smem_base + (uint32_t)p.stages * halo_bytes;
   const int cin_blocks = p.cin_pad / p.KC;
   const int my_n = pair % n_tiles;
-  const int m_first = pair / n_tiles, m_step = n_pairs / n_tiles;
+  // pair c keeps filter tile c % n_tiles and the c / n_tiles-th of (n_pairs / n_tiles) equal, contiguous tile ranges
+  const int m_slots = n_pairs / n_tiles, m_slot = pair / n_tiles;
+  const int m_first = (int)((long long)m_slot * m_total / m_slots);
+  const int m_stop = (int)((long long)(m_slot + 1) * m_total / m_slots);
   const uint32_t acc_cols = (uint32_t)p.BN;
   const uint32_t want = 2u * acc_cols;
   const uint32_t tmem_cols = want <= 32 ? 32u : (want <= 64 ? 64u : (want <= 128 ? 128u : (want <= 256 ? 256u : 512u)));
@@ -883,17 +955,19 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int kb = 0; kb < nblk; ++kb)
             tma_load_2d_pair(bring_base + kb * b_half, &tmB, fb, kb * p.KC, my_n * p.BN + rank * bn_half);
         }
-        for (int m = m_first; m < m_total; m += m_step) {
-          const TileCoord tc = decode_tile(p, my_n, m);
+        for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p)) {
+          const TileCoord tc = it.coord(p);
           const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
           const int brow = tc.n0 + rank * bn_half;
           const int ntap = p.n_taps[tc.z];
           for (int cb = 0; cb < cin_blocks; ++cb) {
             mbar_wait(empty0 + 8u * s, ph ^ 1u);
+            if (!(p.dbg_knob & 16)) {   // (timing experiment: bit 4 = no activation loads at all)
             if (leader) mbar_expect_tx(full0 + 8u * s, 2u * (uint32_t)p.np * plane_tx);
             for (int q = 0; q < p.np; ++q)
               tma_load_4d_pair(smem_base + s * halo_bytes + q * plane_bytes, &tmA, full0 + 8u * s, cb * p.KC,
                                w0 + p.pl_dw[q], h0 + p.pl_dh[q], tc.n_img);
+            }
             if (++s == p.stages) {
               s = 0;
               ph ^= 1u;
@@ -914,8 +988,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
       } else
-      for (int m = m_first; m < m_total; m += m_step) {
-        const TileCoord tc = decode_tile(p, my_n, m);
+      for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p)) {
+        const TileCoord tc = it.coord(p);
         const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
         const int brow = tc.n0 + rank * bn_half;
         // the tile's K-blocks in (tap, channel block) order, kg of them per stage -- a stage may span taps
@@ -978,8 +1052,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int sb = 0;
         uint32_t phb = 0;
         if (p.bres) mbar_wait(fullB0, 0);
-        for (int m = m_first; m < m_total; m += m_step, ++lt) {
-          const TileCoord tc = decode_tile(p, my_n, m);
+        for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
+          const TileCoord tc = it.coord(p);
           const int buf = lt & 1;
           const uint32_t acc = tmem + buf * acc_cols;
           mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);
@@ -990,12 +1064,33 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t* tapA = s_tapA[tc.z];
           const uint32_t* tapB = s_tapB[tc.z];
           for (int cb = 0; cb < cin_blocks; ++cb) {
-            mbar_wait(full0 + 8u * s, ph);
+            if (!(p.dbg_knob & 16)) mbar_wait(full0 + 8u * s, ph);
             if (lt == 0 && cb == 0) dbg_mark(p, 2);
             // (descriptor start-address fields are 14 bits of (address >> 4) below the template's other
             //  fields: offsets are ADDED to the template, no carries out of the field at < 256 KB)
             const uint32_t abase = h_lo + ((smem_base + s * halo_bytes) >> 4);
             const uint32_t bres_base = d_lo + (bring_base >> 4) + (uint32_t)cb * (b_half >> 4);
+            if (p.bres && p.KC == 64 && !p.dbg_knob) {
+              // resident filter, 64-channel blocks: one flat tap loop, unrolled so that the table loads and
+              // register -> uniform-register moves of four taps overlap (a lone thread runs dependent
+              // uniform-datapath instructions at ~10 cycles each: ~400 cycles per tap when taken one by one)
+#pragma unroll 4
+              for (int t = 0; t < ntap; ++t) {
+                const uint32_t a_lo = abase + tapA[t];
+                const uint32_t bb = bres_base + tapB[t];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (bb + 2u * k), idesc, accum);
+                  accum = 1u;
+                }
+              }
+              umma_commit_pair(empty0 + 8u * s, 3);
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+              }
+              continue;
+            }
             uint32_t next_a = tapA[0], next_b = tapB[0];   // the table entry of tap t + 1 is fetched while tap t's MMAs issue
             for (int t0 = 0; t0 < ntap; t0 += p.tb) {
               uint32_t b_lo = 0;
@@ -1004,6 +1099,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 b_lo = d_lo + ((bring_base + sb * bslot_bytes) >> 4);
               }
               tc_fence_after();
+#pragma unroll 3
               for (int j = 0; j < p.tb; ++j, b_lo += b_half >> 4) {
                 const int t = t0 + j;
                 const uint32_t a_lo = abase + next_a;
@@ -1011,10 +1107,17 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 next_a = tapA[t + 1];
                 next_b = tapB[t + 1];
                 if (p.KC == 64) {
+                  if (!(p.dbg_knob & 32)) {   // (timing experiment: bit 5 = no MMAs at all)
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (bb + 2u * k), idesc, accum);
                     accum = 1u;
+                  }
+                  }
+                  if (p.dbg_knob & 8) {   // timing experiment: every MMA twice
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16_pair(acc, ((uint64_t)h_hi << 32) | (a_lo + 2u * k), ((uint64_t)d_hi << 32) | (bb + 2u * k), idesc, 1u);
                   }
                 } else {
 #pragma unroll
@@ -1043,8 +1146,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
         }
       } else
-      for (int m = m_first; m < m_total; m += m_step, ++lt) {
-        const TileCoord tc = decode_tile(p, my_n, m);
+      for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
+        const TileCoord tc = it.coord(p);
         const int buf = lt & 1;
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // both epilogues drained it
@@ -1058,6 +1161,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc_fence_after();
           uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
           uint32_t b_lo = a_lo + (b_off >> 4);
+#pragma unroll 4
           for (int j = 0; j < p.kg; ++j) {
             if (p.KC == 64) {
 #pragma unroll
@@ -1090,11 +1194,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // --------------------------------------------------------- epilogue (own 128 rows, 8 warps)
     float* tb = &s_tr[warp - 2][0];
     if (p.out_f32) {
-      if (p.stats != nullptr) pair_epilogue<true, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
-      else pair_epilogue<true, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
+      if (p.stats != nullptr) pair_epilogue<true, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      else pair_epilogue<true, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
     } else {
-      if (p.stats != nullptr) pair_epilogue<false, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
-      else pair_epilogue<false, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_step, m_total, warp, lane);
+      if (p.stats != nullptr) pair_epilogue<false, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      else pair_epilogue<false, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
     }
   }
 
@@ -1668,11 +1772,11 @@ static bool plan_planes(const int* taps, int n, int s, TapPlanes* tp) {
 static int g_smem_optin_done = 0;
 static int ensure_smem_optin() {
   if (g_smem_optin_done) return B200_OK;
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);   // + 8.4 KB static
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    e = cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wgrad_alltaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
   if (e == cudaSuccess)
@@ -1946,7 +2050,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   {
     // few CTAs (<= one per SM): nothing to co-schedule, so go deep; plenty: two stages, many CTAs/SM
     const long ctas = (long)max_tiles * n_classes * (filt_rows / p.BN);
-    const int budget = ctas <= 148 ? 220 * 1024 : (ctas <= 296 ? 110 * 1024 : 2 * stage_bytes);
+    const int budget = ctas <= 148 ? 212 * 1024 : (ctas <= 296 ? 106 * 1024 : 2 * stage_bytes);
     int st = budget / stage_bytes;
     if (st > kMaxStages) st = kMaxStages;
     if (st > max_nk) st = max_nk;
@@ -1954,7 +2058,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     p.stages = st;
   }
   if (st_override >= 2) p.stages = st_override;
-  if (!pair_mode && (p.stages < 2 || p.stages * stage_bytes > 222 * 1024))
+  if (!pair_mode && (p.stages < 2 || p.stages * stage_bytes > 214 * 1024))
     return set_error(B200_EINVAL, "conv_igemm: tile does not fit shared memory");
   p.out = out;
   p.out_ld = out_ld;
@@ -2110,7 +2214,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     for (int z = 0; z < n_classes; ++z) m_total += p.tiles_h[z] * p.tiles_w[z] * N;
     const int total_tiles = m_total * (filt_rows / p.BN);
     // resident CTAs: as many per SM as shared memory and TMEM (2 accumulator buffers each) allow
-    int per_sm = (int)((227 * 1024 - 4096) / (smem + 3 * 1024));
+    int per_sm = (int)((227 * 1024 - 4096) / (smem + 9 * 1024));   // + static shared memory (barriers, statistic slices)
     const int tmem_need = 2 * p.mt * p.BN <= 32 ? 32 : (2 * p.mt * p.BN <= 64 ? 64 : (2 * p.mt * p.BN <= 128 ? 128 : (2 * p.mt * p.BN <= 256 ? 256 : 512)));
     if (per_sm > 512 / tmem_need) per_sm = 512 / tmem_need;
     if (per_sm > 4) per_sm = 4;

@@ -79,14 +79,16 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, in
   __syncwarp();
 }
 
-// wait on a barrier whose arrivals come from the peer CTA of the cluster (remote mbarrier.arrive)
+// wait on a barrier whose arrivals come from the peer CTA of the cluster (remote mbarrier.arrive).
+// .relaxed: the acquire form invalidates the SM's whole L1 (CCTL.IVALL) on every success; the waiter only
+// orders tensor-memory accesses, which tcgen05.fence::after_thread_sync does.
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok)
@@ -320,6 +322,22 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // Flush n (multiple of 4) floats of shared memory into 16-byte aligned global memory.
 __device__ __forceinline__ void flush_add_v4(float* dst, const float* s_src, int n, int tid, int nthreads) {
   for (int i = tid * 4; i < n; i += nthreads * 4) red_add_v4(dst + i, s_src[i], s_src[i + 1], s_src[i + 2], s_src[i + 3]);
+}
+
+// the same for four partial arrays `stride` floats apart (one per epilogue warp), summed on the way out
+__device__ __forceinline__ void flush_add4_v4(float* dst, const float* s_src, int stride, int n, int tid, int nthreads) {
+  for (int i = tid * 4; i < n; i += nthreads * 4) {
+    float4 a = *reinterpret_cast<const float4*>(s_src + i);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(s_src + k * stride + i);
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    red_add_v4(dst + i, a.x, a.y, a.z, a.w);
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

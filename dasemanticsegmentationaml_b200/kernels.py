@@ -162,9 +162,11 @@ def load_tuned(path=None):
 load_tuned()
 
 
-def conv_key(n, hin, win, cin_pad, rows_pad, geom, f32, stats):
-    return "conv %d %d %d c%d r%d %s%s%s" % (n, hin, win, cin_pad, rows_pad, geom.key, " f32" if f32 else "",
-                                              " st" if stats else "")
+def conv_key(n, hin, win, cin_pad, rows_pad, geom, f32, stats, mask=False):
+    """(" mk": the launch also applies a LeakyReLU-backward mask and sums the bias gradient -- another epilogue,
+    tuned separately)"""
+    return "conv %d %d %d c%d r%d %s%s%s%s" % (n, hin, win, cin_pad, rows_pad, geom.key, " f32" if f32 else "",
+                                                " st" if stats else "", " mk" if mask else "")
 
 
 def wgrad_key(n, ho, wo, cout, cin, r, s, stride):
@@ -192,12 +194,13 @@ def conv_igemm(x, filt, out, geom, bias=None, act=0, slope=0.0, stats=None, bn_t
         assert mask.dtype == torch.bfloat16 and tuple(mask.shape[:3]) == (n, hout, wout) and mask.shape[3] >= rows_pad
     flops = 2.0 * geom.px_taps * n * (k_real or min(cin, cin_pad)) * (n_real or rows_pad)
     if bn_tile is None:
-        key = conv_key(n, hin, win, cin_pad, rows_pad, geom, out_f32, stats is not None and not stats_sum_only)
+        key = conv_key(n, hin, win, cin_pad, rows_pad, geom, out_f32, stats is not None and not stats_sum_only, mask is not None)
         bn_tile = TUNED.get(key, 0)
         if RECORD is not None:
             RECORD.append(("conv", key, dict(n=n, hin=hin, win=win, cin=cin, in_ld=in_ld, rows=rows_pad, cin_pad=cin_pad,
                                               n_slabs=n_slabs, geom=geom, f32=out_f32, stats=stats is not None,
-                                              bias=bias is not None, out_ld=out_ld, flops=flops)))
+                                              bias=bias is not None, out_ld=out_ld, flops=flops, mask=mask is not None,
+                                              sum_only=bool(stats_sum_only))))
     call("b200_conv_igemm",
          ptr(x), c_int(in_ld), c_int(0), c_int(cin), c_int(n), c_int(hin), c_int(win),
          ptr(filt), c_int(rows_pad), c_int(cin_pad), c_int(n_slabs),

@@ -37,19 +37,19 @@ def main():
     call("b200_debug_knob", K.c_int(knob))
     names = sys.argv[1:] or list(shapes())
     tunes = {}
-    for a in list(names):
+    for i, a in enumerate(list(names)):
         if "=" in a:
             n, t = a.split("=")
-            tunes[n] = int(t, 0)
-            names[names.index(a)] = n
+            tunes[i] = int(t, 0)
+            names[i] = n
     buf = torch.zeros(8 + 4 * NT, dtype=torch.int64, device=dev)
-    for name in names:
+    for idx, name in enumerate(names):
         xs, fs, geom, st = shapes()[name]
         x = torch.randn(xs, device=dev).to(BF)
         filt = (torch.randn(fs, device=dev) * 0.05).to(BF)
         out = torch.empty((xs[0], geom.Hout, geom.Wout, fs[0]), device=dev, dtype=BF)
         stats = torch.zeros(2, fs[0], device=dev) if st else None
-        tune = tunes.get(name)
+        tune = tunes.get(idx)
         if tune is None:
             key = K.conv_key(xs[0], xs[1], xs[2], fs[2], fs[0], geom, 0, st)
             tune = K.TUNED.get(key, 0)

@@ -76,7 +76,9 @@ def test_tuned_conv_entry(cuda_lib, key):
     if with_bias:
         ref = F.leaky_relu(ref + bias, 0.2)
     # their data gradients carry the producer's LeakyReLU backward + bias gradient
-    with_mask = c["dgrad"] and (r == 4 or (r == 1 and pad == 1)) and not c["stats"] and rows % 16 == 0 and not c.get("pairview")
+    # (a " mk" key IS that launch; older keys without the suffix are exercised both ways)
+    with_mask = (c.get("mask") or (c["dgrad"] and (r == 4 or (r == 1 and pad == 1)))) and not c["stats"] and rows % 16 == 0 \
+        and not c.get("pairview")
     mask = None
     if with_mask:
         mask = torch.randn(n, geom.Hout, geom.Wout, rows, device="cuda", generator=g).to(BF)

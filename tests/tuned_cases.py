@@ -2,7 +2,7 @@
 
 A key is what ``kernels.conv_key`` / ``kernels.wgrad_key`` produce:
 
-    conv  N Hin Win c<cin_pad> r<rows_pad> <f|d><R>x<S>s<stride>p<pad>[ f32][ st]
+    conv  N Hin Win c<cin_pad> r<rows_pad> <f|d><R>x<S>s<stride>p<pad>[ f32][ st][ mk]
     wgrad N Ho  Wo  co<Cout> ci<Cin> <R>x<S>s<stride>[p<pad>]
 
 (older wgrad keys carry no padding: 3x3 -> 1, 4x4 -> 1, 1x1 -> 0, except the point-wise convs of the
@@ -39,12 +39,12 @@ def parse_conv_key(key):
         fwd = m.group(5) == "f"
         return dict(n=n, hin=hin, win=win, cin_pad=64, rows=rows, dgrad=not fwd, r=4, s=4, stride=2, pad=1, f32=False,
                     stats=False, pairview=(2 * hin - 2, win - 2) if fwd else (2 * hin, 2 * win))
-    m = re.match(r"conv (\d+) (\d+) (\d+) c(\d+) r(\d+) ([fd])(\d+)x(\d+)s(\d+)p(\d+)( f32)?( st)?$", key)
+    m = re.match(r"conv (\d+) (\d+) (\d+) c(\d+) r(\d+) ([fd])(\d+)x(\d+)s(\d+)p(\d+)( f32)?( st)?( mk)?$", key)
     assert m, key
     n, hin, win, cin_pad, rows = (int(m.group(i)) for i in range(1, 6))
     return dict(n=n, hin=hin, win=win, cin_pad=cin_pad, rows=rows, dgrad=m.group(6) == "d", r=int(m.group(7)),
                 s=int(m.group(8)), stride=int(m.group(9)), pad=int(m.group(10)), f32=bool(m.group(11)),
-                stats=bool(m.group(12)))
+                stats=bool(m.group(12)), mask=bool(m.group(13)))
 
 
 def parse_wgrad_key(key):
