@@ -2118,7 +2118,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
       if (tb == 0) tb = 3;   // (measured: one barrier round trip per 3 taps beats per-tap slots at every BN)
       tb = fix_tb(tb);
       const size_t bres_bytes = (size_t)n_slabs * cin_blocks * b_half;
-      p.bres = (bres_bytes <= 72 * 1024 && bres_bytes + 2 * halo_slot <= dyn) ? 1 : 0;
+      // (resident whenever it fits beside three activation slots: the resident path has the lean flat tap loop
+      //  and no filter-ring round trips -- the data gradient of a 64 <- 128 4x4/s2 layer keeps all 16 slabs, 128 KB)
+      p.bres = (bres_bytes <= 136 * 1024 && bres_bytes + 3 * halo_slot <= dyn) ? 1 : 0;
       int sa = st_override >= 2 ? st_override : 3;
       int sb = 1;
       size_t bring = bres_bytes;
