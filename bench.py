@@ -138,12 +138,17 @@ def run_reference(args):
     batch = _cpu_batch(args.workload, args.batch)
     rate, ms, threads = cpu_da_step_rate(args.workload, batch, steps, warmup)
     h, w = SHAPES.get(args.workload, (H, W))
-    sample = "%d-image %s step(s) of the oracle port (fp32, torch CPU), %d warm-up" % (batch, args.workload, warmup)
+    sample = ("%d-image %s step(s) of the oracle port (fp32, torch CPU), %d warm-up%s"
+              % (batch, args.workload, warmup,
+                 "" if batch == args.batch else "; a bounded sample of the %d-image step of `config` (the host's free memory / the "
+                 "time limit): the per-image rate of the port grows a few per cent with the batch" % args.batch))
     line = {
         "impl": "reference", "metric": _metric(args.workload),
         "value": rate, "unit": "img/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": batch, "height": h, "width": w, "classes": NCLS},
+        # the GPU arm's workload; `sample_batch` is what one timed CPU step actually processed
+        "config": {"workload": WORKLOADS[args.workload], "batch_per_gpu": args.batch, "height": h, "width": w, "classes": NCLS,
+                   "sample_batch": batch},
         "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
