@@ -642,19 +642,23 @@ def conv_traffic(workload):
     return None, None
 
 
-_REAL_STDOUT = sys.stdout
+_REAL_FD = None
 
 
 def emit(line):
     """The ONE JSON line of the contract goes to the real stdout; everything else any library or
-    module prints while the bench runs (e.g. STDCNet813's 'use pretrain model' notice, kept for parity
-    with stdcnet.py:139) is routed to stderr."""
-    _REAL_STDOUT.write(json.dumps(line) + "\n")
-    _REAL_STDOUT.flush()
+    module prints while the bench runs (STDCNet813's 'use pretrain model' notice, kept for parity
+    with stdcnet.py:139; NCCL's own "NCCL version ..." banner, written by the C library straight to
+    file descriptor 1) is routed to stderr."""
+    os.write(_REAL_FD, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    global _REAL_FD
     args = parse()
+    sys.stdout.flush()
+    _REAL_FD = os.dup(1)      # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)             # ... and point fd 1 at stderr for everything else (C libraries included)
     sys.stdout = sys.stderr
     if args.impl == "reference":
         run_reference(args)
