@@ -219,6 +219,7 @@ def val(model, batches, n_classes=19, device=None):
         hist = torch.zeros(n_classes * n_classes, dtype=torch.int64, device=device)
     ratios = [float(c) / float(t) for c, t in zip(torch.cat(counts).tolist(), totals)] if counts else []
     psum = torch.tensor([float(np.sum(ratios)) if ratios else 0.0, float(len(ratios))], dtype=torch.float64, device=device)
+    val.last_local_hist = hist.clone() if _world() > 1 else hist   # this rank's shard, before the sum over ranks
     if _world() > 1:
         dist.all_reduce(hist)
         dist.all_reduce(psum)
