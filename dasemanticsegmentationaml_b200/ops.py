@@ -377,6 +377,7 @@ class _WgradScratch(object):
     def flush(self):
         """Permute the scratch accumulators gathered so far into their gradients (one launch).  Also
         called by REDUCER.hook(): a gradient span must be final before it is exchanged."""
+        SIDE.join()    # weight gradients still running on the side stream
         if not self.pending:
             return
         schunk, dchunk = self.pending[0][0], self.pending[0][1]
@@ -392,6 +393,7 @@ class _WgradScratch(object):
         self.pending = []
 
     def end(self, ok=True):
+        SIDE.join()
         if ok:
             self.flush()
             self.stable[self.tag] = bool(self.flushed) and self.flushed == self.seen.get(self.tag)
@@ -404,10 +406,53 @@ class _WgradScratch(object):
 WSCRATCH = _WgradScratch()
 
 
+class _SideStream(object):
+    """Weight gradients of SMALL layers run on a second stream, concurrently with the data gradient of the
+    same layer (both only read dz; nothing reads dW before the end of the module backward).  At 1/16 and 1/32
+    resolution either kernel is a few dozen CTAs with a 10-20 us latency chain, so the pair fits the GPU side
+    by side; large layers fill every SM on their own and stay in line (overlap bought nothing there).
+    Inside a CUDA-graph capture the fork / join become graph edges.  Tensors the side kernels touch are
+    kept alive until the join (the caching allocator would hand a freed block to the main stream at once)."""
+
+    def __init__(self):
+        self.streams = {}
+        self.keep = []
+        self.dirty = None
+
+    def run(self, device, keep, fn):
+        key = device.index or 0
+        side = self.streams.get(key)
+        if side is None:
+            side = self.streams[key] = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            fn()
+        self.keep.append(keep)
+        self.dirty = (device, side)
+
+    def join(self):
+        if self.dirty is not None:
+            device, side = self.dirty
+            torch.cuda.current_stream(device).wait_stream(side)
+            self.dirty = None
+            self.keep = []
+
+
+SIDE = _SideStream()
+# layers with at most this many output pixels (N*Ho*Wo) send their weight gradient to the side stream (0 = off).
+# Measured on the DA step (N = 8, 512x1024, graph replay): 0 -> 11.89 ms, 16384 -> 11.83, 65536 -> 11.70,
+# 262144 and beyond -> 11.68-11.71 (the large layers fill the GPU alone: nothing more to overlap).
+WGRAD_SIDE_MAX_PIXELS = 65536
+
+
 def conv_wgrad(dz, x, weight, stride, pad):
     cout, cin, r, s = weight.shape
     dw = zeros_f32((cout, cin, r, s), dz.device)
-    K.conv_wgrad(dz, x, dw, r, s, stride, pad, scratch=WSCRATCH.request(dw, cout, cin, r * s))
+    scratch = WSCRATCH.request(dw, cout, cin, r * s)
+    if WSCRATCH.depth > 0 and dz.shape[0] * dz.shape[1] * dz.shape[2] <= WGRAD_SIDE_MAX_PIXELS:
+        SIDE.run(dz.device, (dz, x, dw, scratch), lambda: K.conv_wgrad(dz, x, dw, r, s, stride, pad, scratch=scratch))
+    else:
+        K.conv_wgrad(dz, x, dw, r, s, stride, pad, scratch=scratch)
     return dw
 
 
