@@ -13,6 +13,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include <stdlib.h>
+#include <string.h>
+#include <mutex>
 
 #include "igemm.cuh"
 #include "ptx.cuh"
@@ -1648,6 +1650,44 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Tensor-map cache for eager callers: cuTensorMapEncodeTiled costs a few microseconds of host time per call
+// and a step re-creates the same few hundred maps (same buffers from the caching allocator, same shapes)
+// every iteration.  Direct-mapped on a hash of ALL encode arguments (base address included); a map is a
+// pure function of those, so a hit can never be stale.  (Graph replays never come here.)
+struct MapKey {
+  uint64_t v[10];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapSlot {
+  MapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int kMapSlots = 1024;
+static MapSlot g_map_cache[kMapSlots];
+static std::mutex g_map_mutex;
+
+static bool map_cache_get(const MapKey& k, CUtensorMap* m) {
+  uint64_t h = 1469598103934665603ull;
+  for (int i = 0; i < 10; ++i) h = (h ^ k.v[i]) * 1099511628211ull;
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  const MapSlot& s = g_map_cache[h % kMapSlots];
+  if (s.used && s.key == k) {
+    *m = s.map;
+    return true;
+  }
+  return false;
+}
+static void map_cache_put(const MapKey& k, const CUtensorMap& m) {
+  uint64_t h = 1469598103934665603ull;
+  for (int i = 0; i < 10; ++i) h = (h ^ k.v[i]) * 1099511628211ull;
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  MapSlot& s = g_map_cache[h % kMapSlots];
+  s.key = k;
+  s.map = m;
+  s.used = true;
+}
+
 // NHWC bf16 activation view: channels [coff, coff+C) of a tensor whose pixels are `ld` apart.
 static int make_act_map(CUtensorMap* m, const void* base, int coff, int C, int ld, int N, int H,
                         int W, int box_c, int box_w, int box_h, int stride, int swizzle_bytes) {
@@ -1661,10 +1701,15 @@ static int make_act_map(CUtensorMap* m, const void* base, int coff, int C, int l
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   void* addr = const_cast<void*>(static_cast<const void*>(static_cast<const __nv_bfloat16*>(base) + coff));
+  const MapKey key = {{(uint64_t)reinterpret_cast<uintptr_t>(addr), (uint64_t)C, (uint64_t)ld, (uint64_t)N, (uint64_t)H, (uint64_t)W,
+                       ((uint64_t)box_c << 32) | (uint32_t)box_w, ((uint64_t)box_h << 32) | (uint32_t)stride,
+                       (uint64_t)swizzle_bytes, 4u}};
+  if (map_cache_get(key, m)) return B200_OK;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+  map_cache_put(key, *m);
   return B200_OK;
 }
 
@@ -1679,10 +1724,14 @@ static int make_filter_map(CUtensorMap* m, const void* base, int rows, int ktot,
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+  const MapKey key = {{(uint64_t)reinterpret_cast<uintptr_t>(base), (uint64_t)rows, (uint64_t)ktot, (uint64_t)box_k,
+                       (uint64_t)box_rows, (uint64_t)swizzle_bytes, 0u, 0u, 0u, 2u}};
+  if (map_cache_get(key, m)) return B200_OK;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled(filter) failed: %d", (int)r);
+  map_cache_put(key, *m);
   return B200_OK;
 }
 

@@ -159,6 +159,13 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
                     float* __restrict__ running_var, float momentum, float eps, int training,
                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int finalize) {
   const Slot t = slot_of(C);
+  const int64_t first = (int64_t)blockIdx.x * t.py * UNR;
+  uint4 cur[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    const int64_t p = first + u * t.py + t.ty;
+    cur[u] = p < npix ? ldraw(x + p * x_ld + t.g * 8) : make_uint4(0u, 0u, 0u, 0u);
+  }
   float sc[8], sh[8];
   if (finalize) {
     // per-channel vectors of this thread's 8 channels with 16-byte loads (the coefficient set-up is a
@@ -223,22 +230,29 @@ bn_act_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
     }
   }
   const int64_t step = (int64_t)gridDim.x * t.py * UNR;
-  for (int64_t base = (int64_t)blockIdx.x * t.py * UNR; base < npix; base += step) {
-    float v[UNR][8];
+  for (int64_t base = first; base < npix; base += step) {
+    // the next batch's loads are issued before this batch is touched (and the first batch's before the
+    // coefficient chain above: on a small layer that chain and the first loads ARE the kernel)
+    uint4 nxt[UNR];
+    const int64_t nb = base + step;
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int64_t p = base + u * t.py + t.ty;
-      if (p < npix) load8(x + p * x_ld + t.g * 8, v[u]);
+      const int64_t p = nb + u * t.py + t.ty;
+      nxt[u] = p < npix ? ldraw(x + p * x_ld + t.g * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int64_t p = base + u * t.py + t.ty;
       if (p < npix) {
+        float v[8];
+        unpack8(cur[u], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[u][j] = act_fwd(v[u][j] * sc[j] + sh[j], act, slope);
-        store8(y + p * y_ld + t.g * 8, v[u]);
+        for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j] * sc[j] + sh[j], act, slope);
+        store8(y + p * y_ld + t.g * 8, v);
       }
     }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) cur[u] = nxt[u];
   }
 }
 
