@@ -79,14 +79,25 @@ __device__ __forceinline__ void apply_mask16(float (&v)[16], const __nv_bfloat16
     const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(m)), u1 = __ldg(reinterpret_cast<const uint4*>(m) + 1);
     w[0] = u0.x; w[1] = u0.y; w[2] = u0.z; w[3] = u0.w; w[4] = u1.x; w[5] = u1.y; w[6] = u1.z; w[7] = u1.w;
   }
+  // factor = a > 0 ? 1 : slope without predicated selects (sixteen select-on-predicate sequences end up
+  // serialised on ONE predicate register by ptxas): with s = [a > 0] as 1.0f / 0.0f (one FSET) it is
+  // max(s, slope) for a slope in [0, 1] (every LeakyReLU / ReLU of the path), else s + (1 - s) * slope --
+  // both exact for both values of s
+  if (slope >= 0.f && slope <= 1.f) {
 #pragma unroll
-  // factor = a > 0 ? 1 : slope as s + (1 - s) * slope with s = [a > 0] as 1.0f / 0.0f (exact for both values of
-  // s): sixteen select-on-predicate sequences end up serialised on ONE predicate register by ptxas
-  for (int k = 0; k < 8; ++k) {
-    const float2 a = unpack_bf16(w[k]);
-    const float sx = a.x > 0.f ? 1.f : 0.f, sy = a.y > 0.f ? 1.f : 0.f;
-    v[2 * k] *= fmaf(1.f - sx, slope, sx);
-    v[2 * k + 1] *= fmaf(1.f - sy, slope, sy);
+    for (int k = 0; k < 8; ++k) {
+      const float2 a = unpack_bf16(w[k]);
+      v[2 * k] *= fmaxf(a.x > 0.f ? 1.f : 0.f, slope);
+      v[2 * k + 1] *= fmaxf(a.y > 0.f ? 1.f : 0.f, slope);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 a = unpack_bf16(w[k]);
+      const float sx = a.x > 0.f ? 1.f : 0.f, sy = a.y > 0.f ? 1.f : 0.f;
+      v[2 * k] *= fmaf(1.f - sx, slope, sx);
+      v[2 * k + 1] *= fmaf(1.f - sy, slope, sy);
+    }
   }
 }
 
@@ -634,104 +645,156 @@ __device__ __forceinline__ void dbg_mark(const ConvParams& p, int slot) {
 }
 
 // ------------------------------------------------------------------ batched epilogue
-// 32 accumulator columns of one output pixel per thread: ONE tcgen05.ld + wait, then bias /
-// activation (branch-free: v > 0 ? v : v * ns with ns = 1 none, 0 ReLU, slope LeakyReLU) / LeakyReLU
-// backward mask / bf16 packing / 256-bit stores.  The BatchNorm column sums go through a per-warp
-// shared-memory transpose instead of shuffles: every lane writes its pixel's 16 values as four
-// 16-byte stores into a [32 rows][16 cols (+4 pad)] tile, then lane (col, half) adds 16 rows of one
-// column (conflict-free both ways) -- ~55 instructions per 16 columns against ~250 for the two
-// 16-value butterflies, which made the epilogue (not the MMAs) the longest phase of a tile.
-constexpr int kTrStride = 20;   // floats per row of the transpose tile
+// 32 accumulator columns of one output pixel per thread (loaded from TMEM by the caller): bias /
+// activation (skipped altogether for the BatchNorm'd layers, whose raw accumulator is the output) /
+// LeakyReLU-backward mask / bf16 packing, then every lane parks its pixel's 32 values -- the 16 bf16 PAIRS
+// it has just packed -- in the warp's staging tile: 32 rows of 64 bytes, dense, 16-byte chunks XOR-swizzled
+// with (row >> 1) & 3.  That is the image TMA's 64-byte swizzle expects, and it is conflict-free both for
+// the four 16-byte row writes and for the column reads below.  From the tile
+//   * ONE elected lane sends the 32 pixels x 32 channels to global memory as a TMA store (box = 32 channels
+//     x (32 pixels of the warp's patch rows), clipped to the class's extent by the tensor map).  The
+//     register path -- 32 lanes x 32 B to 32 different lines, twice per batch -- kept the LSU busy for
+//     ~30 % of an epilogue-bound launch (measured by compiling the stores out: the 64->128 1x1 layer 42.8 ->
+//     30.1 us) and stalled the shared-memory traffic queued behind it (mio throttle: 20 % of the samples);
+//   * BatchNorm column sums: lane (pair, half) walks 16 rows of one column pair and accumulates sum and sum
+//     of squares of BOTH columns with packed fp32 arithmetic (FADD2 / FFMA2, two independent chains each):
+//     ~90 instructions per 32 columns against ~200 for two 16-column fp32 transposes with scalar adds.
+// Rows outside the image are zeroed (statistics) only in tiles that have any (warp-uniform test).
+constexpr int kTrWords = 512;   // 32-bit words of a warp's staging tile (32 rows x 64 bytes)
+
+struct OutMaps {
+  CUtensorMap m[kMaxClasses];
+};
+struct StoreCoord {
+  const CUtensorMap* map;   // the class's output map (nullptr: register stores)
+  int c, w, h, n;           // channel (relative to the output view), pixel of the warp's first row, image
+};
+
+__device__ __forceinline__ int stage_word(int row, int word) {
+  return row * 16 + ((((word >> 2) ^ (row >> 1)) & 3) << 2) + (word & 3);
+}
 
 template <bool F32, bool STATS>
-__device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t taddr, bool valid, size_t obase,
-                                                 size_t pix, int gcol, float ns, float* tb, float (&r_sum)[2],
-                                                 float (&r_sq)[2], int lane, bool mark = false) {
-  uint32_t r[32];
-  if (p.dbg_knob & 2) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = (uint32_t)lane;
-  } else {
-    tmem_ld32(taddr, r);
-    tmem_ld_wait();
-  }
-  if (mark) dbg_mark(p, 4);
-  if (p.dbg_knob & 1) valid = false;
+__device__ __forceinline__ void epilogue_batch32(const ConvParams& p, const uint32_t (&r)[32], bool valid, bool all_valid,
+                                                 size_t obase, size_t pix, int gcol, float ns, float* tb,
+                                                 const StoreCoord& sc, uint64_t& a_sum, uint64_t& a_sq, int lane) {
+  const bool plain = p.bias == nullptr && p.act == 0;
+  uint32_t pk[16];
 #pragma unroll
   for (int hv = 0; hv < 2; ++hv) {
     const int cc = 16 * hv;
     float v[16];
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol + cc);
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float4 b = __ldg(b4 + jj);
-        v[4 * jj] = __uint_as_float(r[cc + 4 * jj]) + b.x;
-        v[4 * jj + 1] = __uint_as_float(r[cc + 4 * jj + 1]) + b.y;
-        v[4 * jj + 2] = __uint_as_float(r[cc + 4 * jj + 2]) + b.z;
-        v[4 * jj + 3] = __uint_as_float(r[cc + 4 * jj + 3]) + b.w;
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[cc + j]);
+    if (!plain) {
+      if (p.bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol + cc);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 b = __ldg(b4 + jj);
+          v[4 * jj] += b.x;
+          v[4 * jj + 1] += b.y;
+          v[4 * jj + 2] += b.z;
+          v[4 * jj + 3] += b.w;
+        }
       }
-    } else {
+      // act(v) = max(v, 0) + ns * min(v, 0): no predicates (see apply_mask16)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[cc + j]);
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(ns, fminf(v[j], 0.f), fmaxf(v[j], 0.f));
     }
-    // act(v) = max(v, 0) + ns * min(v, 0): no predicates (see apply_mask16)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaf(ns, fminf(v[j], 0.f), fmaxf(v[j], 0.f));
     if (p.mask != nullptr && valid)
       apply_mask16(v, static_cast<const __nv_bfloat16*>(p.mask) + pix * p.mask_ld + gcol + cc, p.mask_slope, p.wide);
-    float x[16];
     if (F32) {
       if (valid) store16(p, obase + cc, v);
+      if (STATS) {
+        // fp32 outputs (no product layer combines them with statistics): one 16-column fp32 transpose per half
+        // (rows of 16 floats: bank conflicts accepted); lane (col, half) keeps column cc + col in the low
+        // (hv = 0) / high (hv = 1) word of its accumulators
+        __syncwarp();
+        float4* w4 = reinterpret_cast<float4*>(tb + lane * 16);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = valid ? v[j] : 0.f;
+        for (int jj = 0; jj < 4; ++jj)
+          w4[jj] = valid ? make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        const int col = lane & 15, hf = lane >> 4;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t = tb[(hf * 16 + i) * 16 + col];
+          s1 += t;
+          s2 = fmaf(t, t, s2);
+        }
+        float2 cs = f32x2_unpack(a_sum), cq = f32x2_unpack(a_sq);
+        if (hv == 0) {
+          cs.x += s1;
+          cq.x += s2;
+        } else {
+          cs.y += s1;
+          cq.y += s2;
+        }
+        a_sum = f32x2_pack(cs.x, cs.y);
+        a_sq = f32x2_pack(cq.x, cq.y);
+      }
     } else {
-      uint32_t pk[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-      if (mark && hv == 0) dbg_mark(p, 5);
-      if (valid) {
+      for (int j = 0; j < 8; ++j) pk[8 * hv + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      if (sc.map == nullptr && valid && !(p.dbg_knob & 1)) {   // register stores ((timing experiment: bit 0 = none))
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + obase + cc;
         if (p.wide) {
-          st_global_v8(o, pk);
-        } else {
-          reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-      if (STATS) {
-        // statistics of the values as stored (bf16-rounded): mean / var describe the tensor the
-        // normalisation pass will read
+          uint32_t q8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          x[2 * j] = valid ? __uint_as_float(pk[j] << 16) : 0.f;
-          x[2 * j + 1] = valid ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
+          for (int j = 0; j < 8; ++j) q8[j] = pk[8 * hv + j];
+          st_global_v8(o, q8);
+        } else {
+          reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[8 * hv], pk[8 * hv + 1], pk[8 * hv + 2], pk[8 * hv + 3]);
+          reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[8 * hv + 4], pk[8 * hv + 5], pk[8 * hv + 6], pk[8 * hv + 7]);
         }
       }
     }
-    if (mark && hv == 0) dbg_mark(p, 6);
-    if (STATS && !(p.dbg_knob & 4)) {
-      __syncwarp();   // the previous chunk's column reads are done
-      float4* w4 = reinterpret_cast<float4*>(tb + lane * kTrStride);
+  }
+  if (!F32 && (STATS || sc.map != nullptr)) {
+    // statistics of the values as stored (bf16-rounded): mean / var describe the tensor the normalisation
+    // pass will read
+    if (STATS && !all_valid) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) w4[jj] = make_float4(x[4 * jj], x[4 * jj + 1], x[4 * jj + 2], x[4 * jj + 3]);
-      __syncwarp();
-      const int col = lane & 15, hf = lane >> 4;
-      float s1 = 0.f, s2 = 0.f;
+      for (int j = 0; j < 16; ++j) pk[j] = valid ? pk[j] : 0u;
+    }
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tb);
+    if (sc.map != nullptr && lane == 0) bulk_wait_read_all();   // the previous batch's TMA store has read the tile
+    __syncwarp();   // ... and its column reads are done
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      *reinterpret_cast<uint4*>(tw + lane * 16 + ((jj ^ sw) << 2)) = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+    if (sc.map != nullptr) fence_proxy_async_smem();
+    __syncwarp();
+    if (sc.map != nullptr && lane == 0 && !(p.dbg_knob & 1)) {
+      tma_store_4d(sc.map, smem_u32(tw), sc.c, sc.w, sc.h, sc.n);
+      bulk_commit_group();
+    }
+    if (STATS) {
+      const int cp = lane & 15, hf = lane >> 4;
+      uint64_t s1a = 0ull, s1b = 0ull, s2a = 0ull, s2b = 0ull;   // (+0.f, +0.f)
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        // the two half-warps walk their 16 rows 4 apart, which puts them on disjoint banks
-        const float t = tb[(hf * 16 + ((i + 4 * hf) & 15)) * kTrStride + col];
-        s1 += t;
-        s2 = fmaf(t, t, s2);
+        // the half-warps read rows of opposite parity: the 16 words of a 64-byte row cover half the banks
+        const int row = hf * 16 + ((i + hf) & 15);
+        const uint32_t w = tw[stage_word(row, cp)];
+        const uint64_t t = f32x2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+        if (i & 1) {
+          s1b = f32x2_add(s1b, t);
+          s2b = f32x2_fma(t, t, s2b);
+        } else {
+          s1a = f32x2_add(s1a, t);
+          s2a = f32x2_fma(t, t, s2a);
+        }
       }
-      // lane (col, hf) keeps its 16-row partial of column gcol + cc + col in REGISTERS across the tiles of
-      // this CTA (fp32 atomicAdd on shared memory is a compare-and-swap loop: with eight warps on the same
+      // lane (pair, half) keeps its 16-row partials of columns gcol + 2 pair, + 1 in REGISTERS across the tiles
+      // of this CTA (fp32 atomicAdd on shared memory is a compare-and-swap loop: with eight warps on the same
       // columns it was most of the epilogue); pair_epilogue folds them once per filter tile
-      r_sum[hv] += s1;
-      r_sq[hv] += s2;
+      a_sum = f32x2_add(a_sum, f32x2_add(s1a, s1b));
+      a_sq = f32x2_add(a_sq, f32x2_add(s2a, s2b));
     }
-    if (mark && hv == 0) dbg_mark(p, 7);
   }
 }
 
@@ -742,9 +805,10 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, uint32_t t
 // HALF of the filter tile (BN/2 rows) through shared memory -- the tensor cores read the other half
 // from the peer SM -- so per FLOP a CTA pulls (128 + BN/2) rows of operands instead of (128 + BN):
 // the L2->SM fill that bounds the big layers drops by a third at BN = 256.
-// Persistent like conv_igemm_persistent_kernel: pair c keeps filter tile c % n_tiles, TWO TMEM
-// accumulators (tfull / tempty) overlap a tile's epilogue with the next tile's MMAs; the epilogue
-// reads TMEM in 32-column batches (one tcgen05.wait::ld per 32 columns).
+// Persistent like conv_igemm_persistent_kernel: pair c keeps filter tile c % n_tiles, FOUR TMEM
+// accumulators (two at BN = 256; tfull / tempty) let the MMAs run up to three tiles ahead of the epilogue; the
+// epilogue reads TMEM in 32-column batches, the load of batch b + 1 in flight under the arithmetic of batch b,
+// and hands a buffer back as soon as its last batch is in registers.
 //   leader (even) CTA : arms full[s] with the bytes of BOTH CTAs, issues every MMA, multicasts the
 //                       commits (stage free / accumulator full) to both CTAs
 //   both CTAs         : TMA producer (own A rows, own half of B, signalling the leader's full[s]),
@@ -754,54 +818,71 @@ struct PairBarriers {
   uint64_t empty[kMaxStages];
   uint64_t fullB[kMaxStages];    // halo mode: the filter ring (full / empty are the activation-halo ring)
   uint64_t emptyB[kMaxStages];
-  uint64_t tfull[2];
-  uint64_t tempty[2];
+  uint64_t tfull[4];
+  uint64_t tempty[4];
   uint32_t tmem_base;
 };
 
 constexpr int kPairThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
+// log2 of the number of TMEM accumulators: four while they fit 512 columns (BN <= 128) -- with small K a
+// tile's MMAs are issued in a fraction of the time the accumulator takes to come back through the epilogue, and
+// with two buffers the tile period was (MMA latency + epilogue + two barrier round trips) / 2
+__device__ __forceinline__ int pair_acc_log2(int bn) { return bn <= 128 ? 2 : 1; }
+
 template <bool F32, bool STATS>
-__device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers& bars, float (*s_stats)[256], float* tb,
-                                              uint32_t tmem, int rank, int my_n, int m_first, int m_stop,
+__device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps& om, PairBarriers& bars, float (*s_stats)[256],
+                                              float* tb, uint32_t tmem, int rank, int my_n, int m_first, int m_stop,
                                               int warp, int lane) {
   const int q = warp & 3;              // TMEM lane quarter this warp may read
-  const int half = (warp - 2) >> 2;    // which 32-column batches: b % 2 == half
+  const int half = (warp - 2) >> 2;    // warp group: 32-column batches b % 2 == half ...
+  const bool alt = p.BN == 32;         // ... or, when a tile has ONE batch, the tiles lt % 2 == half
   const int row = q * 32 + lane;
   const int hl = row / p.tw, wl = row - hl * p.tw;
   const int t = threadIdx.x - 64;      // 0..255 among the epilogue threads
   const float ns = p.act == 0 ? 1.f : (p.act == 1 ? 0.f : p.slope);
   const uint32_t acc_cols = (uint32_t)p.BN;
-  // per-lane statistics partials: [32-column batch of this warp][16-column half]
-  float r_sum[4][2], r_sq[4][2];
+  const int nl = pair_acc_log2(p.BN);
+  const int c0 = alt ? 0 : 32 * half;  // first column of this warp's batches (then every 64th)
+  // TMA stores: the warp's 32 accumulator rows are box_h patch rows of box_w pixels, starting at (hs, ws)
+  const bool tma_out = !F32 && p.tma_out;
+  const int hs = (q * 32) / p.tw, ws = (q * 32) - hs * p.tw;
+  // per-lane statistics partials, one packed pair (two columns) per 32-column batch of this warp
+  uint64_t a_sum[4], a_sq[4];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) r_sum[b][0] = r_sum[b][1] = r_sq[b][0] = r_sq[b][1] = 0.f;
+  for (int b = 0; b < 4; ++b) a_sum[b] = a_sq[b] = 0ull;
   // registers -> the CTA's shared column sums (once per filter tile), without atomics: every warp parks its
-  // partials in its OWN transpose tile ([batch][half][column][sum, sumsq]), then thread `col` adds the four
-  // warps (one per TMEM lane quarter) that cover its column
+  // partials in its OWN tile ([batch][column][sum, sumsq]), then thread `col` adds the warps that cover its column
   auto fold_stats = [&]() {
+    if (tma_out && lane == 0) bulk_wait_read_all();   // the staging tile is about to be reused
     __syncwarp();
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      if (32 * half + 64 * b < p.BN) {
-#pragma unroll
-        for (int hv = 0; hv < 2; ++hv) {
-          const float s1 = r_sum[b][hv] + __shfl_xor_sync(0xffffffffu, r_sum[b][hv], 16);
-          const float s2 = r_sq[b][hv] + __shfl_xor_sync(0xffffffffu, r_sq[b][hv], 16);
-          if (lane < 16) *reinterpret_cast<float2*>(tb + ((b * 2 + hv) * 16 + lane) * 2) = make_float2(s1, s2);
-          r_sum[b][hv] = r_sq[b][hv] = 0.f;
+      if (c0 + 64 * b < p.BN) {
+        float2 s = f32x2_unpack(a_sum[b]), sq = f32x2_unpack(a_sq[b]);
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, 16);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
+        sq.x += __shfl_xor_sync(0xffffffffu, sq.x, 16);
+        sq.y += __shfl_xor_sync(0xffffffffu, sq.y, 16);
+        if (lane < 16) {
+          if (F32) {   // lane = column, low word = columns 0..15, high word = columns 16..31 of the batch
+            *reinterpret_cast<float2*>(tb + (b * 32 + lane) * 2) = make_float2(s.x, sq.x);
+            *reinterpret_cast<float2*>(tb + (b * 32 + 16 + lane) * 2) = make_float2(s.y, sq.y);
+          } else {     // lane = column pair
+            *reinterpret_cast<float4*>(tb + (b * 32 + 2 * lane) * 2) = make_float4(s.x, sq.x, s.y, sq.y);
+          }
         }
+        a_sum[b] = a_sq[b] = 0ull;
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float* tiles = tb - (warp - 2) * (32 * kTrStride);
+    const float* tiles = tb - (warp - 2) * kTrWords;
     for (int col = t; col < p.BN; col += 256) {
-      const int cb = col >> 6, chalf = (col >> 5) & 1, chv = (col >> 4) & 1;
+      const int cb = col >> 5;
+      const int w0 = alt ? 0 : (cb & 1) * 4, nw = alt ? 8 : 4, slot = alt ? 0 : cb >> 1;
       float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const float2 v = *reinterpret_cast<const float2*>(tiles + (chalf * 4 + qq) * (32 * kTrStride) +
-                                                           ((cb * 2 + chv) * 16 + (col & 15)) * 2);
+      for (int qq = 0; qq < nw; ++qq) {
+        const float2 v = *reinterpret_cast<const float2*>(tiles + (w0 + qq) * kTrWords + (slot * 32 + (col & 31)) * 2);
         a1 += v.x;
         a2 += v.y;
       }
@@ -828,28 +909,74 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
       }
       cur_n0 = tc.n0;
     }
-    const int buf = lt & 1;
+    if (alt && (lt & 1) != half) continue;   // the other warp group's tile
+    const int buf = lt & ((1 << nl) - 1);
     const uint32_t acc = tmem + buf * acc_cols + ((uint32_t)(q * 32) << 16);
-    mbar_wait_warp(smem_u32(&bars.tfull[buf]), (lt >> 1) & 1, lane);
+    const bool mark = p.dbg != nullptr && warp == 2 && lane == 0 && rank == 0 && lt < kDbgTiles;
+    mbar_wait_warp(smem_u32(&bars.tfull[buf]), (lt >> nl) & 1, lane);
     tc_fence_after();
-    if (warp == 2 && lane == 0 && rank == 0 && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 2);
+    if (mark) dbg_mark(p, 8 + 4 * lt + 2);
     const int h = tc.h0 + rank * p.th + hl, w = tc.w0 + wl;
     const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+    const bool all_valid = __all_sync(0xffffffffu, valid);
     const size_t pix =
         ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
     const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
+    StoreCoord sc;
+    sc.map = tma_out ? &om.m[z] : nullptr;
+    sc.w = tc.w0 + ws;
+    sc.h = tc.h0 + rank * p.th + hs;
+    sc.n = tc.n_img;
+    // one ROLLED loop over the warp's batches (the body is ~350 instructions: four unrolled copies per
+    // output type made the tile loop stream ~25 KB of code through the 6 KB L0 instruction cache of a
+    // scheduler that has two warps to hide the misses with); the next batch's TMEM load is in flight under
+    // this batch's arithmetic, and the statistics accumulators are picked by select, not by index
+    const int nb = alt ? 1 : (p.BN >> 6);
+#ifdef B200_EPI_PREFETCH
+    uint32_t r[32], rn[32];
+    tmem_ld32(acc + c0, r);
+#else
+    uint32_t r[32];
+#endif
+#pragma unroll 1
+    for (int b = 0; b < nb; ++b) {
+      const int c = c0 + 64 * b;
+#ifndef B200_EPI_PREFETCH
+      tmem_ld32(acc + c, r);
+#endif
+      tmem_ld_wait32(r);
+      if (b + 1 < nb) {
+#ifdef B200_EPI_PREFETCH
+        tmem_ld32(acc + c + 64, rn);
+#endif
+      } else {
+        // the warp's last batch is in registers: hand the accumulator back to the leader's MMA warp now
+        // (count = the warps that read a buffer, in both CTAs)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(smem_u32(&bars.tempty[buf]));
+        if (mark) dbg_mark(p, 8 + 4 * lt + 3);
+      }
+      if (b == 0 && mark && lt == 1) dbg_mark(p, 4);
+      uint64_t bs = 0ull, bq = 0ull;
+      sc.c = tc.n0 + c;
+      epilogue_batch32<F32, STATS>(p, r, valid, all_valid, obase + c, pix, tc.n0 + c, ns, tb, sc, bs, bq, lane);
+      if (STATS) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int c = 32 * half + 64 * b;
-      if (c < p.BN)
-        epilogue_batch32<F32, STATS>(p, acc + c, valid, obase + c, pix, tc.n0 + c, ns, tb, r_sum[b], r_sq[b], lane,
-                                     p.dbg != nullptr && warp == 2 && lane == 0 && rank == 0 && lt == 1 && c == 0);
+        for (int k = 0; k < 4; ++k) {
+          a_sum[k] = f32x2_add(a_sum[k], b == k ? bs : 0ull);
+          a_sq[k] = f32x2_add(a_sq[k], b == k ? bq : 0ull);
+        }
+      }
+      if (b == 0 && mark && lt == 1) dbg_mark(p, 5);
+#ifdef B200_EPI_PREFETCH
+      if (b + 1 < nb) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = rn[j];
+      }
+#endif
     }
-    // this warp is done with the buffer: tell the leader's MMA warp (count 16 = both CTAs)
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_leader(smem_u32(&bars.tempty[buf]));
-    if (warp == 2 && lane == 0 && rank == 0 && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 3);
+    if (mark && lt == 1) dbg_mark(p, 6);
   }
   if (STATS && cur_n0 >= 0) {
     fold_stats();
@@ -857,15 +984,18 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, PairBarriers&
     flush_add_v4(p.stats + cur_n0, s_stats[0], p.BN, t, 256);
     if (!p.stats_sum_only) flush_add_v4(p.stats + p.stats_ld + cur_n0, s_stats[1], p.BN, t, 256);
   }
+  // shared memory must outlive the TMA engine's reads of it
+  if (tma_out && lane == 0) bulk_wait_read_all();
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ ConvParams p, int m_total, int n_tiles, int n_slabs) {
+                       const __grid_constant__ OutMaps om, const __grid_constant__ ConvParams p, int m_total,
+                       int n_tiles, int n_slabs) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ PairBarriers bars;
   __shared__ float s_stats[2][256];
-  __shared__ __align__(16) float s_tr[8][32 * kTrStride];   // per-warp transpose tiles of the epilogue
+  __shared__ __align__(1024) float s_tr[8][kTrWords];   // per-warp staging tiles of the epilogue (TMA store source)
   // per-tap operand offsets, looked up by the two issuing threads (an indexed load from the parameter block
   // costs them hundreds of cycles per tap): [z][t] = {A window offset inside the K-block's boxes (>> 4),
   // resident-filter offset of the tap's slab (>> 4), filter K coordinate of the slab}
@@ -895,7 +1025,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int m_first = (int)((long long)m_slot * m_total / m_slots);
   const int m_stop = (int)((long long)(m_slot + 1) * m_total / m_slots);
   const uint32_t acc_cols = (uint32_t)p.BN;
-  const uint32_t want = 2u * acc_cols;
+  const int nl = pair_acc_log2(p.BN);   // log2(TMEM accumulators)
+  const uint32_t want = acc_cols << nl;
   const uint32_t tmem_cols = want <= 32 ? 32u : (want <= 64 ? 64u : (want <= 128 ? 128u : (want <= 256 ? 256u : 512u)));
 
   if (threadIdx.x == 0) {
@@ -905,9 +1036,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(smem_u32(&bars.fullB[s]), 1);
       mbar_init(smem_u32(&bars.emptyB[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(smem_u32(&bars.tfull[b]), 1);
-      mbar_init(smem_u32(&bars.tempty[b]), 16);  // eight epilogue warps of each CTA
+      // the epilogue warps of both CTAs that read a buffer: all eight, or (BN = 32: the two warp groups take
+      // alternate tiles) four
+      mbar_init(smem_u32(&bars.tempty[b]), p.BN == 32 ? 8 : 16);
     }
     fence_mbar_init();
   }
@@ -1056,9 +1189,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (p.bres) mbar_wait(fullB0, 0);
         for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
           const TileCoord tc = it.coord(p);
-          const int buf = lt & 1;
+          const int buf = lt & ((1 << nl) - 1);
           const uint32_t acc = tmem + buf * acc_cols;
-          mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);
+          mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> nl) & 1) ^ 1u);
           tc_fence_after();
           const int ntap = p.n_taps[tc.z];
           uint32_t accum = 0;
@@ -1150,9 +1283,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       } else
       for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
         const TileCoord tc = it.coord(p);
-        const int buf = lt & 1;
+        const int buf = lt & ((1 << nl) - 1);
         const uint32_t acc = tmem + buf * acc_cols;
-        mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> 1) & 1) ^ 1u);  // both epilogues drained it
+        mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> nl) & 1) ^ 1u);  // both epilogues drained it
         tc_fence_after();
         const int nk = p.n_taps[tc.z] * cin_blocks / p.kg;
         uint32_t accum = 0;
@@ -1196,11 +1329,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // --------------------------------------------------------- epilogue (own 128 rows, 8 warps)
     float* tb = &s_tr[warp - 2][0];
     if (p.out_f32) {
-      if (p.stats != nullptr) pair_epilogue<true, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
-      else pair_epilogue<true, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      if (p.stats != nullptr) pair_epilogue<true, true>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      else pair_epilogue<true, false>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
     } else {
-      if (p.stats != nullptr) pair_epilogue<false, true>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
-      else pair_epilogue<false, false>(p, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      if (p.stats != nullptr) pair_epilogue<false, true>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      else pair_epilogue<false, false>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
     }
   }
 
@@ -1713,6 +1846,30 @@ static int make_act_map(CUtensorMap* m, const void* base, int coff, int C, int l
   return B200_OK;
 }
 
+// Output map of one class of the CTA-pair kernel's TMA stores: the class's pixels (h * os + oa, w * os + ob)
+// as a dense [N][Ho][Wo][C] tensor with pixel strides os * ld / os * Wout * ld, so that the extents clip a
+// ragged tile exactly at the class's border; box = 32 channels x box_w x box_h pixels, 64-byte swizzle.
+static int make_out_map(CUtensorMap* m, const void* out, int coff, int C, int ld, int N, int Hout, int Wout,
+                        int Ho, int Wo, int oa, int ob, int os, int box_w, int box_h) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled entry point not found");
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(out) + coff + ((size_t)oa * Wout + ob) * ld;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)os * ld * 2, (cuuint64_t)os * Wout * ld * 2, (cuuint64_t)Hout * Wout * ld * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const MapKey key = {{(uint64_t)reinterpret_cast<uintptr_t>(base), (uint64_t)C, (uint64_t)ld, (uint64_t)N,
+                       ((uint64_t)Hout << 32) | (uint32_t)Wout, ((uint64_t)Ho << 32) | (uint32_t)Wo, (uint64_t)os,
+                       ((uint64_t)box_h << 32) | (uint32_t)box_w, 64u, 5u}};
+  if (map_cache_get(key, m)) return B200_OK;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B200_EDRIVER, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+  map_cache_put(key, *m);
+  return B200_OK;
+}
+
 static int make_filter_map(CUtensorMap* m, const void* base, int rows, int ktot, int box_k,
                            int box_rows, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_fn();
@@ -2138,6 +2295,25 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   if (pair_mode) {
     if (p.mt != 2 || p.BN < 32 || p.BN % 32)
       return set_error(B200_EINVAL, "conv_igemm: the CTA-pair kernel needs BN in {32, 64, 128, 256} (got %d)", p.BN);
+    // bf16 outputs of tiles >= 128 channels wide leave through TMA stores when the view is 16-byte addressable
+    // (tune bit 27: register stores, bit 28: TMA stores at any width).  Measured per launch inside a graph,
+    // register -> TMA stores: BN 128 1x1 64->128 42.8 -> 37.2 us, 384->256 29.0 -> 26.1; BN 256 3x3 58.9 -> 56.9;
+    // BN 64 neutral (17.2 -> 17.4, 86.6 -> 87.2) or worse (the pair-view data gradient, two tiles per us and SM:
+    // 106 -> 139 us); BN 32 161 -> 168: a store moves 32 pixel rows of 64 bytes, and that many small rows per
+    // microsecond cost the TMA unit more than they save the LSU.
+    OutMaps om;
+    memset(&om, 0, sizeof(om));
+    p.tma_out = 0;
+    if (!out_f32 && !((tune >> 27) & 1) && (p.BN >= 128 || ((tune >> 28) & 1)) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+        out_ld % 8 == 0 && out_coff % 8 == 0) {
+      const int box_w = p.tw < 32 ? p.tw : 32, box_h = 32 / box_w;
+      p.tma_out = 1;
+      for (int z = 0; z < n_classes; ++z) {
+        rc = make_out_map(&om.m[z], out, out_coff, filt_rows, out_ld, N, Hout, Wout, class_Ho[z], class_Wo[z], class_oa[z],
+                          class_ob[z], out_stride, box_w, box_h);
+        if (rc) return rc;
+      }
+    }
     // K-blocks per pipeline stage (tune bits 24-26, 0 = automatic): one barrier round trip and one
     // commit per stage cost the issuing threads a few hundred cycles, so a stage should hold >= ~512
     // tensor cycles of work: 2 K-blocks at BN = 256, more for narrower tiles (as far as the channel
@@ -2210,7 +2386,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
         if (pairs > total_tiles) pairs = total_tiles;
         pairs = (pairs / n_tiles) * n_tiles;
         if (pairs < n_tiles) pairs = n_tiles;
-        conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles, n_slabs);
+        conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, om, p, m_total, n_tiles, n_slabs);
         return check_launch("conv_igemm(pair, halo)");
       }
     }
@@ -2240,7 +2416,7 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     if (pairs > total_tiles) pairs = total_tiles;
     pairs = (pairs / n_tiles) * n_tiles;      // every pair keeps one filter tile
     if (pairs < n_tiles) pairs = n_tiles;
-    conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, p, m_total, n_tiles, n_slabs);
+    conv_igemm_pair_kernel<<<2 * pairs, kPairThreads, psmem, stream>>>(tmA, tmB, om, p, m_total, n_tiles, n_slabs);
     return check_launch("conv_igemm(pair)");
   }
   rc = make_act_map(&tmA, in, in_coff, in_C, in_ld, N, Hin, Win, p.KC, p.tw, p.th * p.mt, in_stride, p.KC * 2);

@@ -62,6 +62,7 @@ struct ConvParams {
   int8_t tap_off[kMaxClasses][kMaxTaps];  // first row of the tap's window inside its box (oh * box_w + ow)
   int tb, sb;        // taps per filter-ring slot, filter-ring slots
   int bres;          // 1: the pair's whole filter tile (all slabs, all K-blocks) stays resident in shared memory
+  int tma_out;       // 1: bf16 output tiles leave through TMA stores (CTA-pair kernel; one tensor map per class)
   // diagnostic (b200_debug_timeline): CTA pair 0 records %globaltimer at its phase boundaries here
   //   [0] kernel entry  [1] set-up done  [2] first operands landed  [3] exit
   //   [8 + 4*lt + {0: MMAs of tile lt start, 1: committed, 2: epilogue starts (accumulator full), 3: epilogue done}]

@@ -29,6 +29,9 @@ def shapes():
     out["s8"] = ((8, 64, 128, 128), (64, 9, 128), K.fwd_geometry(64, 128, 3, 3, 1, 1), True)      # M65536 N64 K128x9
     out["big"] = ((8, 64, 128, 256), (256, 9, 256), K.fwd_geometry(64, 128, 3, 3, 1, 1), True)    # M65536 N256 K256x9
     out["d2fwd"] = ((8, 256, 512, 64), (128, 16, 64), K.fwd_geometry(256, 512, 4, 4, 2, 1), False)
+    out["stem"] = ((8, 512, 1024, 32), (32, 1, 32), K.fwd_geometry(512, 1024, 1, 1, 1, 0), True)   # M1048576 N32 K32x1
+    out["c1x1"] = ((8, 128, 256, 64), (128, 1, 64), K.fwd_geometry(128, 256, 1, 1, 1, 0), True)    # M262144 N128 K64x1
+    out["f1x1"] = ((8, 64, 128, 384), (256, 1, 384), K.fwd_geometry(64, 128, 1, 1, 1, 0), True)    # M65536 N256 K384x1
     return out
 
 
@@ -85,14 +88,14 @@ def main():
               (name, tune, us, rel(t[1]), rel(t[2]), rel(t[3])))
         if t[4]:
             e1 = t[8 + 4 + 2]
-            print("  tile 1, first 32-column batch of warp 2 (us after the accumulator was full): TMEM load done %.2f, first 16 "
-                  "columns packed %.2f, stored %.2f, statistics done %.2f" % tuple((v - e1) / 1e3 for v in t[4:8]))
+            print("  tile 1, warp 2 (us after the accumulator was full): first TMEM batch in registers %.2f, first batch done %.2f, "
+                  "tile done %.2f" % tuple((v - e1) / 1e3 for v in t[4:7]))
         rows = []
         for lt in range(NT):
             a = t[8 + 4 * lt: 12 + 4 * lt]
             if a[0] == 0:
                 break
-            rows.append("  tile %2d: mma %.2f-%.2f  epilogue %.2f-%.2f" % (lt, rel(a[0]), rel(a[1]), rel(a[2]), rel(a[3])))
+            rows.append("  tile %2d: mma %.2f-%.2f  accumulator held by the epilogue %.2f-%.2f" % (lt, rel(a[0]), rel(a[1]), rel(a[2]), rel(a[3])))
         print("\n".join(rows[:6] + (["  ..."] if len(rows) > 8 else []) + rows[-2:] if len(rows) > 8 else rows))
 
 

@@ -16,6 +16,7 @@ CASES = [  # n, cin, cout, h, w, r, stride, pad, stats
     (8, 64, 128, 256, 512, 4, 2, 1, False),    # discriminator conv2
     (8, 1024, 128, 16, 32, 3, 1, 1, True),     # arm32: small M, deep K
     (8, 384, 256, 64, 128, 1, 1, 0, True),     # ffm 1x1
+    (8, 64, 128, 128, 256, 1, 1, 0, True),     # stage-3 1x1, memory bound (M262144 N128 K64)
 ]
 if os.environ.get("CASE"):
     CASES = [CASES[int(c)] for c in os.environ["CASE"].split(",")]

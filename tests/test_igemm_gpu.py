@@ -241,7 +241,9 @@ def test_conv_pair_kernel(cuda_lib, case, bn):
     bias = torch.randn(filt.shape[0], device="cuda", generator=g)
     ref = F.leaky_relu(ref + bias[:rows], 0.2)
     outs, sts = [], []
-    words = [bn | (1 << 22), bn | (1 << 22) | (3 << 16), 0]
+    # (bit 27: the epilogue stores from registers, bit 28: it hands its staging tiles to TMA stores at any tile
+    #  width -- the default does so from 128 channels up)
+    words = [bn | (1 << 22), bn | (1 << 22) | (3 << 16), bn | (1 << 22) | (1 << 27), bn | (1 << 22) | (1 << 28), 0]
     if (r == 3 and stride == 1) or (dgrad and r in (3, 4)) or (r == 4 and stride == 2):
         # input-halo reuse (bit 23): every tap is a shifted descriptor window into one box per K-block (four
         # input-parity planes for the stride-2 forward convs); bits 24-26 = taps per filter-ring slot
