@@ -813,6 +813,9 @@ __device__ __forceinline__ void epilogue_batch32(const ConvParams& p, const uint
 //                       commits (stage free / accumulator full) to both CTAs
 //   both CTAs         : TMA producer (own A rows, own half of B, signalling the leader's full[s]),
 //                       epilogue of their own 128 rows, arrival on the leader's tempty[buf]
+struct PairClass {
+  int n_taps, Ho, Wo, oa, ob;
+};
 struct PairBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -829,21 +832,26 @@ constexpr int kPairThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilog
 // tile's MMAs are issued in a fraction of the time the accumulator takes to come back through the epilogue, and
 // with two buffers the tile period was (MMA latency + epilogue + two barrier round trips) / 2
 __device__ __forceinline__ int pair_acc_log2(int bn) { return bn <= 128 ? 2 : 1; }
+// tiles up to this width are taken whole by ONE group of four epilogue warps, the two groups alternating
+// between tiles (half the per-tile barrier waits / coordinate arithmetic / arrivals per warp, two tiles in flight)
+constexpr int kPairAltBN = 32;
 
 template <bool F32, bool STATS>
-__device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps& om, PairBarriers& bars, float (*s_stats)[256],
+__device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps& om, const PairClass* cls, PairBarriers& bars, float (*s_stats)[256],
                                               float* tb, uint32_t tmem, int rank, int my_n, int m_first, int m_stop,
                                               int warp, int lane) {
   const int q = warp & 3;              // TMEM lane quarter this warp may read
   const int half = (warp - 2) >> 2;    // warp group: 32-column batches b % 2 == half ...
-  const bool alt = p.BN == 32;         // ... or, when a tile has ONE batch, the tiles lt % 2 == half
+  const bool alt = p.BN <= kPairAltBN; // ... or, for narrow tiles, every batch of the tiles lt % 2 == half
   const int row = q * 32 + lane;
   const int hl = row / p.tw, wl = row - hl * p.tw;
   const int t = threadIdx.x - 64;      // 0..255 among the epilogue threads
   const float ns = p.act == 0 ? 1.f : (p.act == 1 ? 0.f : p.slope);
   const uint32_t acc_cols = (uint32_t)p.BN;
   const int nl = pair_acc_log2(p.BN);
-  const int c0 = alt ? 0 : 32 * half;  // first column of this warp's batches (then every 64th)
+  const int c0 = alt ? 0 : 32 * half;  // first column of this warp's batches ...
+  const int cstep = alt ? 32 : 64;     // ... and their distance
+  const int nb = alt ? (p.BN >> 5) : (p.BN >> 6);
   // TMA stores: the warp's 32 accumulator rows are box_h patch rows of box_w pixels, starting at (hs, ws)
   const bool tma_out = !F32 && p.tma_out;
   const int hs = (q * 32) / p.tw, ws = (q * 32) - hs * p.tw;
@@ -858,7 +866,7 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps
     __syncwarp();
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      if (c0 + 64 * b < p.BN) {
+      if (b < nb) {
         float2 s = f32x2_unpack(a_sum[b]), sq = f32x2_unpack(a_sq[b]);
         s.x += __shfl_xor_sync(0xffffffffu, s.x, 16);
         s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
@@ -879,7 +887,7 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps
     const float* tiles = tb - (warp - 2) * kTrWords;
     for (int col = t; col < p.BN; col += 256) {
       const int cb = col >> 5;
-      const int w0 = alt ? 0 : (cb & 1) * 4, nw = alt ? 8 : 4, slot = alt ? 0 : cb >> 1;
+      const int w0 = alt ? 0 : (cb & 1) * 4, nw = alt ? 8 : 4, slot = alt ? cb : cb >> 1;
       float a1 = 0.f, a2 = 0.f;
       for (int qq = 0; qq < nw; ++qq) {
         const float2 v = *reinterpret_cast<const float2*>(tiles + (w0 + qq) * kTrWords + (slot * 32 + (col & 31)) * 2);
@@ -917,10 +925,11 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps
     tc_fence_after();
     if (mark) dbg_mark(p, 8 + 4 * lt + 2);
     const int h = tc.h0 + rank * p.th + hl, w = tc.w0 + wl;
-    const bool valid = (h < p.Ho[z]) && (w < p.Wo[z]);
+    const PairClass kc = cls[z];
+    const bool valid = (h < kc.Ho) && (w < kc.Wo);
     const bool all_valid = __all_sync(0xffffffffu, valid);
     const size_t pix =
-        ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + p.oa[z])) * p.Wout + (w * p.os + p.ob[z]);
+        ((size_t)tc.n_img * p.Hout + (size_t)(h * p.os + kc.oa)) * p.Wout + (w * p.os + kc.ob);
     const size_t obase = pix * p.out_ld + p.out_coff + tc.n0;
     StoreCoord sc;
     sc.map = tma_out ? &om.m[z] : nullptr;
@@ -931,7 +940,6 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps
     // output type made the tile loop stream ~25 KB of code through the 6 KB L0 instruction cache of a
     // scheduler that has two warps to hide the misses with); the next batch's TMEM load is in flight under
     // this batch's arithmetic, and the statistics accumulators are picked by select, not by index
-    const int nb = alt ? 1 : (p.BN >> 6);
 #ifdef B200_EPI_PREFETCH
     uint32_t r[32], rn[32];
     tmem_ld32(acc + c0, r);
@@ -940,14 +948,14 @@ __device__ __forceinline__ void pair_epilogue(const ConvParams& p, const OutMaps
 #endif
 #pragma unroll 1
     for (int b = 0; b < nb; ++b) {
-      const int c = c0 + 64 * b;
+      const int c = c0 + cstep * b;
 #ifndef B200_EPI_PREFETCH
       tmem_ld32(acc + c, r);
 #endif
       tmem_ld_wait32(r);
       if (b + 1 < nb) {
 #ifdef B200_EPI_PREFETCH
-        tmem_ld32(acc + c + 64, rn);
+        tmem_ld32(acc + c + cstep, rn);
 #endif
       } else {
         // the warp's last batch is in registers: hand the accumulator back to the leader's MMA warp now
@@ -1000,6 +1008,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   // costs them hundreds of cycles per tap): [z][t] = {A window offset inside the K-block's boxes (>> 4),
   // resident-filter offset of the tap's slab (>> 4), filter K coordinate of the slab}
   __shared__ uint32_t s_tapA[kMaxClasses][kMaxTaps + 1], s_tapB[kMaxClasses][kMaxTaps + 1], s_tapK[kMaxClasses][kMaxTaps + 1];
+  // per-class scalars every role looks up once per tile, and the plane / tap offsets of the producer (the same
+  // reason: an indexed parameter load is a few hundred cycles for the lone thread that waits for it)
+  __shared__ PairClass s_cls[kMaxClasses];
+  __shared__ int s_pl[4][2];
+  __shared__ int s_tapD[kMaxClasses][kMaxTaps][2];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1038,9 +1051,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(smem_u32(&bars.tfull[b]), 1);
-      // the epilogue warps of both CTAs that read a buffer: all eight, or (BN = 32: the two warp groups take
-      // alternate tiles) four
-      mbar_init(smem_u32(&bars.tempty[b]), p.BN == 32 ? 8 : 16);
+      // the epilogue warps of both CTAs that read a buffer: all eight, or (narrow tiles: the two warp groups
+      // take alternate tiles) four
+      mbar_init(smem_u32(&bars.tempty[b]), p.BN <= kPairAltBN ? 8 : 16);
     }
     fence_mbar_init();
   }
@@ -1052,6 +1065,22 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     s_tapA[z][t] = live ? ((uint32_t)p.tap_pl[z][t] * plane_bytes + (uint32_t)p.tap_off[z][t] * (uint32_t)p.KC * 2u) >> 4 : 0u;
     s_tapB[z][t] = ((uint32_t)(tk * cin_blocks) * b_half) >> 4;
     s_tapK[z][t] = (uint32_t)(tk * p.cin_pad);
+  }
+  if (threadIdx.x < kMaxClasses) {
+    const int z = threadIdx.x;
+    s_cls[z].n_taps = p.n_taps[z];
+    s_cls[z].Ho = p.Ho[z];
+    s_cls[z].Wo = p.Wo[z];
+    s_cls[z].oa = p.oa[z];
+    s_cls[z].ob = p.ob[z];
+  } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
+    s_pl[threadIdx.x - 32][0] = p.pl_dh[threadIdx.x - 32];
+    s_pl[threadIdx.x - 32][1] = p.pl_dw[threadIdx.x - 32];
+  }
+  for (int i = threadIdx.x; i < kMaxClasses * kMaxTaps; i += kPairThreads) {
+    const int z = i / kMaxTaps, t = i - z * kMaxTaps;
+    s_tapD[z][t][0] = p.tap_dh[z][t];
+    s_tapD[z][t][1] = p.tap_dw[z][t];
   }
   if (warp == 1) {
     tmem_alloc_pair(smem_u32(&bars.tmem_base), tmem_cols);
@@ -1094,14 +1123,14 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const TileCoord tc = it.coord(p);
           const int h0 = (tc.h0 + rank * p.th) * p.in_stride, w0 = tc.w0 * p.in_stride;
           const int brow = tc.n0 + rank * bn_half;
-          const int ntap = p.n_taps[tc.z];
+          const int ntap = s_cls[tc.z].n_taps;
           for (int cb = 0; cb < cin_blocks; ++cb) {
             mbar_wait(empty0 + 8u * s, ph ^ 1u);
             if (!(p.dbg_knob & 16)) {   // (timing experiment: bit 4 = no activation loads at all)
             if (leader) mbar_expect_tx(full0 + 8u * s, 2u * (uint32_t)p.np * plane_tx);
             for (int q = 0; q < p.np; ++q)
               tma_load_4d_pair(smem_base + s * halo_bytes + q * plane_bytes, &tmA, full0 + 8u * s, cb * p.KC,
-                               w0 + p.pl_dw[q], h0 + p.pl_dh[q], tc.n_img);
+                               w0 + s_pl[q][1], h0 + s_pl[q][0], tc.n_img);
             }
             if (++s == p.stages) {
               s = 0;
@@ -1129,7 +1158,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int brow = tc.n0 + rank * bn_half;
         // the tile's K-blocks in (tap, channel block) order, kg of them per stage -- a stage may span taps
         // (64-channel layers have ONE block per tap; the launcher picks kg dividing taps x blocks)
-        const int nblk = p.n_taps[tc.z] * cin_blocks;
+        const int nblk = s_cls[tc.z].n_taps * cin_blocks;
         int t = 0, cb = 0;
         for (int q = 0; q < nblk; q += p.kg) {
           mbar_wait(empty0 + 8u * s, ph ^ 1u);
@@ -1138,14 +1167,14 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           uint32_t sa = smem_base + s * stage_bytes;
           int t2 = t, cb2 = cb;
           for (int j = 0; j < p.kg; ++j, sa += a_bytes) {
-            tma_load_4d_pair(sa, &tmA, full, cb * p.KC, w0 + p.tap_dw[tc.z][t], h0 + p.tap_dh[tc.z][t], tc.n_img);
+            tma_load_4d_pair(sa, &tmA, full, cb * p.KC, w0 + s_tapD[tc.z][t][1], h0 + s_tapD[tc.z][t][0], tc.n_img);
             if (++cb == cin_blocks) {
               cb = 0;
               ++t;
             }
           }
           for (int j = 0; j < p.kg; ++j, sa += b_half) {
-            tma_load_2d_pair(sa, &tmB, full, p.tap_k[tc.z][t2] * p.cin_pad + cb2 * p.KC, brow);
+            tma_load_2d_pair(sa, &tmB, full, (int)s_tapK[tc.z][t2] + cb2 * p.KC, brow);
             if (++cb2 == cin_blocks) {
               cb2 = 0;
               ++t2;
@@ -1193,7 +1222,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t acc = tmem + buf * acc_cols;
           mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> nl) & 1) ^ 1u);
           tc_fence_after();
-          const int ntap = p.n_taps[tc.z];
+          const int ntap = s_cls[tc.z].n_taps;
           uint32_t accum = 0;
           if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
           const uint32_t* tapA = s_tapA[tc.z];
@@ -1287,7 +1316,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> nl) & 1) ^ 1u);  // both epilogues drained it
         tc_fence_after();
-        const int nk = p.n_taps[tc.z] * cin_blocks / p.kg;
+        const int nk = s_cls[tc.z].n_taps * cin_blocks / p.kg;
         uint32_t accum = 0;
         if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
         for (int kit = 0; kit < nk; ++kit) {
@@ -1329,11 +1358,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // --------------------------------------------------------- epilogue (own 128 rows, 8 warps)
     float* tb = &s_tr[warp - 2][0];
     if (p.out_f32) {
-      if (p.stats != nullptr) pair_epilogue<true, true>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
-      else pair_epilogue<true, false>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      if (p.stats != nullptr) pair_epilogue<true, true>(p, om, s_cls, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      else pair_epilogue<true, false>(p, om, s_cls, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
     } else {
-      if (p.stats != nullptr) pair_epilogue<false, true>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
-      else pair_epilogue<false, false>(p, om, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      if (p.stats != nullptr) pair_epilogue<false, true>(p, om, s_cls, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
+      else pair_epilogue<false, false>(p, om, s_cls, bars, s_stats, tb, tmem, rank, my_n, m_first, m_stop, warp, lane);
     }
   }
 

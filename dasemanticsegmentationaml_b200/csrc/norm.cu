@@ -46,7 +46,8 @@ __device__ __forceinline__ float act_grad(float pre, int act, float slope) {
 // and walks pixels in batches of UNR independent 16-byte loads per tensor (memory-level parallelism).
 constexpr int UNR = 4;   // single-tensor kernels
 constexpr int UNR3 = 2;  // kernels streaming three tensors
-constexpr int UNRF = 2;  // the fused BatchNorm backward: two batches of UNRF x 3 loads live per thread (double buffering)
+constexpr int UNRF = 2;  // the fused BatchNorm backward: two batches of UNRF x 3 loads live per thread (double buffering) ...
+constexpr int UNRF1 = 4; // ... or of UNRF1 x 2 loads when there is one gradient input
 constexpr int kRedRep = 8;  // replicas of the partial-sum buffer of the fused BatchNorm backward
 
 struct Slot {
@@ -376,24 +377,30 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
 // scripts/bench_small.py).  After the grid barrier ONE pass over the kRedRep partial-sum replicas per
 // CTA rebuilds the totals in shared memory (every thread re-reading all replicas for its 8 channels
 // cost 128 L2 loads per thread -- the 12-25 us floor of the small layers).
+// Bytes in flight bound these passes (512 threads per SM x loads per thread x 16 B against ~1.2 us of loaded HBM
+// latency): a layer with ONE gradient input (most of them) has no use for the registers of the second one and
+// runs UNRF1 = 4 pixels per batch instead of UNRF = 2 -- 64 KB per SM in flight instead of 32.
+template <bool DY2, int U>
 struct BwdBatch {
-  uint4 d[UNRF], z[UNRF], e[UNRF];
+  uint4 d[U], z[U], e[DY2 ? U : 1];
 };
 
-__device__ __forceinline__ void bwd_load(BwdBatch& b, const __nv_bfloat16* dy1, int dy1_ld, const __nv_bfloat16* dy2,
+template <bool DY2, int U>
+__device__ __forceinline__ void bwd_load(BwdBatch<DY2, U>& b, const __nv_bfloat16* dy1, int dy1_ld, const __nv_bfloat16* dy2,
                                          int dy2_ld, const __nv_bfloat16* z, int z_ld, int64_t base, int64_t npix,
                                          const Slot& t) {
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-  for (int u = 0; u < UNRF; ++u) {
+  for (int u = 0; u < U; ++u) {
     const int64_t p = base + u * t.py + t.ty;
     const bool ok = base >= 0 && p < npix;
     b.d[u] = ok ? ldraw(dy1 + p * dy1_ld + t.g * 8) : zero4;  // zero gradient: contributes nothing
     b.z[u] = ok ? ldraw(z + p * z_ld + t.g * 8) : zero4;
-    b.e[u] = (ok && dy2 != nullptr) ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
+    if (DY2) b.e[u] = ok ? ldraw(dy2 + p * dy2_ld + t.g * 8) : zero4;
   }
 }
 
+template <bool DY2, int U>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
                         const __nv_bfloat16* __restrict__ dy2, int dy2_ld,
@@ -415,25 +422,29 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
     sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
     sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
   }
-  const int64_t step = (int64_t)gridDim.x * t.py * UNRF;
-  const int64_t first = (int64_t)blockIdx.x * t.py * UNRF;
+  const int64_t step = (int64_t)gridDim.x * t.py * U;
+  const int64_t first = (int64_t)blockIdx.x * t.py * U;
   int64_t last_base = -1;
   {
-    BwdBatch cur, nxt;
+    BwdBatch<DY2, U> cur, nxt;
     bwd_load(cur, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, first < npix ? first : -1, npix, t);
     for (int64_t base = first; base < npix; base += step) {
       last_base = base;
       const int64_t nb = base + step;
       bwd_load(nxt, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, nb < npix ? nb : -1, npix, t);
 #pragma unroll
-      for (int u = 0; u < UNRF; ++u) {
+      for (int u = 0; u < U; ++u) {
         float d[8], zz[8], e[8];
         unpack8(cur.d[u], d);
         unpack8(cur.z[u], zz);
-        unpack8(cur.e[u], e);
+        if (DY2) {
+          unpack8(cur.e[u], e);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] += e[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+          const float gg = d[j] * act_grad(zz[j] * sc[j] + sh[j], act, slope);
           a1[j] += gg;
           a2[j] += gg * zz[j];
         }
@@ -486,21 +497,25 @@ bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy1, int dy1_ld,
     k0[j] = -sc[j] * r0 - k1[j] * mean[c];
   }
   {
-    BwdBatch cur, nxt;
+    BwdBatch<DY2, U> cur, nxt;
     bwd_load(cur, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, last_base, npix, t);
     for (int64_t base = last_base; base >= 0; base -= step) {
       bwd_load(nxt, dy1, dy1_ld, dy2, dy2_ld, z, z_ld, base - step, npix, t);   // base - step < 0: nothing
 #pragma unroll
-      for (int u = 0; u < UNRF; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int64_t p = base + u * t.py + t.ty;
         if (p < npix) {
           float d[8], zz[8], e[8], o[8];
           unpack8(cur.d[u], d);
           unpack8(cur.z[u], zz);
-          unpack8(cur.e[u], e);
+          if (DY2) {
+            unpack8(cur.e[u], e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] += e[j];
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float gg = (d[j] + e[j]) * act_grad(zz[j] * sc[j] + sh[j], act, slope);
+            const float gg = d[j] * act_grad(zz[j] * sc[j] + sh[j], act, slope);
             o[j] = sc[j] * gg + k1[j] * zz[j] + k0[j];
           }
           store8(dz + p * dz_ld + t.g * 8, o);
@@ -698,7 +713,8 @@ int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_
   }
   // two co-resident CTAs of <= 256 threads per SM (128 registers per thread): the whole grid must
   // be resident for the grid barrier
-  const int64_t blocks = (npix + (int64_t)py * UNRF - 1) / ((int64_t)py * UNRF);
+  const int unr = dy2 == nullptr ? UNRF1 : UNRF;
+  const int64_t blocks = (npix + (int64_t)py * unr - 1) / ((int64_t)py * unr);
   const int cap = n_sm * (threads <= 256 ? 2 : 1);
   const int grid = (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
   const __nv_bfloat16* a0 = static_cast<const __nv_bfloat16*>(dy1);
@@ -707,8 +723,8 @@ int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_
   __nv_bfloat16* a3 = static_cast<__nv_bfloat16*>(dz);
   void* args[] = {&a0, &dy1_ld, &a1, &dy2_ld, &a2, &z_ld, &a3, &dz_ld, &C, &npix, &scale, &shift,
                   &mean, &rstd, &red, &inv_count, &act, &slope};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)bn_act_bwd_fused_kernel, dim3(grid), dim3(threads),
-                                              args, smem, stream);
+  const void* fn = dy2 == nullptr ? (const void*)bn_act_bwd_fused_kernel<false, UNRF1> : (const void*)bn_act_bwd_fused_kernel<true, UNRF>;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream);
   if (e != cudaSuccess) return set_error(B200_ECUDA, "bn_act_bwd_fused: %s", cudaGetErrorString(e));
   return check_launch("bn_act_bwd_fused");
 }

@@ -233,26 +233,30 @@ for key, (kind, m) in sorted(records.items()):
         if kind == "conv":
             # CTA-pair kernel (cta_group::2, tune bit 22): BN x pipeline depth
             # (K-blocks per stage: automatic, 1 or 2; pipeline depth: automatic = as deep as fits)
-            for bn, kg in itertools.product((256, 128, 64, 32), (0, 1, 2, 3, 4)):
-                if m["rows"] % bn:
+            # x epilogue store path (bit 27: register stores where TMA stores are the default, i.e. BN >= 128;
+            # bit 28: TMA stores where they are not)
+            for bn, kg, alt_store in itertools.product((256, 128, 64, 32), (0, 1, 2, 3, 4), (0, 1)):
+                if m["rows"] % bn or (alt_store and m["f32"]):
                     continue
-                tune = bn | (kg << 24) | (1 << 22)
+                sbit = 0 if not alt_store else ((1 << 27) if bn >= 128 else (1 << 28))
+                tune = bn | (kg << 24) | (1 << 22) | sbit
                 try:
                     if not correct(tune):
                         continue
-                    results.append((timeit(lambda: run(tune)), tune, "BN%d KG%d PAIR" % (bn, kg)))
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d KG%d%s PAIR" % (bn, kg, " altstore" if alt_store else "")))
                 except Exception:
                     continue
             # CTA-pair kernel with input-halo reuse (bit 23; the launcher rejects shapes it does not apply
             # to): BN x taps per filter-ring slot x activation-ring depth
-            for bn, tb, sa in itertools.product((256, 128, 64, 32), (1, 2, 3), (2, 3)):
-                if m["rows"] % bn:
+            for bn, tb, sa, alt_store in itertools.product((256, 128, 64, 32), (1, 2, 3), (2, 3), (0, 1)):
+                if m["rows"] % bn or (alt_store and m["f32"]):
                     continue
-                tune = bn | (tb << 24) | (sa << 16) | (3 << 22)
+                sbit = 0 if not alt_store else ((1 << 27) if bn >= 128 else (1 << 28))
+                tune = bn | (tb << 24) | (sa << 16) | (3 << 22) | sbit
                 try:
                     if not correct(tune):
                         continue
-                    results.append((timeit(lambda: run(tune)), tune, "BN%d TB%d SA%d HALO PAIR" % (bn, tb, sa)))
+                    results.append((timeit(lambda: run(tune)), tune, "BN%d TB%d SA%d%s HALO PAIR" % (bn, tb, sa, " altstore" if alt_store else "")))
                 except Exception:
                     continue
         results.sort()
