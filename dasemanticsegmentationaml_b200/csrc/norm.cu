@@ -713,8 +713,12 @@ int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_
   }
   // two co-resident CTAs of <= 256 threads per SM (128 registers per thread): the whole grid must
   // be resident for the grid barrier
-  const int unr = dy2 == nullptr ? UNRF1 : UNRF;
-  const int64_t blocks = (npix + (int64_t)py * unr - 1) / ((int64_t)py * unr);
+  // pixels per batch and thread: the deepest that still leaves every SM its two CTAs (a small layer would rather
+  // have the CTAs: 4096 pixels x 128 channels are 64 CTAs at 4 pixels per batch, 256 at one)
+  const int cap0 = n_sm * (threads <= 256 ? 2 : 1);
+  auto blocks_at = [&](int u) { return (npix + (int64_t)py * u - 1) / ((int64_t)py * u); };
+  const int unr = (dy2 == nullptr && blocks_at(UNRF1) >= cap0) ? UNRF1 : (blocks_at(UNRF) >= cap0 ? UNRF : 1);
+  const int64_t blocks = blocks_at(unr);
   const int cap = n_sm * (threads <= 256 ? 2 : 1);
   const int grid = (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
   const __nv_bfloat16* a0 = static_cast<const __nv_bfloat16*>(dy1);
@@ -723,7 +727,10 @@ int b200_bn_act_bwd_fused(const void* dy1, int dy1_ld, const void* dy2, int dy2_
   __nv_bfloat16* a3 = static_cast<__nv_bfloat16*>(dz);
   void* args[] = {&a0, &dy1_ld, &a1, &dy2_ld, &a2, &z_ld, &a3, &dz_ld, &C, &npix, &scale, &shift,
                   &mean, &rstd, &red, &inv_count, &act, &slope};
-  const void* fn = dy2 == nullptr ? (const void*)bn_act_bwd_fused_kernel<false, UNRF1> : (const void*)bn_act_bwd_fused_kernel<true, UNRF>;
+  const void* fn = dy2 != nullptr ? (unr == 1 ? (const void*)bn_act_bwd_fused_kernel<true, 1> : (const void*)bn_act_bwd_fused_kernel<true, UNRF>)
+                   : unr == UNRF1 ? (const void*)bn_act_bwd_fused_kernel<false, UNRF1>
+                   : unr == UNRF  ? (const void*)bn_act_bwd_fused_kernel<false, UNRF>
+                                  : (const void*)bn_act_bwd_fused_kernel<false, 1>;
   cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, stream);
   if (e != cudaSuccess) return set_error(B200_ECUDA, "bn_act_bwd_fused: %s", cudaGetErrorString(e));
   return check_launch("bn_act_bwd_fused");
