@@ -39,6 +39,9 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(lib_path):
     assert "UTCHMMA" in out or "UTCMMA" in out, "no tcgen05.mma in SASS"
     assert "UTMALDG" in out, "no TMA tensor loads in SASS"
     assert "LDTM" in out, "no TMEM loads in SASS"
+    assert "UTMASTG" in out, "no TMA tensor stores in SASS (the conv epilogue's staging tiles)"
+    assert "UTCHMMA.2CTA" in out or "2CTA" in out, "no cta_group::2 MMA in SASS"
+    assert "FFMA2" in out and "FADD2" in out, "no packed fp32 arithmetic in SASS (BatchNorm column sums of the conv epilogue)"
 
 
 def test_product_state_dict_layout_matches_reference():
