@@ -73,6 +73,42 @@ def test_conv_forward_epilogue_and_views(cuda_lib):
     assert rel_l2(stats[1], (flat * flat).sum(0)) < 1e-3
 
 
+@pytest.mark.parametrize("bn", [32, 64, 128])
+@pytest.mark.parametrize("dgrad", [False, True])
+def test_conv_pair_tma_store_into_channel_slice(cuda_lib, bn, dgrad):
+    """The CTA-pair kernel's TMA-store epilogue (tune bit 28 forces it at any tile width) writing a channel slice of a
+    wider bf16 buffer on a ragged map (partial tiles; four output-parity classes for the stride-2 data gradient):
+    bit-identical to the register-store epilogue (bit 27), nothing written outside the slice or the map."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    n, cin, cout, h, w, r, stride, pad = (2, 64, 128, 37, 61, 4, 2, 1) if dgrad else (2, 64, 128, 23, 45, 3, 1, 1)
+    x, wgt = make_case(n, cin, cout, h, w, r, stride, pad, seed=5)
+    if dgrad:
+        ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - r) // stride + 1
+        g = torch.Generator(device="cuda").manual_seed(4)
+        inp = torch.randn(n, ho, wo, cout, device="cuda", generator=g).to(torch.bfloat16)
+        filt = K.pack_filter(wgt, transpose=True)
+        geom = K.dgrad_geometry(h, w, r, r, stride, pad)
+    else:
+        inp = x
+        filt = K.pack_filter(wgt)
+        geom = K.fwd_geometry(h, w, r, r, stride, pad)
+    rows = filt.shape[0]
+    if rows % bn:
+        pytest.skip("BN does not divide the filter rows")
+    outs = []
+    for store_bit in (27, 28):
+        big = torch.full((n, geom["Hout"], geom["Wout"], rows + 64), 3.0, device="cuda", dtype=torch.bfloat16)
+        stats = torch.zeros(2, rows, device="cuda")
+        K.conv_igemm(inp, filt, big[..., 32:32 + rows], geom, stats=stats, bn_tile=bn | (1 << 22) | (1 << store_bit))
+        torch.cuda.synchronize()
+        assert (big[..., :32] == 3.0).all() and (big[..., 32 + rows:] == 3.0).all()
+        flat = big[..., 32:32 + rows].float().reshape(-1, rows)
+        assert rel_l2(stats[0], flat.sum(0)) < 1e-3
+        outs.append((big, stats))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_l2(outs[0][1], outs[1][1]) < 1e-5
+
+
 DGRAD_CASES = [
     (2, 64, 64, 16, 32, 3, 1, 1),
     (2, 64, 128, 16, 32, 1, 1, 0),
