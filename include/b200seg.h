@@ -71,8 +71,11 @@ int b200_pack_filters_batched(const int64_t* table_dev, int n_filters, cudaStrea
  * with the transposed filter and (for stride 2) the four output-parity classes it is the data
  * gradient autograd derives for the same layers.  Out-of-bounds input is read as zero (padding).
  * stats != NULL: adds per-channel sum / sum of squares of the stored values to stats[0][.] /
- * stats[1][.] (train-mode BatchNorm, stdcnet.py:10,14).  tune: 0 = automatic tile, else
- * BN | (sub-tiles << 12) | (pipeline stages << 16) from the tuned table.  * mask (optional, bf16 NHWC view shaped like the output): the result is multiplied by
+ * stats[1][.] (train-mode BatchNorm, stdcnet.py:10,14).  tune: 0 = automatic tile, else the packed word of the
+ * tuned table: BN | (sub-tiles << 12) | (pipeline stages << 16) | bit 20 persistent one-CTA kernel | bit 21 resident
+ * filter | bit 22 CTA-pair kernel (cta_group::2) | bit 23 input-halo reuse | bits 24-26 K-blocks per stage / taps per
+ * filter-ring slot | bit 27 epilogue stores from registers | bit 28 epilogue TMA stores at any tile width.
+ * mask (optional, bf16 NHWC view shaped like the output): the result is multiplied by
  * LeakyReLU'(mask) = (mask > 0 ? 1 : mask_slope) -- the backward of the discriminators' biased
  * conv + LeakyReLU layers (discriminator.py:17-26) folded into the data-gradient launch that produces
  * the layer's output gradient; with stats_sum_only = 1 the statistics path then returns only

@@ -62,6 +62,17 @@ for c, h, w in ((128, 128, 256), (256, 64, 128), (512, 32, 64)):
     run("dwconv_s2_fwd  C%d %dx%d +pool +stats" % (c, h, w), lambda: K.dwconv_s2_fwd(x, 3, wt, None, z, pool, 0, 0.0, stats), e + e // 2)
     run("dwconv_s2_dgrad C%d %dx%d +dpool" % (c, h, w), lambda: K.dwconv_s2_dgrad(dz, dpool, 3, wt, dx), e + e // 2)
     run("dwconv_s2_wgrad C%d %dx%d" % (c, h, w), lambda: K.dwconv_s2_wgrad(dz, x, 3, dw, None), e + e // 4)
+# ---- depthwise 4x4 s2 (+bias) of the depthwise-separable discriminators (config[3]; the pointwise k=1, p=1 convs
+#      grow every map by 2 pixels)
+for c, h, w in ((32, 512, 1024), (64, 258, 514), (128, 131, 259), (256, 67, 131), (512, 35, 67)):
+    x = act(N, h, w, c)
+    wt, bs = torch.randn(c, 1, 4, 4, device=dev), torch.randn(c, device=dev)
+    ho, wo = (h + 2 - 4) // 2 + 1, (w + 2 - 4) // 2 + 1
+    z, dz, dx = act(N, ho, wo, c), act(N, ho, wo, c), act(N, h, w, c)
+    dw, db, e = torch.zeros(c, 1, 4, 4, device=dev), torch.zeros(c, device=dev), x.numel() * 2
+    run("dwconv_s2_fwd  k4 C%d %dx%d +bias" % (c, h, w), lambda: K.dwconv_s2_fwd(x, 4, wt, bs, z, None, 0, 0.0, None), e + e // 4)
+    run("dwconv_s2_dgrad k4 C%d %dx%d" % (c, h, w), lambda: K.dwconv_s2_dgrad(dz, None, 4, wt, dx), e + e // 4)
+    run("dwconv_s2_wgrad k4 C%d %dx%d +dbias" % (c, h, w), lambda: K.dwconv_s2_wgrad(dz, x, 4, dw, db), e + e // 4)
 # ---- discriminator head (Cout = 1, 4x4 s2) on [8, 32, 64, 512]
 x = act(N, 32, 64, 512)
 wt, b = torch.randn(1, 512, 4, 4, device=dev) * 0.01, torch.zeros(1, device=dev)
