@@ -2102,8 +2102,14 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
   // (bit 20: persistent kernel)
   // (bit 22: CTA-pair kernel, cta_group::2 -- implies two 128-pixel sub-tiles, one per CTA)
   // tune == 0 (no table entry): the CTA-pair kernel whenever the filter rows allow a 32-column tile
+  // (except thin inputs under a full filter -- 32 input channels, >= 9 taps: half-width K-blocks make the pair
+  //  kernel's per-tap costs the whole tile, and the one-CTA kernel with two stacked sub-tiles measured 1.5-2x
+  //  faster on every such shape of the sweep, profiles/r2_tile_sweep_epilogue.txt)
   int pair_mode = (tune >> 22) & 1;
-  if (tune == 0 && filt_rows % 32 == 0) pair_mode = 1;
+  int auto_taps = 0;
+  for (int z = 0; z < n_classes && z < kMaxClasses; ++z) auto_taps = class_ntaps[z] > auto_taps ? class_ntaps[z] : auto_taps;
+  const bool thin_auto = tune == 0 && cin_pad == 32 && auto_taps >= 9;
+  if (tune == 0 && filt_rows % 32 == 0 && !thin_auto) pair_mode = 1;
   const int bn_override = tune & 0xFFF, mt_override = pair_mode ? 2 : (tune >> 12) & 0xF, st_override = (tune >> 16) & 0xF;
   if (n_classes < 1 || n_classes > kMaxClasses) return set_error(B200_EINVAL, "conv_igemm: bad class count %d", n_classes);
   if (cin_pad % 32) return set_error(B200_EINVAL, "conv_igemm: cin_pad %d not a multiple of 32", cin_pad);
@@ -2200,7 +2206,11 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     // (automatic only at stride 1 -- one box, or two boxes serving >= 4 taps each: the four parity planes
     //  of a stride-2 conv cost 80 KB per K-block at 64 channels and measured slower than per-tap boxes on
     //  the discriminator's layers)
-    if (halo_ok && (halo_mode || (tune == 0 && s == 1 && np <= 2 && min_taps >= 4 * np))) {
+    // (and only on maps of >= 32768 output pixels: on the 1/16 and 1/32 resolution layers, one or two tiles per
+    //  pair, the per-tap pipeline with several K-blocks per stage measured up to 2x faster than the halo rings)
+    long auto_px = 0;
+    for (int z = 0; z < n_classes; ++z) auto_px += (long)class_Ho[z] * class_Wo[z] * N;
+    if (halo_ok && (halo_mode || (tune == 0 && s == 1 && np <= 2 && min_taps >= 4 * np && auto_px >= 32768))) {
       halo_mode = 1;
       p.tw = 8;
       p.th = 16;
@@ -2247,12 +2257,17 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
     if (bn_override > 0 && bn != bn_override) continue;
     // keep at least ~one wave of CTAs (CTA pairs: 74 of them, each covering two pixel tiles) unless
     // nothing smaller divides Cout
-    if (pair_mode ? ((m_tiles + 1) / 2 * (filt_rows / bn) < 74 && bn > 32) : (m_tiles * (filt_rows / bn) < 148 && bn > 32)) continue;
+    // (deep reductions -- K >= 1152 -- on small maps: narrow tiles multiply the MMA count, so 48 pair tiles
+    //  are enough and the tile stays >= 64 channels wide; same sweep)
+    const bool deep = (long)max_nk * p.KC >= 1152;
+    if (pair_mode ? ((m_tiles + 1) / 2 * (filt_rows / bn) < (deep ? 48 : 74) && bn > (deep ? 64 : 32))
+                  : (m_tiles * (filt_rows / bn) < 148 && bn > 32)) continue;
     best_bn = bn;
   }
   if (best_bn == 0) best_bn = (bn_override > 0 && filt_rows % bn_override == 0) ? bn_override : (filt_rows % 32 == 0 ? 32 : 16);
   if (best_bn == 128 && max_nk >= 16 && m_tiles * (filt_rows / best_bn) >= 1184 && p.th * 2 * in_stride <= 256)
     best_mt = 2;
+  if (thin_auto) best_mt = 2;
   if (mt_override > 0) best_mt = mt_override;
   if (best_bn == 0) return set_error(B200_EINVAL, "conv_igemm: no tile shape for %d output channels", filt_rows);
   if (best_mt * best_bn > 512) best_mt = 512 / best_bn;

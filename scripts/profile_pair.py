@@ -17,6 +17,13 @@ CASES = [  # n, cin, cout, h, w, r, stride, pad, stats
     (8, 1024, 128, 16, 32, 3, 1, 1, True),     # arm32: small M, deep K
     (8, 384, 256, 64, 128, 1, 1, 0, True),     # ffm 1x1
     (8, 64, 128, 128, 256, 1, 1, 0, True),     # stage-3 1x1, memory bound (M262144 N128 K64)
+    # shapes where the launcher's heuristic (tune = 0) was >= 1.5x off the tuner's best (profiles/r2_tile_sweep_epilogue.txt)
+    (8, 1024, 128, 16, 32, 3, 1, 1, True),     # 7: tuned 28.3 us
+    (8, 512, 256, 16, 32, 3, 1, 1, True),      # 8: tuned 19.5 us
+    (8, 256, 128, 32, 64, 3, 1, 1, True),      # 9: tuned 16.7 us
+    (8, 32, 32, 128, 256, 3, 1, 1, False),     # 10: tuned 21.0 us
+    (8, 32, 32, 90, 160, 3, 1, 1, True),       # 11: tuned 17.0 us
+    (8, 1024, 128, 23, 40, 3, 1, 1, True),     # 12: tuned 35.4 us
 ]
 if os.environ.get("CASE"):
     CASES = [CASES[int(c)] for c in os.environ["CASE"].split(",")]
