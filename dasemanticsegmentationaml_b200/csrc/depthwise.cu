@@ -150,6 +150,192 @@ dwconv_s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H
   }
 }
 
+// ---------------------------------------------------------------- 4x4 / stride 2, shared-memory tiles
+// The kernels above read every input pixel of a 4x4 stride-2 window from global memory once per output pixel that
+// uses it (4x): 16 loads, 16 address computations and up to 128 L1 tag look-ups per 8 output values -- 0.17-0.34
+// of HBM inside a graph on the depthwise-separable discriminators' layers (scripts/bench_small.py).  Here a CTA
+// stages the (2 TH + 2) x (2 TW + 2) input pixels x CT channels under a TH x TW output tile in shared memory with
+// 16-byte cp.async (zero-filled outside the map = the conv's padding), double buffered over a persistent tile
+// loop, and every window element is a conflict-free LDS.128; a thread owns TWO output pixels of one channel group,
+// so a filter tap's weights are read once for both.  Used for the two widest layers (C <= 64), see the launcher.
+//   CT = 64: a pixel is 128 B; lanes = 8 groups of one pixel first, then the tile row.
+//   CT = 32: a pixel is 64 B; lanes = 4 groups, then two tile ROWS (row pitch padded by 32 B: two input rows apart
+//            = 64 B apart in bank space), then the columns.
+constexpr int kDwTH = 4;                      // output rows per tile
+constexpr int kDwIH = 2 * kDwTH + 2;          // input rows under it
+template <int CT>
+struct DwTile {
+  static constexpr int G = CT / 8;                        // 16-byte channel groups per pixel
+  static constexpr int TW = 512 / (kDwTH * G);            // output columns per tile (512 (pixel, group) items)
+  static constexpr int IW = 2 * TW + 2;                   // input columns under it
+  static constexpr int PITCH = IW * CT * 2 + (CT == 32 ? 32 : 0);   // bytes per staged input row
+  static constexpr int BYTES = kDwIH * PITCH;
+  static constexpr int PIECES = kDwIH * IW * G;           // 16-byte pieces per tile
+};
+
+template <int CT>
+__device__ __forceinline__ void dw4_stage(uint32_t dst, const __nv_bfloat16* __restrict__ x, int x_ld, int n, int H, int W,
+                                          int c0, int h_in0, int w_in0) {
+  using T = DwTile<CT>;
+  for (int i = threadIdx.x; i < T::PIECES; i += blockDim.x) {
+    const int g = i % T::G;
+    const int col = (i / T::G) % T::IW;
+    const int row = i / (T::G * T::IW);
+    const int h = h_in0 + row, w = w_in0 + col;
+    const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+    const __nv_bfloat16* src = x + (((size_t)n * H + (ok ? h : 0)) * W + (ok ? w : 0)) * x_ld + c0 + g * 8;
+    cp_async16(dst + row * T::PITCH + col * (CT * 2) + g * 16, src, ok ? 16u : 0u);
+  }
+}
+
+// z = act(dwconv4x4s2p1(x) + bias) (+ BatchNorm statistics of the stored values).  C % CT == 0.
+template <int CT>
+__global__ void __launch_bounds__(256, 2)
+dw4_fwd_tiled_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int N, int H, int W, int C,
+                     const float* __restrict__ w, const float* __restrict__ bias,
+                     __nv_bfloat16* __restrict__ z, int z_ld, int Ho, int Wo, int act, float slope,
+                     float* __restrict__ stats) {
+  using T = DwTile<CT>;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  uint8_t* s_tile = s_raw;                                          // two input tiles
+  float* s_w = reinterpret_cast<float*>(s_raw + 2 * T::BYTES);      // [16][CT] filter of the current channel chunk
+  float* s_b = s_w + 16 * CT;                                       // [CT] bias
+  float* s_acc = s_b + CT;                                          // [2][CT] statistics of the current chunk
+  const int tiles_w = (Wo + T::TW - 1) / T::TW, tiles_h = (Ho + kDwTH - 1) / kDwTH;
+  const int chunks = C / CT;
+  const int per_chunk = N * tiles_h * tiles_w;
+  const int total = chunks * per_chunk;
+  // item = (group, pixel of the tile); the thread's two items are 256 apart: same group (256 % G == 0)
+  int g, ty[2], tx[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int it = threadIdx.x + 256 * j;
+    if (CT == 64) {
+      g = it % T::G;
+      tx[j] = (it / T::G) % T::TW;
+      ty[j] = it / (T::G * T::TW);
+    } else {
+      g = it % T::G;
+      const int rp = (it / T::G) % 2;                 // row of a row pair
+      tx[j] = (it / (T::G * 2)) % T::TW;
+      ty[j] = 2 * (it / (T::G * 2 * T::TW)) + rp;
+    }
+  }
+  auto coords = [&](int t, int* cc, int* n, int* h0, int* w0) {
+    *cc = t / per_chunk;
+    int r = t - *cc * per_chunk;
+    *n = r / (tiles_h * tiles_w);
+    r -= *n * tiles_h * tiles_w;
+    *h0 = (r / tiles_w) * kDwTH;
+    *w0 = (r % tiles_w) * T::TW;
+  };
+  const uint32_t tile_u32 = smem_u32(s_tile);
+  float s1[8] = {0}, s2[8] = {0};
+  int cur_cc = -1;
+  auto flush_stats = [&]() {   // this thread's partial sums -> the chunk's shared sums -> global
+    for (int off = T::G; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+      }
+    }
+    if ((threadIdx.x & 31) < T::G) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&s_acc[g * 8 + j], s1[j]);
+        atomicAdd(&s_acc[CT + g * 8 + j], s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CT; i += blockDim.x) {
+      atomicAdd(&stats[cur_cc * CT + i], s_acc[i]);
+      atomicAdd(&stats[C + cur_cc * CT + i], s_acc[CT + i]);
+    }
+  };
+  int t = blockIdx.x, buf = 0;
+  if (t < total) {
+    int cc, n, h0, w0;
+    coords(t, &cc, &n, &h0, &w0);
+    dw4_stage<CT>(tile_u32, x, x_ld, n, H, W, cc * CT, 2 * h0 - 1, 2 * w0 - 1);
+  }
+  cp_async_commit();
+  for (; t < total; t += gridDim.x, buf ^= 1) {
+    int cc, n, h0, w0;
+    coords(t, &cc, &n, &h0, &w0);
+    const int tn = t + gridDim.x;
+    if (tn < total) {
+      int cc2, n2, h2, w2;
+      coords(tn, &cc2, &n2, &h2, &w2);
+      dw4_stage<CT>(tile_u32 + (buf ^ 1) * T::BYTES, x, x_ld, n2, H, W, cc2 * CT, 2 * h2 - 1, 2 * w2 - 1);
+    }
+    cp_async_commit();
+    if (cc != cur_cc) {   // (block-uniform) next channel chunk: its filter, bias, statistics
+      if (stats != nullptr && cur_cc >= 0) flush_stats();
+      __syncthreads();
+      for (int i = threadIdx.x; i < 16 * CT; i += blockDim.x) {
+        const int c = i % CT, tap = i / CT;
+        s_w[i] = __ldg(w + (size_t)(cc * CT + c) * 16 + tap);
+      }
+      for (int i = threadIdx.x; i < CT; i += blockDim.x) {
+        s_b[i] = bias != nullptr ? __ldg(bias + cc * CT + i) : 0.f;
+        s_acc[i] = 0.f;
+        s_acc[CT + i] = 0.f;
+      }
+      cur_cc = cc;
+    }
+    cp_async_wait<1>();    // this tile has landed (the next one may still be in flight)
+    __syncthreads();
+    const uint8_t* tile = s_tile + buf * T::BYTES;
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[j][c] = s_b[g * 8 + c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const float* wrow = s_w + (r * 4 + s) * CT + g * 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(tile + (2 * ty[j] + r) * T::PITCH + (2 * tx[j] + s) * (CT * 2) + g * 16);
+          float v[8];
+          up8(raw, v);
+          fma8(acc[j], v, wrow);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ho = h0 + ty[j], wo = w0 + tx[j];
+      if (ho < Ho && wo < Wo) {
+        if (act == 2) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[j][c] = fmaxf(acc[j][c], 0.f) + slope * fminf(acc[j][c], 0.f);
+        } else if (act == 1) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[j][c] = fmaxf(acc[j][c], 0.f);
+        }
+        st8(z + (((size_t)n * Ho + ho) * Wo + wo) * z_ld + cc * CT + g * 8, acc[j]);
+        if (stats != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float rr = __bfloat162float(__float2bfloat16(acc[j][c]));
+            s1[c] += rr;
+            s2[c] += rr * rr;
+          }
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with this buffer before the next iteration's loads overwrite it
+  }
+  cp_async_wait<0>();
+  if (stats != nullptr && cur_cc >= 0) flush_stats();
+}
+
 // Data gradient: dx[n,h,w,c] = sum_{r,s} dz[n,(h+1-r)/2,(w+1-s)/2,c] * w[c,r,s]
 //                              (+ sum over the 3x3/s2 pooling windows covering (h,w) of dpool / 9)
 // One work item = the 2x2 block of dx pixels (2i+ph, 2j+pw): which filter tap links an output
@@ -362,6 +548,29 @@ int b200_dwconv_s2_fwd(const void* x, int x_ld, int N, int H, int W, int C, int 
   auto xx = static_cast<const __nv_bfloat16*>(x);
   auto zz = static_cast<__nv_bfloat16*>(z);
   auto pp = static_cast<__nv_bfloat16*>(pool);
+  if (K == 4 && pool == nullptr && (C == 32 || C == 64) && x_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // shared-memory tiled kernel (two CTAs of ~92 KB per SM, persistent over the tiles) on the wide, thin layers:
+    // 19(32) channels at 512x1024 148.7 -> 121.1 us, 64 at 258x514 87.6 -> 79.6 us inside a graph; from 128
+    // channels up (maps of <= 131x259) the per-pixel kernel is as fast or faster (47.9 / 28.1 / 21.1 us against
+    // 46.0 / 31.6 / 22.6).  What bounds the tiled kernel is shared-memory bandwidth: 256 B of window data plus
+    // 256 B of filter taps per (pixel, group) item -- four items per thread and a sliding window would halve it.
+    static int optin4 = 0;
+    if (!optin4) {
+      cudaFuncSetAttribute(dw4_fwd_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(dw4_fwd_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      optin4 = 1;
+    }
+    const int ct = C == 32 ? 32 : 64;
+    const int tw = ct == 32 ? DwTile<32>::TW : DwTile<64>::TW;
+    const long tiles = (long)(C / ct) * N * ((Ho + kDwTH - 1) / kDwTH) * ((Wo + tw - 1) / tw);
+    const int tgrid = (int)(tiles < 296 ? tiles : 296);
+    const size_t tsmem = 2 * (size_t)(ct == 32 ? DwTile<32>::BYTES : DwTile<64>::BYTES) + (size_t)(16 + 1 + 2) * ct * sizeof(float);
+    if (ct == 32)
+      dw4_fwd_tiled_kernel<32><<<tgrid, 256, tsmem, stream>>>(xx, x_ld, N, H, W, C, w, bias, zz, z_ld, Ho, Wo, act, slope, stats);
+    else
+      dw4_fwd_tiled_kernel<64><<<tgrid, 256, tsmem, stream>>>(xx, x_ld, N, H, W, C, w, bias, zz, z_ld, Ho, Wo, act, slope, stats);
+    return check_launch("dwconv_s2_fwd(tiled)");
+  }
   if (K == 3)
     dwconv_s2_fwd_kernel<3><<<grid, threads, smem, stream>>>(xx, x_ld, N, H, W, C, w, bias, zz, z_ld, pp, pool_ld, Ho, Wo, act, slope, stats);
   else

@@ -188,6 +188,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
+// ------------------------------------------------------------- cp.async (LDGSTS), 16 bytes
+// src_bytes = 0 writes 16 zero bytes (padding / ragged edges) without reading `src` (which must still be a valid
+// address); .cg: the data bypasses L1 -- the shared-memory tile IS the cache.
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ------------------------------------------------------------- TMA stores (shared -> global)
 // One thread hands a dense (optionally swizzled) shared-memory box to the TMA engine; elements outside the
 // tensor map's extents are not written.  Generic-proxy writes to the box must be fenced
