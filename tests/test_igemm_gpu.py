@@ -109,6 +109,27 @@ def test_conv_pair_tma_store_into_channel_slice(cuda_lib, bn, dgrad):
     assert rel_l2(outs[0][1], outs[1][1]) < 1e-5
 
 
+def test_batched_filter_packing_matches_the_single_filter_kernel(cuda_lib):
+    """b200_pack_filters_batched (shared-memory tiles, both orientations, ragged channel counts, 1x1 .. 4x4 taps)
+    against b200_pack_filter, bit for bit, padding included."""
+    from dasemanticsegmentationaml_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(21)
+    shapes = [(64, 32, 3), (128, 64, 3), (19, 256, 1), (256, 384, 1), (40, 72, 3), (512, 256, 4), (128, 1024, 3), (32, 27, 1)]
+    rows, want = [], []
+    for cout, cin, r in shapes:
+        wgt = torch.randn(cout, cin, r, r, device="cuda", generator=g)
+        for tr in (False, True):
+            ref = K.pack_filter(wgt, transpose=tr)
+            buf = torch.full_like(ref, 7.0)
+            rows.append([wgt.data_ptr(), buf.data_ptr(), cout, cin, r * r, buf.shape[0], buf.shape[2], int(tr)])
+            want.append((wgt, ref, buf))
+    table = torch.tensor(rows, dtype=torch.int64).cuda()
+    K.call("b200_pack_filters_batched", K.ptr(table), K.c_int(len(rows)), K.stream())
+    torch.cuda.synchronize()
+    for _, ref, buf in want:
+        assert torch.equal(ref, buf)
+
+
 DGRAD_CASES = [
     (2, 64, 64, 16, 32, 3, 1, 1),
     (2, 64, 128, 16, 32, 1, 1, 0),
