@@ -1066,21 +1066,18 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     s_tapB[z][t] = ((uint32_t)(tk * cin_blocks) * b_half) >> 4;
     s_tapK[z][t] = (uint32_t)(tk * p.cin_pad);
   }
-  if (threadIdx.x < kMaxClasses) {
-    const int z = threadIdx.x;
-    s_cls[z].n_taps = p.n_taps[z];
-    s_cls[z].Ho = p.Ho[z];
-    s_cls[z].Wo = p.Wo[z];
-    s_cls[z].oa = p.oa[z];
-    s_cls[z].ob = p.ob[z];
-  } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
-    s_pl[threadIdx.x - 32][0] = p.pl_dh[threadIdx.x - 32];
-    s_pl[threadIdx.x - 32][1] = p.pl_dw[threadIdx.x - 32];
-  }
-  for (int i = threadIdx.x; i < kMaxClasses * kMaxTaps; i += kPairThreads) {
-    const int z = i / kMaxTaps, t = i - z * kMaxTaps;
-    s_tapD[z][t][0] = p.tap_dh[z][t];
-    s_tapD[z][t][1] = p.tap_dw[z][t];
+  // (ONE indexed parameter load per thread: a thread that does five of them in a row holds the whole CTA at the
+  //  barrier below for ~0.3 us)
+  if (threadIdx.x >= 72 && threadIdx.x < 72 + 5 * kMaxClasses) {
+    const int z = (threadIdx.x - 72) / 5, f = (threadIdx.x - 72) % 5;
+    int* dst = reinterpret_cast<int*>(&s_cls[z]) + f;
+    *dst = f == 0 ? p.n_taps[z] : f == 1 ? p.Ho[z] : f == 2 ? p.Wo[z] : f == 3 ? p.oa[z] : p.ob[z];
+  } else if (threadIdx.x >= 96 && threadIdx.x < 104) {
+    const int q = (threadIdx.x - 96) >> 1;
+    s_pl[q][threadIdx.x & 1] = (threadIdx.x & 1) ? p.pl_dw[q] : p.pl_dh[q];
+  } else if (threadIdx.x >= 128 && threadIdx.x < 128 + 2 * kMaxClasses * kMaxTaps) {
+    const int i = (threadIdx.x - 128) >> 1, z = i / kMaxTaps, t = i - z * kMaxTaps;
+    s_tapD[z][t][threadIdx.x & 1] = (threadIdx.x & 1) ? (int)p.tap_dw[z][t] : (int)p.tap_dh[z][t];
   }
   if (warp == 1) {
     tmem_alloc_pair(smem_u32(&bars.tmem_base), tmem_cols);
@@ -1195,6 +1192,23 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // built by adding to a precomputed template, stage / phase advance by increment, the K steps are
     // unrolled, and the next stage's barrier is polled right after this stage's MMAs were queued.
     if (leader && elect_one()) {
+      // (everything this thread does between two tcgen05.mma is serial latency, ~10 cycles per dependent instruction:
+      //  the debug stamps are one predicated branch on a hoisted flag, and the walk over the tile range only
+      //  tracks what the issue loop needs -- the tile's class, by a countdown to the next class boundary)
+      const bool dbg_on = p.dbg != nullptr && blockIdx.x < 2;
+      int mz = 0, mleft = 0;
+      {
+        int rem = m_first;
+        for (;;) {
+          const int cnt = p.tiles_h[mz] * p.tiles_w[mz] * p.n_img;
+          if (rem < cnt || mz + 1 >= kMaxClasses || p.n_taps[mz + 1] <= 0) {
+            mleft = cnt - rem;
+            break;
+          }
+          rem -= cnt;
+          ++mz;
+        }
+      }
       const uint32_t idesc = make_idesc_bf16(256, p.BN, 0, 0);
       const uint32_t sbo = 8u * p.KC * 2u;
       const uint64_t dtmpl = make_smem_desc(0, 16, sbo, (p.KC == 64) ? 2u : 4u);
@@ -1216,20 +1230,27 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int sb = 0;
         uint32_t phb = 0;
         if (p.bres) mbar_wait(fullB0, 0);
-        for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
-          const TileCoord tc = it.coord(p);
+        int ntap = s_cls[mz].n_taps;
+        const uint32_t* tapA = s_tapA[mz];
+        const uint32_t* tapB = s_tapB[mz];
+        for (int m = m_first; m < m_stop; ++m, ++lt) {
+          if (mleft == 0) {   // next class (stride-2 data gradients: other taps)
+            ++mz;
+            mleft = p.tiles_h[mz] * p.tiles_w[mz] * p.n_img;
+            ntap = s_cls[mz].n_taps;
+            tapA = s_tapA[mz];
+            tapB = s_tapB[mz];
+          }
+          --mleft;
           const int buf = lt & ((1 << nl) - 1);
           const uint32_t acc = tmem + buf * acc_cols;
           mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> nl) & 1) ^ 1u);
           tc_fence_after();
-          const int ntap = s_cls[tc.z].n_taps;
           uint32_t accum = 0;
-          if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
-          const uint32_t* tapA = s_tapA[tc.z];
-          const uint32_t* tapB = s_tapB[tc.z];
+          if (dbg_on && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
           for (int cb = 0; cb < cin_blocks; ++cb) {
             if (!(p.dbg_knob & 16)) mbar_wait(full0 + 8u * s, ph);
-            if (lt == 0 && cb == 0) dbg_mark(p, 2);
+            if (dbg_on && lt == 0 && cb == 0) dbg_mark(p, 2);
             // (descriptor start-address fields are 14 bits of (address >> 4) below the template's other
             //  fields: offsets are ADDED to the template, no carries out of the field at < 256 KB)
             const uint32_t abase = h_lo + ((smem_base + s * halo_bytes) >> 4);
@@ -1307,21 +1328,27 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
           umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
-          if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
+          if (dbg_on && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
         }
       } else
-      for (TileIter it(p, my_n, m_first, m_stop); it.valid(); it.next(p), ++lt) {
-        const TileCoord tc = it.coord(p);
+      {
+      int nk = s_cls[mz].n_taps * cin_blocks / p.kg;
+      for (int m = m_first; m < m_stop; ++m, ++lt) {
+        if (mleft == 0) {
+          ++mz;
+          mleft = p.tiles_h[mz] * p.tiles_w[mz] * p.n_img;
+          nk = s_cls[mz].n_taps * cin_blocks / p.kg;
+        }
+        --mleft;
         const int buf = lt & ((1 << nl) - 1);
         const uint32_t acc = tmem + buf * acc_cols;
         mbar_wait_cluster(smem_u32(&bars.tempty[buf]), ((lt >> nl) & 1) ^ 1u);  // both epilogues drained it
         tc_fence_after();
-        const int nk = s_cls[tc.z].n_taps * cin_blocks / p.kg;
         uint32_t accum = 0;
-        if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
+        if (dbg_on && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt);
         for (int kit = 0; kit < nk; ++kit) {
           if (!ready) mbar_wait(full0 + 8u * s, ph);
-          if (lt == 0 && kit == 0) dbg_mark(p, 2);
+          if (dbg_on && lt == 0 && kit == 0) dbg_mark(p, 2);
           tc_fence_after();
           uint32_t a_lo = d_lo | ((smem_base + s * stage_bytes) >> 4);
           uint32_t b_lo = a_lo + (b_off >> 4);
@@ -1351,7 +1378,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           ready = mbar_try_wait(full0 + 8u * s, ph);   // poll the next stage while the MMAs above execute
         }
         umma_commit_pair(smem_u32(&bars.tfull[buf]), 3);
-        if (lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
+        if (dbg_on && lt < kDbgTiles) dbg_mark(p, 8 + 4 * lt + 1);
+      }
       }
     }
   } else {
