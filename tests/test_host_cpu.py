@@ -231,3 +231,31 @@ def test_fused_optimizers_refuse_cpu_parameters():
             opt.step()
     with pytest.raises(ValueError):
         B200Optim.FusedSGD([p], lr=0.1, nesterov=True)
+
+def test_tuned_tile_table_is_well_formed():
+    """dasemanticsegmentationaml_b200/tuned_tiles.json: every entry parses back into a launch the C launcher accepts by
+    construction (the GPU suite, tests/test_tuned_gpu.py, then checks each one numerically)."""
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dasemanticsegmentationaml_b200",
+                        "tuned_tiles.json")
+    table = json.load(open(path))
+    assert len(table) >= 100
+    for key, word in table.items():
+        assert isinstance(word, int) and 0 < word < (1 << 31), key
+        if key.startswith("conv "):
+            m = re.match(r"conv (\d+) (\d+) (\d+) c(\d+) r(\d+) (\S+)( f32)?( st)?( mk)?$", key)
+            assert m, key
+            rows, bn = int(m.group(5)), word & 0xFFF
+            assert bn in (16, 32, 64, 128, 256) and rows % bn == 0, (key, bn)
+            pair, persistent, halo = (word >> 22) & 1, (word >> 20) & 1, (word >> 23) & 1
+            assert not (pair and persistent), key
+            assert not halo or pair, key                       # halo rings exist in the CTA-pair kernel only
+            if pair:
+                assert bn >= 32, key
+            assert not ((word >> 27) & 1 and (word >> 28) & 1), key   # register stores XOR forced TMA stores
+            assert not (m.group(7) and (word >> 28) & 1), key          # fp32 outputs never leave through TMA stores
+        else:
+            m = re.match(r"wgrad (\d+) (\d+) (\d+) co(\d+) ci(\d+) (\d+)x(\d+)s(\d+)$", key)
+            assert m, key
+            assert (word & 0xFFF) in (64, 128, 192, 256), key
+            assert 0 <= ((word >> 12) & 0xF) <= 8 and ((word >> 28) & 3) in (0, 1, 2), key
