@@ -1532,28 +1532,41 @@ wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_consta
     mbar_wait_warp(smem_u32(&bars.accum), 0, lane);
     tc_fence_after();
     const int rs = p.tap_rs[tap];
-    for (int c = 0; c < p.BNW; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, r);
-      tmem_ld_wait();
-      if (co < p.Cout) {
-        if (p.scratch != nullptr) {
-          if (ci0 + c < p.ci_pad) {
-            float* dst = p.scratch + ((size_t)rs * p.Cout + co) * p.ci_pad + ci0 + c;
+    // 32 accumulator columns per tcgen05.ld, the next 32 in flight while this batch's reductions are issued (BNW is
+    // a multiple of 64: two register sets alternate with static indices).  The epilogue runs once per CTA, but a
+    // split-K launch is hundreds of short CTAs: one load + wait per 16 columns was 1-5 us at the end of each.
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16);
+    auto emit32 = [&](const uint32_t (&r)[32], int c) {
+      if (co >= p.Cout) return;
+      if (p.scratch != nullptr) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (ci0 + c + 16 * h < p.ci_pad) {
+            float* dst = p.scratch + ((size_t)rs * p.Cout + co) * p.ci_pad + ci0 + c + 16 * h;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              red_add_v4(dst + 4 * k, __uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]),
-                         __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ci = ci0 + c + j;
-            if (ci < p.Cin)
-              atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.RS + rs, __uint_as_float(r[j]));
+              red_add_v4(dst + 4 * k, __uint_as_float(r[16 * h + 4 * k]), __uint_as_float(r[16 * h + 4 * k + 1]),
+                         __uint_as_float(r[16 * h + 4 * k + 2]), __uint_as_float(r[16 * h + 4 * k + 3]));
           }
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int ci = ci0 + c + j;
+          if (ci < p.Cin)
+            atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * p.RS + rs, __uint_as_float(r[j]));
+        }
       }
+    };
+    uint32_t ra[32], rb[32];
+    tmem_ld32(tbase, ra);
+    for (int c = 0; c < p.BNW; c += 64) {
+      tmem_ld_wait32(ra);
+      tmem_ld32(tbase + c + 32, rb);
+      emit32(ra, c);
+      tmem_ld_wait32(rb);
+      if (c + 64 < p.BNW) tmem_ld32(tbase + c + 64, ra);
+      emit32(rb, c + 32);
     }
   }
 
