@@ -2393,7 +2393,9 @@ int b200_conv_igemm(const void* in, int in_ld, int in_coff, int in_C, int N, int
         out_ld % 8 == 0 && out_coff % 8 == 0) {
       const int box_w = p.tw < 32 ? p.tw : 32, box_h = 32 / box_w;
       p.tma_out = 1;
-      for (int z = 0; z < n_classes; ++z) {
+      for (int z = 0; z < n_classes; ++z)
+        if (class_Ho[z] < 1 || class_Wo[z] < 1) p.tma_out = 0;   // an empty class has no tensor map: register stores
+      for (int z = 0; z < n_classes && p.tma_out; ++z) {
         rc = make_out_map(&om.m[z], out, out_coff, filt_rows, out_ld, N, Hout, Wout, class_Ho[z], class_Wo[z], class_oa[z],
                           class_ob[z], out_stride, box_w, box_h);
         if (rc) return rc;
